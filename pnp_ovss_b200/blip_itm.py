@@ -1,0 +1,270 @@
+"""Random-init stand-in for the patched BLIP ITM-large model (BITM:19-314, MED, VIT) with the reference's
+capture protocol, whose block-8 cross-attention softmax is the fused CUDA kernel (a).
+
+The checkpoint (model_large_retrieval_flickr.pth) and LAVIS are not available offline, so weights are
+normal(0, 0.02) like MED:727-737 / VIT:261-268 and the architecture is restated from the literals in the
+reference: ViT-L/16 (width 1024, depth 24, 16 heads, VIT:511-523) and BERT-base with a cross-attention in every
+layer (hidden 768, 12 layers, 12 heads, intermediate 3072, encoder_width 1024), ITM head Linear(768, 2).
+All GEMMs are plain torch dense contractions (nn.Linear / matmul / SDPA), as north_star prescribes; only the
+cross-attention softmax + capture + GradCAM of the selected block is custom.
+
+Two ways to get GradCAM (both end in pnp_xattn_softmax_bwd_gradcam):
+  * trimmed (default): weights frozen, ViT and BERT layers below the block run under no_grad, the loss is
+    differentiated w.r.t. the block's attention probabilities only;
+  * reference-style (`full_backward=True`): everything requires grad and loss.backward() runs through the whole
+    model like BITM:399-404; the autograd.Function's backward emits dscores and the GradCAM in one pass."""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class GradcamCapture:
+    """Side channel of FusedXattnSoftmax: which head to capture and where the results go."""
+
+    def __init__(self, head, token_mask):
+        self.head = int(head)
+        self.token_mask = token_mask  # int64 [B, >=T] (the max_length=500 padded attention_mask, BITM:415-416)
+        self.probs = None             # [B,h,T,K]  == get_attention_map()
+        self.dprobs = None            # [B,h,T,K]  == get_attn_gradients()
+        self.gradcam = None           # [B,T-1,K-1]
+
+
+class FusedXattnSoftmax(torch.autograd.Function):
+    """probs = softmax(scores*scale + key_mask); backward = softmax backward fused with the GradCAM of one head."""
+
+    @staticmethod
+    def forward(ctx, scores, key_mask, scale, capture):
+        probs = ops.softmax_fwd(scores.contiguous(), key_mask, scale)
+        ctx.save_for_backward(probs)
+        ctx.scale = scale
+        ctx.capture = capture
+        if capture is not None:
+            capture.probs = probs
+        return probs
+
+    @staticmethod
+    def backward(ctx, dprobs):
+        (probs,) = ctx.saved_tensors
+        cap = ctx.capture
+        dprobs = dprobs.contiguous()
+        dscores, cam = ops.softmax_bwd_gradcam(probs, dprobs, cap.token_mask if cap is not None else None,
+                                               cap.head if cap is not None else 0, ctx.scale, need_dscores=True,
+                                               need_gradcam=cap is not None)
+        if cap is not None:
+            cap.dprobs = dprobs
+            cap.gradcam = cam
+        return dscores, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------- ViT-L/16
+class _VitBlock(nn.Module):
+    def __init__(self, dim, heads, mlp_ratio=4.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.fc1 = nn.Linear(dim, int(dim * mlp_ratio))
+        self.fc2 = nn.Linear(int(dim * mlp_ratio), dim)
+        self.heads = heads
+
+    def forward(self, x):
+        B, L, D = x.shape
+        qkv = self.qkv(self.norm1(x)).view(B, L, 3, self.heads, D // self.heads).permute(2, 0, 3, 1, 4)
+        a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
+        x = x + self.proj(a.transpose(1, 2).reshape(B, L, D))
+        return x + self.fc2(F.gelu(self.fc1(self.norm2(x))))
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, img_size=336, patch=16, dim=1024, depth=24, heads=16):
+        super().__init__()
+        self.patch_embed = nn.Conv2d(3, dim, patch, patch)
+        n = (img_size // patch) ** 2
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, n + 1, dim))
+        self.blocks = nn.ModuleList([_VitBlock(dim, heads) for _ in range(depth)])
+        self.norm = nn.LayerNorm(dim, eps=1e-6)
+
+    def forward(self, x):
+        x = self.patch_embed(x).flatten(2).transpose(1, 2)
+        x = torch.cat([self.cls_token.expand(x.shape[0], -1, -1), x], 1) + self.pos_embed
+        for blk in self.blocks:
+            x = blk(x)
+        return self.norm(x)
+
+
+# ------------------------------------------------------------------------------------------------- BERT with cross-attention
+class CrossAttentionSelf(nn.Module):
+    """BertSelfAttention(is_cross_attention=True), MED:126-311, with the capture protocol of MED:164-180."""
+
+    def __init__(self, hidden, heads, enc_width):
+        super().__init__()
+        self.query = nn.Linear(hidden, hidden)
+        self.key = nn.Linear(enc_width, hidden)
+        self.value = nn.Linear(enc_width, hidden)
+        self.heads = heads
+        self.save_attention = False
+        self.capture = None          # GradcamCapture while save_attention is on
+        self.detach_probs = False    # trimmed mode: probs become the leaf the loss is differentiated against
+
+    def get_attention_map(self):
+        return self.capture.probs
+
+    def get_attn_gradients(self):
+        return self.capture.dprobs
+
+    def _split(self, x):
+        B, L, D = x.shape
+        return x.view(B, L, self.heads, D // self.heads).permute(0, 2, 1, 3)
+
+    def forward(self, hidden, enc, enc_mask=None):
+        q, k, v = self._split(self.query(hidden)), self._split(self.key(enc)), self._split(self.value(enc))
+        scores = torch.matmul(q, k.transpose(-1, -2))                       # MED:228
+        scale = 1.0 / math.sqrt(q.shape[-1])                                 # MED:267
+        if self.save_attention:
+            probs = FusedXattnSoftmax.apply(scores, enc_mask, scale, self.capture)   # MED:269-283 fused
+            if self.detach_probs:
+                probs = probs.detach().requires_grad_(True)
+                self.capture.probs = probs
+        else:
+            s = scores * scale
+            if enc_mask is not None:
+                s = s + enc_mask[:, None, None, :]
+            probs = torch.softmax(s, -1)
+        ctx = torch.matmul(probs, v)                                         # MED:300
+        B, h, T, d = ctx.shape
+        return ctx.permute(0, 2, 1, 3).reshape(B, T, h * d)
+
+
+class _BertLayer(nn.Module):
+    def __init__(self, hidden, heads, inter, enc_width, eps=1e-12):
+        super().__init__()
+        self.heads = heads
+        self.q, self.k, self.v = nn.Linear(hidden, hidden), nn.Linear(hidden, hidden), nn.Linear(hidden, hidden)
+        self.attn_out = nn.Linear(hidden, hidden)
+        self.attn_ln = nn.LayerNorm(hidden, eps=eps)
+        self.crossattention = nn.Module()
+        self.crossattention.self = CrossAttentionSelf(hidden, heads, enc_width)
+        self.cross_out = nn.Linear(hidden, hidden)
+        self.cross_ln = nn.LayerNorm(hidden, eps=eps)
+        self.inter = nn.Linear(hidden, inter)
+        self.out = nn.Linear(inter, hidden)
+        self.out_ln = nn.LayerNorm(hidden, eps=eps)
+
+    def self_attention(self, x, add_mask):
+        B, T, D = x.shape
+        sp = lambda t: t.view(B, T, self.heads, D // self.heads).permute(0, 2, 1, 3)
+        a = F.scaled_dot_product_attention(sp(self.q(x)), sp(self.k(x)), sp(self.v(x)), attn_mask=add_mask)
+        return self.attn_ln(self.attn_out(a.permute(0, 2, 1, 3).reshape(B, T, D)) + x)
+
+    def cross_and_ffn(self, x, enc):
+        x = self.cross_ln(self.cross_out(self.crossattention.self(x, enc)) + x)
+        return self.out_ln(self.out(F.gelu(self.inter(x))) + x)
+
+
+class BlipITM(nn.Module):
+    def __init__(self, img_size=336, tokenizer=None, vocab=30524, hidden=768, layers=12, heads=12, inter=3072,
+                 vit_dim=1024, vit_depth=24, vit_heads=16, max_pos=512):
+        super().__init__()
+        self.tokenizer = tokenizer
+        self.patch_num = img_size // 16
+        self.visual_encoder = VisionTransformer(img_size, 16, vit_dim, vit_depth, vit_heads)
+        self.word_emb = nn.Embedding(vocab, hidden)
+        self.pos_emb = nn.Embedding(max_pos, hidden)
+        self.emb_ln = nn.LayerNorm(hidden, eps=1e-12)
+        self.layer = nn.ModuleList([_BertLayer(hidden, heads, inter, vit_dim) for _ in range(layers)])
+        self.itm_head = nn.Linear(hidden, 2)
+        self.apply(self._init)
+        nn.init.normal_(self.visual_encoder.pos_embed, std=0.02)
+        nn.init.normal_(self.visual_encoder.cls_token, std=0.02)
+        self.gemm_precision = "fp32"
+
+    @staticmethod
+    def _init(m):
+        if isinstance(m, (nn.Linear, nn.Embedding, nn.Conv2d)):
+            nn.init.normal_(m.weight, mean=0.0, std=0.02)
+            if getattr(m, "bias", None) is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.ones_(m.weight)
+            nn.init.zeros_(m.bias)
+
+    # ---- pieces -----------------------------------------------------------------------------------
+    def _tokenize(self, text_input, device):
+        text = self.tokenizer(text_input, padding="longest", truncation=True, max_length=500, return_tensors="pt")  # BITM:230-236
+        ids = text.input_ids.to(device).clone()
+        ids[:, 0] = self.tokenizer.enc_token_id  # BITM:238-239
+        return ids, text.attention_mask.to(device)
+
+    def _embed(self, ids):
+        pos = torch.arange(ids.shape[1], device=ids.device)
+        return self.emb_ln(self.word_emb(ids) + self.pos_emb(pos)[None])
+
+    def _vit(self, imgs):
+        if self.gemm_precision == "bf16":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return self.visual_encoder(imgs).float()
+        return self.visual_encoder(imgs)
+
+    def forward(self, visual_input, text_input):
+        """ITM logits [B,2] (BITM:217-249, match_head='itm')."""
+        ids, att = self._tokenize(text_input, visual_input.device)
+        enc = self._vit(visual_input)
+        add_mask = ((1.0 - att.float()) * -10000.0)[:, None, None, :]
+        x = self._embed(ids)
+        for lyr in self.layer:
+            x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc)
+        return self.itm_head(x[:, 0])
+
+    # ---- GradCAM of one (block, head) ----------------------------------------------------------------
+    def gradcam(self, visual_input, text_input, tokenized_text, layer=7, head=9, full_backward=False):
+        """Returns (gradcam [B,T-1,P,P], itm_logits [B,2]) for block `layer`, head `head` (BITM:386-457)."""
+        dev = visual_input.device
+        ids, att = self._tokenize(text_input, dev)
+        B, T = ids.shape
+        token_mask = tokenized_text.attention_mask.to(dev)
+        if token_mask.dtype != torch.int64:
+            token_mask = token_mask.long()
+        token_mask = token_mask.contiguous()
+        cap = GradcamCapture(head, token_mask)
+        xattn = self.layer[layer].crossattention.self
+        xattn.save_attention, xattn.capture, xattn.detach_probs = True, cap, not full_backward
+        add_mask = ((1.0 - att.float()) * -10000.0)[:, None, None, :]
+        try:
+            if full_backward:
+                with torch.enable_grad():
+                    enc = self._vit(visual_input)
+                    x = self._embed(ids)
+                    for lyr in self.layer:
+                        x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc)
+                    out = self.itm_head(x[:, 0])
+                    loss = out[:, 1].sum()       # BITM:399
+                    self.zero_grad()
+                    loss.backward()              # BITM:404; FusedXattnSoftmax.backward fills cap.gradcam
+                cam = cap.gradcam
+            else:
+                with torch.no_grad():
+                    enc = self._vit(visual_input)
+                    x = self._embed(ids)
+                    for lyr in self.layer[:layer]:
+                        x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc)
+                    x = self.layer[layer].self_attention(x, add_mask)
+                with torch.enable_grad():
+                    x = self.layer[layer].cross_and_ffn(x, enc)   # probs become a leaf inside (detach_probs)
+                    for lyr in self.layer[layer + 1:]:
+                        x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc)
+                    out = self.itm_head(x[:, 0])
+                    loss = out[:, 1].sum()
+                    (dprobs,) = torch.autograd.grad(loss, cap.probs)
+                cap.dprobs = dprobs
+                _, cam = ops.softmax_bwd_gradcam(cap.probs.detach(), dprobs.contiguous(), token_mask, head,
+                                                 1.0 / math.sqrt(64), need_dscores=False, need_gradcam=True)
+        finally:
+            xattn.save_attention, xattn.capture, xattn.detach_probs = False, None, False
+        P = self.patch_num
+        return cam.view(B, T - 1, P, P), out.detach()

@@ -1,0 +1,159 @@
+// confusion.cu -- (f) argmax over channels, relabel LUT, mIoU confusion-matrix histogram.
+// Replaces DRV:387 / DRV:1073 (argmax), DRV:390-399 / DRV:468-480 (relabel), DRV:1106-1112 (_fast_hist).
+// HBM-bound: argmax streams C*N floats once with 128-bit loads; the histogram streams labels + gt once and
+// keeps its bins in shared memory, fed by warp-aggregated atomics (one atomic per distinct bin per warp).
+#include "common.cuh"
+
+namespace pnp {
+
+// ------------------------------------------------------------------ argmax over channels, 4 pixels/thread
+// first maximum wins; NaN counts as the maximum and the first NaN wins (numpy.argmax / torch.argmax).
+__device__ __forceinline__ void argmax_step(float v, int c, float &best, int &bi) {
+    if (!(best != best) && (v > best || v != v)) {
+        best = v;
+        bi = c;
+    }
+}
+
+__global__ void __launch_bounds__(256) argmax_channels_vec4(const float *__restrict__ maps, int32_t *__restrict__ labels,
+                                                            int C, int N4, long long total4) {
+    // maps [B,C,N], N = 4*N4; one thread owns 4 consecutive pixels of one image
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+        long long b = i / N4;
+        int q = (int)(i - b * N4);
+        const float *base = maps + (b * C) * (long long)N4 * 4 + (long long)q * 4;
+        float4 best = ldg_stream4(base);
+        int4 bi = make_int4(0, 0, 0, 0);
+        for (int c = 1; c < C; ++c) {
+            float4 v = ldg_stream4(base + (long long)c * N4 * 4);
+            argmax_step(v.x, c, best.x, bi.x);
+            argmax_step(v.y, c, best.y, bi.y);
+            argmax_step(v.z, c, best.z, bi.z);
+            argmax_step(v.w, c, best.w, bi.w);
+        }
+        *reinterpret_cast<int4 *>(labels + i * 4) = bi;
+    }
+}
+
+__global__ void __launch_bounds__(256) argmax_channels_scalar(const float *__restrict__ maps, int32_t *__restrict__ labels,
+                                                              int C, int N, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long b = i / N;
+        int p = (int)(i - b * N);
+        const float *base = maps + (b * C) * (long long)N + p;
+        float best = base[0];
+        int bi = 0;
+        for (int c = 1; c < C; ++c) argmax_step(base[(long long)c * N], c, best, bi);
+        labels[i] = bi;
+    }
+}
+
+// ------------------------------------------------------------------ confusion matrix
+// Warp-aggregated increment: lanes holding the same bin elect a leader which adds the group's size.
+template <typename CounterT>
+__device__ __forceinline__ void warp_aggregated_inc(CounterT *bins, int bin, bool valid) {
+    unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    unsigned peers = __match_any_sync(active, bin);
+    int leader = __ffs(peers) - 1;
+    if ((int)(threadIdx.x & 31) == leader) atomicAdd(&bins[bin], (CounterT)__popc(peers));
+}
+
+template <bool kSmemBins>
+__global__ void __launch_bounds__(512) confusion_kernel(const int32_t *__restrict__ labels, const float *__restrict__ gt,
+                                                        const int32_t *__restrict__ lut, int lut_stride,
+                                                        float *__restrict__ pred_out, unsigned long long *__restrict__ hist,
+                                                        int32_t *__restrict__ bad_count, int N, long long total,
+                                                        int n_class) {
+    extern __shared__ unsigned int s_bins[];
+    const int n_bins = n_class * n_class;
+    if (kSmemBins) {
+        for (int i = threadIdx.x; i < n_bins; i += blockDim.x) s_bins[i] = 0u;
+        __syncthreads();
+    }
+    int bad = 0;
+    // every lane of a warp runs the same number of iterations (match_any needs convergent warps)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long rounds = (total + stride - 1) / stride;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (long long r = 0; r < rounds; ++r, i += stride) {
+        bool in_range = i < total;
+        bool valid = false;
+        int bin = 0;
+        if (in_range) {
+            int lab = labels[i];
+            long long b = i / N;
+            int pred = lut ? lut[b * lut_stride + lab] : lab;
+            if (pred_out) pred_out[i] = (float)pred;
+            float g = gt[i];
+            if (g >= 0.0f && g < (float)n_class) {  // DRV:1107 mask, evaluated on the float32 ground truth
+                if (pred >= 0 && pred < n_class) {
+                    valid = true;
+                    bin = n_class * (int)g + pred;  // .astype(int) truncates toward zero
+                } else {
+                    ++bad;
+                }
+            }
+        }
+        if (kSmemBins)
+            warp_aggregated_inc<unsigned int>(s_bins, bin, valid);
+        else
+            warp_aggregated_inc<unsigned long long>(hist, bin, valid);
+    }
+    if (bad_count && bad) atomicAdd(bad_count, bad);
+    if (kSmemBins) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < n_bins; k += blockDim.x) {
+            unsigned int v = s_bins[k];
+            if (v) atomicAdd(&hist[k], (unsigned long long)v);
+        }
+    }
+}
+
+}  // namespace pnp
+
+using namespace pnp;
+
+extern "C" int pnp_argmax_channels(const float *maps, int32_t *labels, int B, int C, int N, pnp_stream_t stream) {
+    if (!maps || !labels || B < 0 || C < 1 || N < 1) return PNP_ERR_INVALID_ARGUMENT;
+    if (B == 0) return PNP_OK;
+    cudaStream_t st = as_stream(stream);
+    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(maps) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(labels) & 15) == 0);
+    if (vec) {
+        long long total4 = (long long)B * (N / 4);
+        int grid = (int)min((long long)kNumSMs * 16, (total4 + 255) / 256);
+        argmax_channels_vec4<<<grid, 256, 0, st>>>(maps, labels, C, N / 4, total4);
+    } else {
+        long long total = (long long)B * N;
+        int grid = (int)min((long long)kNumSMs * 16, (total + 255) / 256);
+        argmax_channels_scalar<<<grid, 256, 0, st>>>(maps, labels, C, N, total);
+    }
+    return launch_status();
+}
+
+extern "C" int pnp_confusion_accumulate(const int32_t *labels, const float *gt, const int32_t *lut, int lut_stride,
+                                        float *pred_out, int64_t *hist, int32_t *bad_count, int B, int N, int n_class,
+                                        pnp_stream_t stream) {
+    if (!labels || !gt || !hist || B < 0 || N < 1 || n_class < 1 || n_class > 30000) return PNP_ERR_INVALID_ARGUMENT;
+    if (B == 0) return PNP_OK;
+    cudaStream_t st = as_stream(stream);
+    long long total = (long long)B * N;
+    size_t smem = (size_t)n_class * n_class * sizeof(unsigned int);
+    int grid = (int)min((long long)kNumSMs * 2, (total + 511) / 512);
+    if (smem <= 200 * 1024) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(confusion_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_err(e);
+            grid = (int)min((long long)kNumSMs, (total + 511) / 512);
+        }
+        confusion_kernel<true><<<grid, 512, smem, st>>>(labels, gt, lut, lut_stride, pred_out,
+                                                         reinterpret_cast<unsigned long long *>(hist), bad_count, N, total,
+                                                         n_class);
+    } else {
+        confusion_kernel<false><<<grid, 512, 0, st>>>(labels, gt, lut, lut_stride, pred_out,
+                                                      reinterpret_cast<unsigned long long *>(hist), bad_count, N, total,
+                                                      n_class);
+    }
+    return launch_status();
+}

@@ -1,0 +1,424 @@
+// crf.cu -- (e) part 2: filtering on the permutohedral lattice and dense-CRF mean-field inference.
+// Replaces pydensecrf's DenseCRF2D.inference (DRV:1071) and unary_from_softmax (DRV:1057-1063).
+//
+// Data layout: per-pixel / per-vertex channel vectors are contiguous ([B,N,Cp], [rows,Cp], Cp = 4*ceil(C/4)), so
+// every gather moves whole rows with 128-bit accesses; one thread owns one float4 chunk of one row.
+//   splat   gather over the vertex's CSR row (pixels in ascending order): values[v] = sum w * (norm * Q[pix])
+//   blur    values'[v] = values[v] + 0.5 (values[n1] + values[n2]) along each of the d+1 axes (ping-pong)
+//   update  per pixel: slice every kernel's lattice, add the weighted messages to -U, softmax over channels,
+//           write Q (and, on the last iteration, the argmax label) -- one pass over Q/U per iteration.
+// Sums are written with explicit __fmul_rn/__fadd_rn in the reference's order (it is compiled without FMA
+// contraction), so the filter is bit-identical to the sequential CPU restatement; only expf/logf differ by ulps.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "lattice.cuh"
+
+namespace pnp {
+
+__device__ __forceinline__ float4 f4_mul(float4 a, float s) {
+    return make_float4(__fmul_rn(a.x, s), __fmul_rn(a.y, s), __fmul_rn(a.z, s), __fmul_rn(a.w, s));
+}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
+    return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+}
+
+// rows of a value buffer that one image (shared lattice) or the whole batch (batched lattice) occupies
+__host__ __device__ __forceinline__ long long value_rows(const LatticeView &L, int B) {
+    return L.shared ? (long long)B * (L.M + 1) : (long long)L.M + 1;
+}
+
+// ------------------------------------------------------------------------------------------ splat
+// grid.y = image for shared lattices (1 otherwise)
+__global__ void __launch_bounds__(256) splat_kernel(LatticeView L, const float *__restrict__ x, float *__restrict__ values, int Cp,
+                                                    int normalized) {
+    const int nch = Cp >> 2;
+    const int b = blockIdx.y;
+    const float *xb = L.shared ? x + (long long)b * L.N * Cp : x;
+    float *vb = L.shared ? values + (long long)b * (L.M + 1) * Cp : values;
+    const long long total = (long long)(L.M + 1) * nch;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx / nch), ch = (int)(idx - (long long)v * nch);
+        if (v == L.M) {  // sentinel row 0 stays zero
+            *reinterpret_cast<float4 *>(vb + 4 * ch) = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int end = L.row_ptr[v + 1];
+        for (int k = L.row_ptr[v]; k < end; ++k) {
+            const int lp = L.csr_pix[k];
+            const float w = L.csr_w[k];
+            float4 xv = *reinterpret_cast<const float4 *>(xb + (long long)lp * Cp + 4 * ch);
+            if (normalized) xv = f4_mul(xv, L.norm[lp]);
+            acc = f4_add(acc, f4_mul(xv, w));
+        }
+        *reinterpret_cast<float4 *>(vb + (long long)(v + 1) * Cp + 4 * ch) = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ blur along one axis
+__global__ void __launch_bounds__(256) blur_axis_kernel(LatticeView L, const float *__restrict__ old_v, float *__restrict__ new_v, int axis,
+                                                        int Cp) {
+    const int nch = Cp >> 2;
+    const int b = blockIdx.y;
+    const long long img_off = L.shared ? (long long)b * (L.M + 1) * Cp : 0;
+    const float *ob = old_v + img_off;
+    float *nb = new_v + img_off;
+    const int2 *nbr = reinterpret_cast<const int2 *>(L.nbr) + (size_t)axis * L.vertex_stride;
+    const long long total = (long long)(L.M + 1) * nch;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx / nch), ch = (int)(idx - (long long)v * nch);
+        if (v == L.M) {
+            *reinterpret_cast<float4 *>(nb + 4 * ch) = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const int2 n = nbr[v];
+        const float4 c = *reinterpret_cast<const float4 *>(ob + (long long)(v + 1) * Cp + 4 * ch);
+        const float4 a1 = *reinterpret_cast<const float4 *>(ob + (long long)n.x * Cp + 4 * ch);
+        const float4 a2 = *reinterpret_cast<const float4 *>(ob + (long long)n.y * Cp + 4 * ch);
+        // new = old + 0.5f * (n1 + n2)
+        *reinterpret_cast<float4 *>(nb + (long long)(v + 1) * Cp + 4 * ch) = f4_add(c, f4_mul(f4_add(a1, a2), 0.5f));
+    }
+}
+
+// slice one lattice at (pixel gp of image b, chunk ch): sum_j (w_j * values[o_j]) * alpha, optionally * norm
+__device__ __forceinline__ float4 slice_pixel(const LatticeView &L, const float *__restrict__ values, int b, int pix, long long gp,
+                                              int ch, int Cp, bool normalized) {
+    const long long lp = L.shared ? pix : gp;
+    const float *vb = L.shared ? values + (long long)b * (L.M + 1) * Cp : values;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < L.Dp1; ++j) {
+        const int o = L.offset[lp * L.Dp1 + j] + 1;
+        const float w = L.bary[lp * L.Dp1 + j];
+        const float4 v = *reinterpret_cast<const float4 *>(vb + (long long)o * Cp + 4 * ch);
+        out = f4_add(out, f4_mul(f4_mul(v, w), L.alpha));
+    }
+    if (normalized) out = f4_mul(out, L.norm[lp]);
+    return out;
+}
+
+__global__ void __launch_bounds__(256) slice_kernel(LatticeView L, const float *__restrict__ values, float *__restrict__ y, int B, int Cp,
+                                                    int normalized) {
+    const int nch = Cp >> 2;
+    const long long total = (long long)B * L.N * nch;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long gp = idx / nch;
+        const int ch = (int)(idx - gp * nch);
+        const int b = (int)(gp / L.N), pix = (int)(gp - (long long)b * L.N);
+        *reinterpret_cast<float4 *>(y + gp * Cp + 4 * ch) = slice_pixel(L, values, b, pix, gp, ch, Cp, normalized != 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ mean-field update
+constexpr int kMaxKernels = 4;
+struct MeanFieldParams {
+    LatticeView lat[kMaxKernels];
+    const float *values[kMaxKernels];
+    float weight[kMaxKernels];
+    int n_kernels;
+};
+
+__device__ __forceinline__ void argmax_first(float v, int c, float &best, int &bi) {
+    if (!(best != best) && (v > best || v != v)) { best = v; bi = c; }
+}
+
+// Q = softmax_c(-U + sum_k w_k * norm_k . slice_k(values_k)); 256 threads = TP pixels x nch chunks
+template <bool kLabels>
+__global__ void __launch_bounds__(256) meanfield_update_kernel(MeanFieldParams P, const float *__restrict__ unary, float *__restrict__ Q,
+                                                               int32_t *__restrict__ labels, int B, int N, int C, int Cp) {
+    __shared__ float s_a[256];
+    __shared__ float s_b[256];
+    __shared__ int s_i[256];
+    const int nch = Cp >> 2;
+    const int TP = 256 / nch;
+    const int pl = threadIdx.x / nch, ch = threadIdx.x - pl * nch;
+    const long long n_pix = (long long)B * N;
+    const long long n_tiles = (n_pix + TP - 1) / TP;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long gp = tile * TP + pl;
+        const bool active = pl < TP && gp < n_pix;
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        float mx = -INFINITY;
+        if (active) {
+            const int b = (int)(gp / N), pix = (int)(gp - (long long)b * N);
+            const float4 u = *reinterpret_cast<const float4 *>(unary + gp * Cp + 4 * ch);
+            float4 acc = make_float4(-u.x, -u.y, -u.z, -u.w);
+            for (int k = 0; k < P.n_kernels; ++k) {
+                float4 s = slice_pixel(P.lat[k], P.values[k], b, pix, gp, ch, Cp, true);
+                acc = f4_add(acc, f4_mul(s, P.weight[k]));  // tmp1 -= (-w * K Q)
+            }
+            t[0] = acc.x; t[1] = acc.y; t[2] = acc.z; t[3] = acc.w;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (4 * ch + i < C) mx = fmaxf(mx, t[i]);
+        }
+        s_a[threadIdx.x] = mx;
+        __syncthreads();
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        float part = 0.f;
+        if (active) {
+            float m = s_a[pl * nch];
+            for (int k = 1; k < nch; ++k) m = fmaxf(m, s_a[pl * nch + k]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (4 * ch + i < C) {
+                    e[i] = expf(t[i] - m);
+                    part += e[i];
+                }
+            }
+        }
+        s_b[threadIdx.x] = part;
+        __syncthreads();
+        float q[4] = {0.f, 0.f, 0.f, 0.f};
+        if (active) {
+            float sum = 0.f;
+            for (int k = 0; k < nch; ++k) sum += s_b[pl * nch + k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (4 * ch + i < C) q[i] = __fdiv_rn(e[i], sum);
+            *reinterpret_cast<float4 *>(Q + gp * Cp + 4 * ch) = make_float4(q[0], q[1], q[2], q[3]);
+        }
+        if (kLabels) {
+            __syncthreads();  // s_a is reused
+            float best = q[0];
+            int bi = 4 * ch;
+#pragma unroll
+            for (int i = 1; i < 4; ++i)
+                if (4 * ch + i < C) argmax_first(q[i], 4 * ch + i, best, bi);
+            s_a[threadIdx.x] = best;
+            s_i[threadIdx.x] = bi;
+            __syncthreads();
+            if (active && ch == 0) {
+                for (int k = 1; k < nch; ++k) argmax_first(s_a[pl * nch + k], s_i[pl * nch + k], best, bi);
+                labels[gp] = bi;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ unary + layout helpers
+// one thread per pixel; channel-major reads are coalesced across the warp, pixel-major writes go through smem
+constexpr int kUnaryPix = 128;
+
+__global__ void __launch_bounds__(kUnaryPix) unary_from_maps_kernel(const float *__restrict__ maps, const float *__restrict__ minmax,
+                                                                    float *__restrict__ unary, int C, int Cp, int N) {
+    extern __shared__ float s_tile[];  // [kUnaryPix][Cp+1]
+    const int b = blockIdx.y;
+    const int pitch = Cp + 1;
+    const int p0 = blockIdx.x * kUnaryPix;
+    const int p = p0 + threadIdx.x;
+    const float *mb = maps + (long long)b * C * N;
+    float *row = s_tile + threadIdx.x * pitch;
+    if (p < N) {
+        float mx = -INFINITY;
+        bool has_nan = false;
+        for (int c = 0; c < C; ++c) {
+            float v = mb[(long long)c * N + p];
+            if (minmax) {
+                float mn = minmax[((long long)b * C + c) * 2], hi = minmax[((long long)b * C + c) * 2 + 1];
+                v = __fdiv_rn(__fsub_rn(v, mn), __fsub_rn(hi, mn));  // DRV:1151-1152
+            }
+            row[c] = v;
+            has_nan = has_nan || (v != v);
+            mx = fmaxf(mx, v);
+        }
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) {
+            float e = expf(row[c] - mx);
+            row[c] = e;
+            sum += e;
+        }
+        for (int c = 0; c < C; ++c) {
+            float pr = __fdiv_rn(row[c], sum);             // F.softmax(mask, dim=0), DRV:1057
+            pr = fminf(fmaxf(pr, 1e-5f), 1.0f);            // np.clip(sm, 1e-5, 1.0)
+            float u = -logf(pr);
+            row[c] = has_nan ? __int_as_float(0x7fc00000) : u;  // softmax of a NaN column is NaN everywhere
+        }
+        for (int c = C; c < Cp; ++c) row[c] = 0.f;
+    }
+    __syncthreads();
+    const int n_here = min(kUnaryPix, N - p0);
+    float *ub = unary + ((long long)b * N + p0) * Cp;
+    for (int i = threadIdx.x; i < n_here * Cp; i += blockDim.x) {
+        int pp = i / Cp, c = i - pp * Cp;
+        ub[i] = s_tile[pp * pitch + c];
+    }
+}
+
+__global__ void __launch_bounds__(kUnaryPix) pack_cn_to_nc_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int Cp, int N) {
+    extern __shared__ float s_tile[];
+    const int b = blockIdx.y, pitch = Cp + 1, p0 = blockIdx.x * kUnaryPix, p = p0 + threadIdx.x;
+    if (p < N) {
+        for (int c = 0; c < C; ++c) s_tile[threadIdx.x * pitch + c] = src[((long long)b * C + c) * N + p];
+        for (int c = C; c < Cp; ++c) s_tile[threadIdx.x * pitch + c] = 0.f;
+    }
+    __syncthreads();
+    const int n_here = min(kUnaryPix, N - p0);
+    float *db = dst + ((long long)b * N + p0) * Cp;
+    for (int i = threadIdx.x; i < n_here * Cp; i += blockDim.x) {
+        int pp = i / Cp, c = i - pp * Cp;
+        db[i] = s_tile[pp * pitch + c];
+    }
+}
+
+__global__ void __launch_bounds__(kUnaryPix) unpack_nc_to_cn_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int Cp, int N) {
+    extern __shared__ float s_tile[];
+    const int b = blockIdx.y, pitch = Cp + 1, p0 = blockIdx.x * kUnaryPix, p = p0 + threadIdx.x;
+    const int n_here = min(kUnaryPix, N - p0);
+    const float *sb = src + ((long long)b * N + p0) * Cp;
+    for (int i = threadIdx.x; i < n_here * Cp; i += blockDim.x) {
+        int pp = i / Cp, c = i - pp * Cp;
+        s_tile[pp * pitch + c] = sb[i];
+    }
+    __syncthreads();
+    if (p < N)
+        for (int c = 0; c < C; ++c) dst[((long long)b * C + c) * N + p] = s_tile[threadIdx.x * pitch + c];
+}
+
+// ------------------------------------------------------------------------------------------ host helpers
+static inline int grid_for(long long work_items, int threads) {
+    return (int)std::max<long long>(1, std::min<long long>((work_items + threads - 1) / threads, (long long)kNumSMs * 16));
+}
+
+static bool lattice_ok(const pnp_lattice *lat, int B) {
+    if (!lat || lat->n_vertices < 0 || !lat->offset) return false;
+    if (!lat->shared && lat->n_images != B) return false;
+    return true;
+}
+
+// enqueue splat + (d+1) blurs; returns the buffer holding the blurred values
+static const float *run_splat_blur(const LatticeView &L, const float *x, float *va, float *vb, int B, int Cp, int normalized,
+                                   cudaStream_t st) {
+    const int nch = Cp / 4;
+    const int gy = L.shared ? B : 1;
+    const int gx = std::max(1, grid_for((long long)(L.M + 1) * nch, 256) / (L.shared ? std::min(B, 8) : 1));
+    splat_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, x, va, Cp, normalized);
+    float *src = va, *dst = vb;
+    for (int j = 0; j < L.Dp1; ++j) {
+        blur_axis_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, src, dst, j, Cp);
+        std::swap(src, dst);
+    }
+    return src;
+}
+
+static size_t unary_smem(int Cp) { return (size_t)kUnaryPix * (Cp + 1) * sizeof(float); }
+
+}  // namespace pnp
+
+using namespace pnp;
+
+extern "C" size_t pnp_crf_scratch_bytes(const pnp_lattice *const *lattices, int n_kernels, int B, int Cp) {
+    if (!lattices || n_kernels < 1 || n_kernels > kMaxKernels || B < 1 || Cp < 4 || Cp % 4) return 0;
+    size_t total = 0;
+    for (int k = 0; k < n_kernels; ++k) {
+        if (!lattice_ok(lattices[k], B)) return 0;
+        LatticeView L = make_view(lattices[k]);
+        total += 2 * align_up((size_t)value_rows(L, B) * Cp * sizeof(float), 256);
+    }
+    return total;
+}
+
+extern "C" int pnp_crf_filter(const pnp_lattice *lat, const float *x, float *y, void *scratch, size_t scratch_bytes, int B,
+                              int Cp, int normalized, pnp_stream_t stream) {
+    if (!x || !y || !scratch || B < 1 || Cp < 4 || Cp % 4 || Cp > 1024 || !lattice_ok(lat, B)) return PNP_ERR_INVALID_ARGUMENT;
+    const pnp_lattice *one[1] = {lat};
+    if (scratch_bytes < pnp_crf_scratch_bytes(one, 1, B, Cp)) return PNP_ERR_WORKSPACE;
+    cudaStream_t st = as_stream(stream);
+    LatticeView L = make_view(lat);
+    size_t buf = align_up((size_t)value_rows(L, B) * Cp * sizeof(float), 256);
+    float *va = reinterpret_cast<float *>(scratch);
+    float *vb = reinterpret_cast<float *>(reinterpret_cast<char *>(scratch) + buf);
+    const float *blurred = run_splat_blur(L, x, va, vb, B, Cp, normalized, st);
+    slice_kernel<<<grid_for((long long)B * L.N * (Cp / 4), 256), 256, 0, st>>>(L, blurred, y, B, Cp, normalized);
+    return launch_status();
+}
+
+extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float *weights, int n_kernels,
+                                 const float *unary, float *Q, void *scratch, size_t scratch_bytes, int32_t *labels, int B,
+                                 int C, int Cp, int n_iter, pnp_stream_t stream) {
+    if (!lattices || !weights || !unary || !Q || !scratch || n_kernels < 1 || n_kernels > kMaxKernels || B < 1 || C < 1 ||
+        Cp < C || Cp % 4 || Cp > 1024 || n_iter < 0)
+        return PNP_ERR_INVALID_ARGUMENT;
+    size_t need = pnp_crf_scratch_bytes(lattices, n_kernels, B, Cp);
+    if (need == 0) return PNP_ERR_INVALID_ARGUMENT;
+    if (scratch_bytes < need) return PNP_ERR_WORKSPACE;
+    const int N = lattices[0]->n_pixels;
+    for (int k = 1; k < n_kernels; ++k)
+        if (lattices[k]->n_pixels != N) return PNP_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = as_stream(stream);
+
+    MeanFieldParams P;
+    float *va[kMaxKernels], *vb[kMaxKernels];
+    char *p = reinterpret_cast<char *>(scratch);
+    for (int k = 0; k < kMaxKernels; ++k) {
+        if (k < n_kernels) {
+            P.lat[k] = make_view(lattices[k]);
+            P.weight[k] = weights[k];
+            size_t buf = align_up((size_t)value_rows(P.lat[k], B) * Cp * sizeof(float), 256);
+            va[k] = reinterpret_cast<float *>(p);
+            vb[k] = reinterpret_cast<float *>(p + buf);
+            p += 2 * buf;
+        } else {
+            P.lat[k] = P.lat[0];
+            P.weight[k] = 0.f;
+            va[k] = vb[k] = nullptr;
+        }
+        P.values[k] = nullptr;
+    }
+    const int TP = 256 / (Cp / 4);
+    const long long n_tiles = ((long long)B * N + TP - 1) / TP;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(n_tiles, (long long)kNumSMs * 8));
+
+    // Q0 = softmax(-U)
+    P.n_kernels = 0;
+    if (n_iter == 0 && labels)
+        meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp);
+    else
+        meanfield_update_kernel<false><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp);
+    for (int it = 0; it < n_iter; ++it) {
+        for (int k = 0; k < n_kernels; ++k) P.values[k] = run_splat_blur(P.lat[k], Q, va[k], vb[k], B, Cp, 1, st);
+        P.n_kernels = n_kernels;
+        if (it == n_iter - 1 && labels)
+            meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp);
+        else
+            meanfield_update_kernel<false><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp);
+    }
+    return launch_status();
+}
+
+extern "C" int pnp_crf_unary_from_maps(const float *maps, const float *minmax, float *unary, int B, int C, int N,
+                                       pnp_stream_t stream) {
+    if (!maps || !unary || B < 1 || C < 1 || N < 1 || B > 65535) return PNP_ERR_INVALID_ARGUMENT;
+    const int Cp = (C + 3) / 4 * 4;
+    size_t smem = unary_smem(Cp);
+    if (smem > 200 * 1024) return PNP_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaFuncSetAttribute(unary_from_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_err(e);
+    unary_from_maps_kernel<<<dim3(ceil_div(N, kUnaryPix), B), kUnaryPix, smem, as_stream(stream)>>>(maps, minmax, unary, C, Cp, N);
+    return launch_status();
+}
+
+extern "C" int pnp_crf_pack_cn_to_nc(const float *src_cn, float *dst_nc, int B, int C, int N, pnp_stream_t stream) {
+    if (!src_cn || !dst_nc || B < 1 || C < 1 || N < 1 || B > 65535) return PNP_ERR_INVALID_ARGUMENT;
+    const int Cp = (C + 3) / 4 * 4;
+    size_t smem = unary_smem(Cp);
+    if (smem > 200 * 1024) return PNP_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaFuncSetAttribute(pack_cn_to_nc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_err(e);
+    pack_cn_to_nc_kernel<<<dim3(ceil_div(N, kUnaryPix), B), kUnaryPix, smem, as_stream(stream)>>>(src_cn, dst_nc, C, Cp, N);
+    return launch_status();
+}
+
+extern "C" int pnp_crf_unpack_nc_to_cn(const float *src_nc, float *dst_cn, int B, int C, int N, pnp_stream_t stream) {
+    if (!src_nc || !dst_cn || B < 1 || C < 1 || N < 1 || B > 65535) return PNP_ERR_INVALID_ARGUMENT;
+    const int Cp = (C + 3) / 4 * 4;
+    size_t smem = unary_smem(Cp);
+    if (smem > 200 * 1024) return PNP_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaFuncSetAttribute(unpack_nc_to_cn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_err(e);
+    unpack_nc_to_cn_kernel<<<dim3(ceil_div(N, kUnaryPix), B), kUnaryPix, smem, as_stream(stream)>>>(src_nc, dst_cn, C, Cp, N);
+    return launch_status();
+}

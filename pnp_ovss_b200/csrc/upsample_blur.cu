@@ -1,0 +1,460 @@
+// upsample_blur.cu -- (d) threshold + bilinear upsample (+Scale_0_1) + background, and the Gaussian blur.
+// Replaces DRV:348-380 / DRV:424-455 / DRV:1078-1094 and DRV:1149-1153 (scipy gaussian_filter) + DRV:1005-1011.
+//
+// upsample: the PxP grids are tiny (L1-resident); the kernel is a pure HBM write stream of C'*H*W floats with
+//           128-bit stores -- the algorithmic minimum 4*C'*N bytes per image.
+// blur:     separable, smem-tiled.  Pass V (axis 0) stages a 64-column strip of the map with its reflected halo
+//           in shared memory and register-blocks 16 output rows per thread; pass H (axis 1) stages 32 full rows,
+//           maps lanes to rows (odd pitch -> conflict-free) and register-blocks 16 output columns per thread,
+//           then stores through shared memory so global writes are coalesced 128-bit.  Min/max of each blurred
+//           map is reduced in the same pass (order-preserving uint keys + atomicMin/Max), so the reference's
+//           (y-min)/(max-min) costs 2 scalars per channel in the consumer instead of another pass over HBM.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pnp {
+
+// ============================================================================================ upsample
+constexpr int kMaxP2 = 1024;
+
+// K1: per (b,c): min-max threshold of the PxP map; optional min/max of its upsampled image (for Scale_0_1)
+__global__ void __launch_bounds__(256) threshold_prep_kernel(const float *__restrict__ class_maps, float *__restrict__ masked,
+                                                             float *__restrict__ scale_params, int C, int P, int H, int W,
+                                                             float threshold, int rescale) {
+    __shared__ float s_grid[kMaxP2];
+    __shared__ float s_red[2][8];
+    __shared__ float s_mm[2];
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int PP = P * P;
+    const long long base = ((long long)b * C + c) * PP;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    float mn = INFINITY, mx = -INFINITY;
+    for (int p = threadIdx.x; p < PP; p += blockDim.x) {
+        float v = class_maps[base + p];
+        s_grid[p] = v;
+        mn = nan_min(mn, v);
+        mx = nan_max(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = s_red[0][0], z = s_red[1][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = nan_min(a, s_red[0][w]); z = nan_max(z, s_red[1][w]); }
+        s_mm[0] = a; s_mm[1] = z;
+    }
+    __syncthreads();
+    mn = s_mm[0];
+    const float range = __fsub_rn(s_mm[1], mn);
+    // DRV:425-433: th = (x-min)/(max-min) >= threshold (0/0 -> NaN -> False); pred = x * th
+    for (int p = threadIdx.x; p < PP; p += blockDim.x) {
+        float v = s_grid[p];
+        float nrm = __fdiv_rn(__fsub_rn(v, mn), range);
+        float keep = (nrm >= threshold) ? v : __fmul_rn(v, 0.0f);
+        s_grid[p] = keep;
+        masked[base + p] = keep;
+    }
+    if (!rescale) return;
+    __syncthreads();
+    // min/max of the upsampled image (needed by Scale_0_1, DRV:1078-1094): evaluate, never store
+    const float rh = (H > 1) ? (float)(P - 1) / (float)(H - 1) : 0.f;
+    const float rw = (W > 1) ? (float)(P - 1) / (float)(W - 1) : 0.f;
+    mn = INFINITY; mx = -INFINITY;
+    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
+        int y = i / W, x = i - y * W;
+        float sy = rh * y, sx = rw * x;
+        int y0 = min((int)sy, P - 1), x0 = min((int)sx, P - 1);
+        int y1 = min(y0 + 1, P - 1), x1 = min(x0 + 1, P - 1);
+        float ly = fminf(fmaxf(sy - y0, 0.f), 1.f), lx = fminf(fmaxf(sx - x0, 0.f), 1.f);
+        float hy = 1.f - ly, hx = 1.f - lx;
+        float top = __fadd_rn(__fmul_rn(hx, s_grid[y0 * P + x0]), __fmul_rn(lx, s_grid[y0 * P + x1]));
+        float bot = __fadd_rn(__fmul_rn(hx, s_grid[y1 * P + x0]), __fmul_rn(lx, s_grid[y1 * P + x1]));
+        float v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+        mn = nan_min(mn, v);
+        mx = nan_max(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __syncthreads();
+    if (lane == 0) { s_red[0][warp] = mn; s_red[1][warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = s_red[0][0], z = s_red[1][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { a = nan_min(a, s_red[0][w]); z = nan_max(z, s_red[1][w]); }
+        scale_params[((long long)b * C + c) * 2 + 0] = a;
+        scale_params[((long long)b * C + c) * 2 + 1] = __fsub_rn(z, a);  // max of (x - min)
+    }
+}
+
+// K2: write out[b, bg + c, y, x..x+VEC) for all c, plus the background channel.
+template <int VEC>
+__global__ void __launch_bounds__(256) upsample_write_kernel(const float *__restrict__ masked, const float *__restrict__ scale_params,
+                                                             float *__restrict__ out, int C, int P, int H, int W, int rescale,
+                                                             int with_background) {
+    const int b = blockIdx.y;
+    const int PP = P * P;
+    const int Wq = W / VEC;
+    const long long N = (long long)H * W;
+    const int Cout = C + (with_background ? 1 : 0);
+    const float rh = (H > 1) ? (float)(P - 1) / (float)(H - 1) : 0.f;
+    const float rw = (W > 1) ? (float)(P - 1) / (float)(W - 1) : 0.f;
+    const float *grid0 = masked + (long long)b * C * PP;
+    float *out_b = out + (long long)b * Cout * N;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < H * Wq; q += gridDim.x * blockDim.x) {
+        const int y = q / Wq, xb = (q - y * Wq) * VEC;
+        const float sy = rh * y;
+        const int y0 = min((int)sy, P - 1), y1 = min(y0 + 1, P - 1);
+        const float ly = fminf(fmaxf(sy - y0, 0.f), 1.f), hy = 1.f - ly;
+        int x0[VEC], x1[VEC];
+        float lx[VEC], hx[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            float sx = rw * (xb + v);
+            x0[v] = min((int)sx, P - 1);
+            x1[v] = min(x0[v] + 1, P - 1);
+            lx[v] = fminf(fmaxf(sx - x0[v], 0.f), 1.f);
+            hx[v] = 1.f - lx[v];
+        }
+        float vmax[VEC];
+        bool vnan[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { vmax[v] = -INFINITY; vnan[v] = false; }
+        for (int c = 0; c < C; ++c) {
+            const float *g = grid0 + c * PP;
+            float mn = 0.f, rg = 1.f;
+            if (rescale) { mn = scale_params[((long long)b * C + c) * 2]; rg = scale_params[((long long)b * C + c) * 2 + 1]; }
+            float r[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                float top = __fadd_rn(__fmul_rn(hx[v], __ldg(g + y0 * P + x0[v])), __fmul_rn(lx[v], __ldg(g + y0 * P + x1[v])));
+                float bot = __fadd_rn(__fmul_rn(hx[v], __ldg(g + y1 * P + x0[v])), __fmul_rn(lx[v], __ldg(g + y1 * P + x1[v])));
+                float val = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+                if (rescale) val = __fdiv_rn(__fsub_rn(val, mn), rg);  // Scale_0_1: AA -= min; AA /= max
+                r[v] = val;
+                vnan[v] = vnan[v] || (val != val);
+                vmax[v] = fmaxf(vmax[v], val);
+            }
+            float *dst = out_b + (long long)(c + (with_background ? 1 : 0)) * N + (long long)y * W + xb;
+            if (VEC == 4)
+                stg_stream4(dst, make_float4(r[0], r[1], r[2], r[3]));
+            else
+                dst[0] = r[0];
+        }
+        if (with_background) {  // DRV:446-450: background = (max over classes == 0); torch.max propagates NaN
+            float r[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) r[v] = (!vnan[v] && vmax[v] == 0.f) ? 1.f : 0.f;
+            float *dst = out_b + (long long)y * W + xb;
+            if (VEC == 4)
+                stg_stream4(dst, make_float4(r[0], r[1], r[2], r[3]));
+            else
+                dst[0] = r[0];
+        }
+    }
+}
+
+// ============================================================================================ blur
+__host__ __device__ __forceinline__ int reflect_index(int i, int n) {  // scipy mode='reflect': d c b a | a b c d | d c b a
+    if (n == 1) return 0;
+    int period = 2 * n;
+    i %= period;
+    if (i < 0) i += period;
+    return i < n ? i : period - 1 - i;
+}
+
+constexpr int kTapPad = 16;  // weights are zero-padded so register-blocked loops never branch on the tap count
+
+// weights[j] = exp(-0.5 x^2 / sigma^2) / sum, x = j - lw (float64 like scipy's _gaussian_kernel1d), stored fp32;
+// also resets the per-map min/max keys.
+__global__ void blur_prologue_kernel(float *__restrict__ weights, unsigned *__restrict__ mm_keys, int n_maps, int lw, int n_w_padded,
+                                     double sigma) {
+    __shared__ double s_sum;
+    const int taps = 2 * lw + 1;
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int j = 0; j < taps; ++j) {
+            double x = (double)(j - lw);
+            s += exp(-0.5 / (sigma * sigma) * x * x);
+        }
+        s_sum = s;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_w_padded; j += blockDim.x) {
+        double x = (double)(j - lw);
+        weights[j] = (j < taps) ? (float)(exp(-0.5 / (sigma * sigma) * x * x) / s_sum) : 0.f;
+    }
+    for (int i = threadIdx.x; i < n_maps; i += blockDim.x) {
+        mm_keys[2 * i + 0] = 0xffffffffu;  // running min key
+        mm_keys[2 * i + 1] = 0u;           // running max key
+    }
+}
+
+constexpr int kVCols = 64;   // columns per CTA in pass V
+constexpr int kVRows = 16;   // output rows per thread per sweep
+constexpr int kVGroups = 8;  // row groups per CTA (kVCols * kVGroups = 512 threads)
+
+// pass V: out[y][x] = sum_j w[j] * in[reflect(y + j - lw)][x]
+__global__ void __launch_bounds__(kVCols *kVGroups) blur_vertical_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                                         const float *__restrict__ weights, int H, int W, int lw,
+                                                                         int tile_rows, int n_w_padded) {
+    extern __shared__ float smem[];
+    float *s_w = smem;                    // [n_w_padded]
+    float *s_in = smem + n_w_padded;      // [tile_rows + 2*lw + kTapPad + kVRows][kVCols]
+    const int map = blockIdx.z;
+    const int x_base = blockIdx.x * kVCols;
+    const int y_base = blockIdx.y * tile_rows;
+    const int rows_here = min(tile_rows, H - y_base);
+    const int n_virtual = rows_here + 2 * lw;
+    const int n_alloc = tile_rows + 2 * lw + kTapPad + kVRows;
+    const float *src = in + (long long)map * H * W;
+    for (int j = threadIdx.x; j < n_w_padded; j += blockDim.x) s_w[j] = weights[j];
+    const int cx = threadIdx.x % kVCols;
+    const int gx = x_base + cx;
+    for (int r = threadIdx.x / kVCols; r < n_alloc; r += kVGroups) {
+        float v = 0.f;
+        if (r < n_virtual && gx < W) v = src[(long long)reflect_index(y_base - lw + r, H) * W + gx];
+        s_in[r * kVCols + cx] = v;
+    }
+    __syncthreads();
+    float *dst = out + (long long)map * H * W;
+    const int grp = threadIdx.x / kVCols;
+    for (int yl = grp * kVRows; yl < rows_here; yl += kVGroups * kVRows) {
+        float acc[kVRows];
+#pragma unroll
+        for (int r = 0; r < kVRows; ++r) acc[r] = 0.f;
+        for (int jc = 0; jc < 2 * lw + 1; jc += 8) {
+            float vv[kVRows + 7], ww[8];
+#pragma unroll
+            for (int i = 0; i < kVRows + 7; ++i) vv[i] = s_in[(yl + jc + i) * kVCols + cx];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ww[i] = s_w[jc + i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int r = 0; r < kVRows; ++r) acc[r] = fmaf(ww[i], vv[i + r], acc[r]);
+        }
+        if (gx < W) {
+#pragma unroll
+            for (int r = 0; r < kVRows; ++r)
+                if (yl + r < rows_here) dst[(long long)(y_base + yl + r) * W + gx] = acc[r];
+        }
+    }
+}
+
+constexpr int kHRows = 32;    // rows per CTA in pass H (one per lane)
+constexpr int kHCols = 16;    // output columns per thread per sweep
+constexpr int kHGroups = 16;  // column groups per CTA (32 * 16 = 512 threads)
+
+// pass H: out[y][x] = sum_j w[j] * in[y][reflect(x + j - lw)], + min/max of the result
+__global__ void __launch_bounds__(kHRows *kHGroups) blur_horizontal_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                                           const float *__restrict__ weights,
+                                                                           unsigned *__restrict__ mm_keys, int H, int W, int lw,
+                                                                           int tile_cols, int pitch, int n_w_padded) {
+    extern __shared__ float smem[];
+    float *s_w = smem;                                   // [n_w_padded]
+    float *s_in = smem + n_w_padded;                     // [kHRows][pitch]
+    float *s_out = s_in + kHRows * pitch;                // [kHRows][kHGroups*kHCols + 1]
+    constexpr int kOutPitch = kHGroups * kHCols + 1;
+    __shared__ unsigned s_mm[2];
+    const int map = blockIdx.z;
+    const int y_base = blockIdx.y * kHRows;
+    const int x_base = blockIdx.x * tile_cols;
+    const int cols_here = min(tile_cols, W - x_base);
+    const int n_virtual = cols_here + 2 * lw;
+    const float *src = in + (long long)map * H * W;
+    float *dst = out + (long long)map * H * W;
+    if (threadIdx.x == 0) { s_mm[0] = 0xffffffffu; s_mm[1] = 0u; }
+    for (int j = threadIdx.x; j < n_w_padded; j += blockDim.x) s_w[j] = weights[j];
+    for (int i = threadIdx.x; i < kHRows * pitch; i += blockDim.x) {
+        int r = i / pitch, v = i - r * pitch;
+        float val = 0.f;
+        int gy = y_base + r;
+        if (v < n_virtual && gy < H) val = src[(long long)gy * W + reflect_index(x_base - lw + v, W)];
+        s_in[i] = val;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int gy = y_base + lane;
+    float mn = INFINITY, mx = -INFINITY;
+    bool has_nan = false;
+    for (int sweep = 0; sweep < cols_here; sweep += kHGroups * kHCols) {
+        const int xl = sweep + grp * kHCols;
+        if (xl < cols_here) {
+            float acc[kHCols];
+#pragma unroll
+            for (int r = 0; r < kHCols; ++r) acc[r] = 0.f;
+            const float *row = s_in + lane * pitch + xl;
+            for (int jc = 0; jc < 2 * lw + 1; jc += 8) {
+                float vv[kHCols + 7], ww[8];
+#pragma unroll
+                for (int i = 0; i < kHCols + 7; ++i) vv[i] = row[jc + i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) ww[i] = s_w[jc + i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int r = 0; r < kHCols; ++r) acc[r] = fmaf(ww[i], vv[i + r], acc[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < kHCols; ++r) s_out[lane * kOutPitch + grp * kHCols + r] = acc[r];
+        }
+        __syncthreads();
+        // coalesced write-back of this sweep's [kHRows][<=256] block, tracking min/max
+        const int sweep_cols = min(kHGroups * kHCols, cols_here - sweep);
+        for (int i = threadIdx.x; i < kHRows * sweep_cols; i += blockDim.x) {
+            int r = i / sweep_cols, c = i - r * sweep_cols;
+            if (y_base + r < H) {
+                float v = s_out[r * kOutPitch + c];
+                dst[(long long)(y_base + r) * W + x_base + sweep + c] = v;
+                has_nan = has_nan || (v != v);
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+            }
+        }
+        __syncthreads();
+    }
+    (void)gy;
+    unsigned kmin = has_nan ? 0u : f2key(mn), kmax = has_nan ? 0xffffffffu : f2key(mx);
+    if (mn == INFINITY && !has_nan) { kmin = 0xffffffffu; kmax = 0u; }  // thread saw no pixel
+    for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if (lane == 0) { atomicMin(&s_mm[0], kmin); atomicMax(&s_mm[1], kmax); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicMin(&mm_keys[2 * map + 0], s_mm[0]);
+        atomicMax(&mm_keys[2 * map + 1], s_mm[1]);
+    }
+}
+
+// decode keys -> (min, max) floats; optional in-place normalisation (y - min) / (max - min)
+__global__ void blur_minmax_decode_kernel(const unsigned *__restrict__ mm_keys, float *__restrict__ minmax, int n_maps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_maps) {
+        minmax[2 * i + 0] = key2f(mm_keys[2 * i + 0]);
+        minmax[2 * i + 1] = key2f(mm_keys[2 * i + 1]);
+    }
+}
+
+__global__ void __launch_bounds__(256) blur_normalize_kernel(float *__restrict__ maps, const float *__restrict__ minmax, long long HW,
+                                                             long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long m = i / HW;
+        float mn = minmax[2 * m], mx = minmax[2 * m + 1];
+        // DRV:1151-1152: att -= att.min(); att /= att.max()
+        maps[i] = __fdiv_rn(__fsub_rn(maps[i], mn), __fsub_rn(mx, mn));
+    }
+}
+
+static inline int blur_radius(double sigma) { return (int)(4.0 * sigma + 0.5); }  // scipy: int(truncate * sd + 0.5)
+static inline int blur_padded_taps(int lw) { return (int)align_up((size_t)(2 * lw + 1), 8) + kTapPad; }
+
+}  // namespace pnp
+
+using namespace pnp;
+
+extern "C" size_t pnp_threshold_upsample_workspace_bytes(int B, int C, int P) {
+    if (B < 0 || C < 0 || P < 0) return 0;
+    return align_up((size_t)B * C * P * P * sizeof(float), 256) + align_up((size_t)B * C * 2 * sizeof(float), 256);
+}
+
+extern "C" int pnp_threshold_upsample(const float *class_maps, float *out, void *workspace, size_t workspace_bytes, int B,
+                                      int C, int P, int H, int W, float threshold, int rescale, int with_background,
+                                      pnp_stream_t stream) {
+    if (!class_maps || !out || !workspace || B < 0 || C < 1 || P < 1 || P * P > kMaxP2 || H < 1 || W < 1 || B > 65535)
+        return PNP_ERR_INVALID_ARGUMENT;
+    if (workspace_bytes < pnp_threshold_upsample_workspace_bytes(B, C, P)) return PNP_ERR_WORKSPACE;
+    if (B == 0) return PNP_OK;
+    cudaStream_t st = as_stream(stream);
+    float *masked = reinterpret_cast<float *>(workspace);
+    float *params = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align_up((size_t)B * C * P * P * sizeof(float), 256));
+    threshold_prep_kernel<<<dim3(C, B), 256, 0, st>>>(class_maps, masked, params, C, P, H, W, threshold, rescale);
+    int rc = launch_status();
+    if (rc != PNP_OK) return rc;
+    const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec) {
+        int gx = max(1, min(ceil_div((long long)H * (W / 4), 256), ceil_div(kNumSMs * 8, B)));
+        upsample_write_kernel<4><<<dim3(gx, B), 256, 0, st>>>(masked, params, out, C, P, H, W, rescale, with_background);
+    } else {
+        int gx = max(1, min(ceil_div((long long)H * W, 256), ceil_div(kNumSMs * 8, B)));
+        upsample_write_kernel<1><<<dim3(gx, B), 256, 0, st>>>(masked, params, out, C, P, H, W, rescale, with_background);
+    }
+    return launch_status();
+}
+
+namespace {
+struct BlurPlan {
+    int lw, n_w_padded, tile_rows, tile_cols, pitch;
+    size_t smem_v, smem_h;
+    size_t off_keys, off_tmp, total;
+};
+constexpr size_t kSmemBudget = 200 * 1024;
+
+bool make_blur_plan(int n_maps, int H, int W, double sigma, BlurPlan &p) {
+    if (!(sigma > 0.0) || n_maps < 0 || H < 1 || W < 1) return false;
+    p.lw = blur_radius(sigma);
+    if (p.lw > 4096) return false;
+    p.n_w_padded = blur_padded_taps(p.lw);
+    // pass V: whole column strip if it fits, else row tiles
+    size_t fixed_rows = 2 * (size_t)p.lw + kTapPad + kVRows;
+    size_t max_rows = (kSmemBudget - p.n_w_padded * sizeof(float)) / (kVCols * sizeof(float));
+    if (max_rows <= fixed_rows + kVRows) return false;
+    p.tile_rows = (int)std::min<size_t>((size_t)H, (max_rows - fixed_rows) / kVRows * kVRows);
+    p.smem_v = (p.n_w_padded + (p.tile_rows + fixed_rows) * kVCols) * sizeof(float);
+    // pass H: full rows if they fit, else column tiles
+    size_t out_floats = (size_t)kHRows * (kHGroups * kHCols + 1);
+    size_t max_pitch = (kSmemBudget - (p.n_w_padded + out_floats) * sizeof(float)) / (kHRows * sizeof(float));
+    size_t fixed_cols = 2 * (size_t)p.lw + kTapPad + kHCols;
+    if (max_pitch <= fixed_cols + kHCols + 1) return false;
+    p.tile_cols = (int)std::min<size_t>((size_t)W, (max_pitch - 1 - fixed_cols) / kHCols * kHCols);
+    p.pitch = (int)(p.tile_cols + fixed_cols) | 1;
+    p.smem_h = (p.n_w_padded + (size_t)kHRows * p.pitch + out_floats) * sizeof(float);
+    p.off_keys = align_up(p.n_w_padded * sizeof(float), 256);
+    p.off_tmp = p.off_keys + align_up((size_t)n_maps * 2 * sizeof(unsigned), 256);
+    p.total = p.off_tmp + align_up((size_t)n_maps * H * W * sizeof(float), 256);
+    return true;
+}
+}  // namespace
+
+extern "C" size_t pnp_gaussian_blur_workspace_bytes(int n_maps, int H, int W, double sigma) {
+    BlurPlan p;
+    return make_blur_plan(n_maps, H, W, sigma, p) ? p.total : 0;
+}
+
+extern "C" int pnp_gaussian_blur(const float *in, float *out, float *minmax, void *workspace, size_t workspace_bytes,
+                                 int n_maps, int H, int W, double sigma, int normalize, pnp_stream_t stream) {
+    BlurPlan p;
+    if (!in || !out || !minmax || !workspace || in == out || !make_blur_plan(n_maps, H, W, sigma, p)) return PNP_ERR_INVALID_ARGUMENT;
+    if (workspace_bytes < p.total) return PNP_ERR_WORKSPACE;
+    if (n_maps == 0) return PNP_OK;
+    if (n_maps > 65535) return PNP_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = as_stream(stream);
+    char *ws = reinterpret_cast<char *>(workspace);
+    float *weights = reinterpret_cast<float *>(ws);
+    unsigned *keys = reinterpret_cast<unsigned *>(ws + p.off_keys);
+    float *tmp = reinterpret_cast<float *>(ws + p.off_tmp);
+    cudaError_t e = cudaFuncSetAttribute(blur_vertical_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_v);
+    if (e != cudaSuccess) return cuda_err(e);
+    e = cudaFuncSetAttribute(blur_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_h);
+    if (e != cudaSuccess) return cuda_err(e);
+    blur_prologue_kernel<<<1, 256, 0, st>>>(weights, keys, n_maps, p.lw, p.n_w_padded, sigma);
+    blur_vertical_kernel<<<dim3(ceil_div(W, kVCols), ceil_div(H, p.tile_rows), n_maps), kVCols * kVGroups, p.smem_v, st>>>(
+        in, tmp, weights, H, W, p.lw, p.tile_rows, p.n_w_padded);
+    blur_horizontal_kernel<<<dim3(ceil_div(W, p.tile_cols), ceil_div(H, kHRows), n_maps), kHRows * kHGroups, p.smem_h, st>>>(
+        tmp, out, weights, keys, H, W, p.lw, p.tile_cols, p.pitch, p.n_w_padded);
+    blur_minmax_decode_kernel<<<ceil_div(n_maps, 256), 256, 0, st>>>(keys, minmax, n_maps);
+    if (normalize) {
+        long long total = (long long)n_maps * H * W;
+        int grid = (int)std::min<long long>((long long)kNumSMs * 16, (total + 255) / 256);
+        blur_normalize_kernel<<<grid, 256, 0, st>>>(out, minmax, (long long)H * W, total);
+    }
+    return launch_status();
+}

@@ -1,0 +1,164 @@
+"""Batched GPU composition of the hot path, as save_img_union_attention (DRV:290-521 / DRVC:337-640) composes it
+per image on the CPU: Salience DropOut rounds -> token merge -> threshold/upsample -> blur -> dense CRF -> argmax,
+relabel, confusion matrix.  Everything stays on the device between stages; images of one launch share
+(C, background rule, H, W) and are bucketed by that key when a batch is ragged."""
+import numpy as np
+import torch
+
+from . import host, ops
+from ._lib import PnpError
+
+CRF_DEFAULTS = dict(n_iter=10, pos_w=7.0, pos_xy_std=3.0, bi_w=10.0, bi_xy_std=50.0, bi_rgb_std=5.0)  # DRV:1036-1041
+BLUR_SCALE = 0.05  # DRV:1009
+SAVE_LEN = 10      # DRV:643
+
+
+# ---------------------------------------------------------------------------------------------- (c) loop
+def salience_dropout_loop(gradcam_fn, imgs, norm_imgs, drop_iter, P, save_len=SAVE_LEN):
+    """DRV:564-722.  gradcam_fn(imgs [B,3,S,S] cuda) -> [B,T-1,P,P] stands for
+    compute_gradcam_ensemble(...)[layer][head].  imgs / norm_imgs are modified in place (pixel blocks zeroed).
+    Returns (gradcam_0, gradcam_agg or None, chosen int32 [B, save_len*drop_iter] or None)."""
+    if drop_iter == 1:  # DRV:565-575
+        return gradcam_fn(imgs).detach().clone(), None, None
+    B, _, S, _ = imgs.shape
+    patch = S // P
+    chosen = torch.full((B, save_len * drop_iter), -1, dtype=torch.int32, device=imgs.device)
+    g0 = agg = None
+    for r in range(drop_iter):
+        g = gradcam_fn(imgs).detach().contiguous()
+        Tm = g.shape[1]
+        if r == 0:
+            g0 = torch.empty_like(g)
+            agg = torch.empty_like(g)
+        ops.salience_dropout_round(g, agg, chosen, save_len * r, imgs, norm_imgs, P, patch, 3, Tm - 1, save_len, r,
+                                   ensemble_r=g0 if r == 0 else None)
+    return g0, agg, chosen
+
+
+# ---------------------------------------------------------------------------------------------- (b) batched merge
+def merge_tokens_batch(gradcam, token_ids, decode, class_lists):
+    """gradcam [B,T-1,P,P]; token_ids [B,>=T] host ints; returns a list of per-image [C_b,P,P] CUDA tensors
+    (one pnp_token_merge launch over the batch, padded to the largest C)."""
+    B = gradcam.shape[0]
+    Cmax = max(len(c) for c in class_lists)
+    start = np.zeros((B, Cmax), np.int32)
+    length = np.zeros((B, Cmax), np.int32)
+    div = np.ones((B, Cmax), np.float32)
+    for b in range(B):
+        toks = host.token_strings(list(token_ids[b]), decode)
+        for c, (s, l, d) in enumerate(host.build_token_segments(toks, len(class_lists[b]))):
+            start[b, c], length[b, c], div[b, c] = s, l, d
+    dev = gradcam.device
+    maps = ops.token_merge(gradcam.contiguous(), torch.from_numpy(start).to(dev), torch.from_numpy(length).to(dev),
+                           torch.from_numpy(div).to(dev), row_offset=3)
+    return [maps[b, :len(class_lists[b])] for b in range(B)]
+
+
+# ---------------------------------------------------------------------------------------------- (d)(e)(f)
+class SpatialLatticeCache:
+    """The Gaussian-kernel lattice depends on (H, W, sxy) only; build once per shape (SURVEY 7 hard part 1)."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def get(self, H, W, sxy, device):
+        key = (H, W, float(sxy), str(device))
+        if key not in self._cache:
+            self._cache[key] = ops.build_lattice(H, W, sxy, device=device)
+        return self._cache[key]
+
+
+_SPATIAL = SpatialLatticeCache()
+
+
+def postprocess_batch(class_maps, guides, gts, luts, hist, *, threshold, rescale, with_background, mode, n_class,
+                      crf=None, bad_count=None, return_labels=False, stats=None):
+    """class_maps [B,C,P,P] -> labels -> hist (accumulated in place).  guides uint8 [B,H,W,3]; gts float32 [B,H,W];
+    luts int32 [B,C'] (composed relabel tables).  mode: the --postprocess string ('', 'blur', 'crf', 'blur+crf')."""
+    B, C = class_maps.shape[:2]
+    H, W = gts.shape[1:]
+    N = H * W
+    x = ops.threshold_upsample(class_maps.contiguous(), H, W, threshold, rescale, with_background)
+    Cc = x.shape[1]
+    minmax = None
+    use_blur = bool(mode) and "blur" in mode
+    use_crf = bool(mode) and "crf" in mode
+    if use_blur:
+        x, minmax = ops.gaussian_blur(x, BLUR_SCALE * max(H, W), normalize=not use_crf)
+    if use_crf:
+        p = dict(CRF_DEFAULTS)
+        p.update(crf or {})
+        U = ops.crf_unary_from_maps(x.view(B, Cc, N), minmax if use_blur else None)
+        del x
+        lat_s = _SPATIAL.get(H, W, p["pos_xy_std"], U.device)
+        lat_b = ops.build_lattice(H, W, p["bi_xy_std"], rgb=guides, srgb=p["bi_rgb_std"])
+        if stats is not None:
+            stats["M_s"], stats["M_b"], stats["max_row_b"] = lat_s.M, lat_b.M, lat_b.struct.max_row
+        _, labels = ops.crf_inference([lat_s, lat_b], [p["pos_w"], p["bi_w"]], U, Cc, p["n_iter"], want_labels=True)
+    else:
+        labels = ops.argmax_channels(x.view(B, Cc, N))
+    pred = torch.empty((B, N), dtype=torch.float32, device=labels.device) if return_labels else None
+    ops.confusion_accumulate(labels, gts.view(B, N), n_class, hist, lut=luts, pred_out=pred, bad_count=bad_count)
+    return pred.view(B, H, W) if return_labels else None
+
+
+def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_ids, gts, guides, *, drop_iter, patch_num,
+                    threshold, data_type, mode, n_class, coco=False, crf=None, norm_imgs=None, stats=None):
+    """One batch of save_img_union_attention: returns (hist_round0 or None, hist_all_drop or None) as int64 CUDA
+    tensors [n,n] -- the matrices the reference saves to hist_withfiltered_caption/ and
+    all_drop_hist_with_filtered_caption/ (DRV:495-520).  `coco` selects the COCO driver's deltas (DRVC:420, 527, 602).
+
+    imgs [B,3,S,S] cuda (modified in place by the DropOut rounds); gts list/array of float32 [H,W]; guides list/array
+    of uint8 [H,W,3]; dataset_ids[b][i] = id written for local class i."""
+    dev = imgs.device
+    g0, agg, chosen = salience_dropout_loop(gradcam_fn, imgs, norm_imgs, drop_iter, patch_num)
+    B = imgs.shape[0]
+    # bucket images by everything a launch must share
+    buckets = {}
+    for b in range(B):
+        C = len(class_lists[b])
+        with_bg = host.add_background_rule(data_type, C)
+        key = (C, with_bg, tuple(np.asarray(gts[b]).shape))
+        buckets.setdefault(key, []).append(b)
+
+    def run(gmaps, rescale):
+        hist = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        per_image = merge_tokens_batch(gmaps, token_ids, decode, class_lists)
+        for (C, with_bg, (H, W)), members in buckets.items():
+            cm = torch.stack([per_image[b] for b in members]).contiguous()
+            gt = torch.stack([torch.as_tensor(np.asarray(gts[b], dtype=np.float32)) for b in members]).to(dev)
+            gd = torch.stack([torch.as_tensor(np.ascontiguousarray(guides[b])) for b in members]).to(dev)
+            lut = torch.tensor([host.relabel_lut(dataset_ids[b], with_bg) for b in members], dtype=torch.int32, device=dev)
+            postprocess_batch(cm, gd, gt, lut, hist, threshold=threshold, rescale=rescale, with_background=with_bg, mode=mode,
+                              n_class=n_class, crf=crf, bad_count=bad, stats=stats)
+        if int(bad.item()):
+            raise PnpError("a relabelled id fell outside [0, n_class)")
+        return hist
+
+    hist0 = hist_agg = None
+    if not coco or drop_iter < 3:
+        hist0 = run(g0, True)           # 1-round path applies Scale_0_1 (DRV:362)
+    if agg is not None:
+        hist_agg = run(agg, coco)       # N-round path: only the COCO driver rescales (DRV:438 vs DRVC:527)
+    return hist0, hist_agg, chosen
+
+
+# ---------------------------------------------------------------------------------------------- multi-GPU + files
+def allreduce_hist(hist):
+    """Sum the int64 confusion matrix over ranks (NCCL over NVLink); no-op without a process group.  This replaces
+    the reference's reduce-through-the-filesystem (DRV:513-520 + Calculate_mIoU.py:204-219)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    return hist
+
+
+def save_hist_npy(hist, save_path, subdir, first_img_id, max_block_num, att_head):
+    """Write the matrix in the layout Calculate_mIoU.py expects (DRV:513-520: float64 [n,n] .npy)."""
+    import os
+    d = os.path.join(save_path, subdir)
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "img_%s_max_blocknum_%s_atthead_%s.npy" % (first_img_id, max_block_num, att_head))
+    np.save(path, hist.detach().cpu().numpy().astype(np.float64))
+    return path

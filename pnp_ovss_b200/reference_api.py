@@ -1,0 +1,259 @@
+"""Drop-in replacements for the Python callables of the reference's mask-extraction path: same names, same
+arguments, same return types, computed by libpnp_ovss_b200.so on the current CUDA device.
+
+    from pnp_ovss_b200.reference_api import (compute_gradcam_ensemble, Inference_BLIP_filteredcaption,
+        Mean_over_filtered_label_tokens, postprocess, blurring, densecrf, Scale_0_1, _fast_hist, scores)
+    from pnp_ovss_b200.reference_api import DenseCRF2D, unary_from_softmax      # pydensecrf surface
+
+Inputs may live on the host (numpy / CPU tensors, as the reference passes them): they are copied to the GPU, the
+kernels run there, and results come back in the container type the reference returns.  There is no CPU code path:
+without a CUDA device or without the built library these functions raise.
+
+DRV = PnP_OVSS_0514_updated_segmentation.py, DRVC = its _coco twin, BITM = blip_image_text_matching.py."""
+import numpy as np
+import torch
+
+from . import host, ops
+from ._lib import PnpError
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise PnpError("pnp_ovss_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_dev(x, dtype=torch.float32):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    return x.to(device=_device(), dtype=dtype, non_blocking=True).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------- a5: Scale_0_1
+def Scale_0_1(AA):
+    """DRV:1078-1094.  Per-channel min-max rescale, in place like the reference, on whatever device AA lives.
+    (On the fused path this is folded into pnp_threshold_upsample(rescale=1); this entry point exists for callers
+    that use it standalone and is plain tensor glue, not a kernel.)"""
+    if AA.dim() == 2:
+        return AA
+    shape = AA.shape
+    flat = AA.view(*shape[:-2], -1)
+    flat -= flat.min(-1, keepdim=True)[0]
+    flat /= flat.max(-1, keepdim=True)[0]
+    return flat.view(shape)
+
+
+# ------------------------------------------------------------------------------------------------- a6: blurring
+def blurring(att_resize, img_shape, scale=0.05):
+    """DRV:1149-1153: gaussian_filter(sigma = scale*max(img_shape)) then min-max.  Returns a numpy [H,W] array."""
+    x = _to_dev(att_resize)
+    if x.dim() != 2:
+        raise PnpError("blurring expects one [H,W] map")
+    out, _ = ops.gaussian_blur(x.unsqueeze(0), scale * max(img_shape), normalize=True)
+    return out[0].cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------- a8: pydensecrf surface
+def unary_from_softmax(sm, scale=None, clip=1e-5):
+    """pydensecrf.utils.unary_from_softmax (host numpy, as upstream): -log(clip(p)) as float32 [C, N]."""
+    sm = np.asarray(sm)
+    num_cls = sm.shape[0]
+    if scale is not None:
+        uniform = np.ones(sm.shape) / num_cls
+        sm = scale * sm + (1 - scale) * uniform
+    if clip is not None:
+        sm = np.clip(sm, clip, 1.0)
+    return -np.log(sm).reshape([num_cls, -1]).astype(np.float32)
+
+
+_SPATIAL_CACHE = {}
+
+
+def _spatial_lattice(H, W, sxy, device):
+    """The Gaussian-kernel lattice depends on (H, W, sxy) only: built once per shape and process."""
+    sx, sy = (sxy, sxy) if np.isscalar(sxy) else sxy
+    key = (int(H), int(W), float(sx), float(sy), str(device))
+    if key not in _SPATIAL_CACHE:
+        _SPATIAL_CACHE[key] = ops.build_lattice(H, W, (sx, sy), device=device)
+    return _SPATIAL_CACHE[key]
+
+
+class DenseCRF2D:
+    """pydensecrf.densecrf.DenseCRF2D for the calls the reference makes (DRV:1066-1071):
+    DenseCRF2D(w,h,c), setUnaryEnergy(float32 [c, w*h]), addPairwiseGaussian(sxy, compat),
+    addPairwiseBilateral(sxy, srgb, rgbim uint8 [h,w,3], compat), inference(n) -> Q [c, w*h] (numpy)."""
+
+    def __init__(self, w, h, c):
+        self.w, self.h, self.c = int(w), int(h), int(c)
+        self._dev = _device()
+        self._unary = None
+        self._lattices = []
+        self._weights = []
+
+    def setUnaryEnergy(self, U):
+        U = np.asarray(U)
+        if U.dtype != np.float32 or not U.flags.c_contiguous:
+            raise ValueError("Buffer dtype mismatch / ndarray is not C-contiguous")
+        if U.shape != (self.c, self.w * self.h):
+            raise ValueError("Bad shape for unary energy (Need (%d, %d), got %s)" % (self.c, self.w * self.h, U.shape))
+        self._unary = ops.crf_pack(_to_dev(U).unsqueeze(0))
+
+    def addPairwiseGaussian(self, sxy, compat, kernel=None, normalization=None):
+        self._lattices.append(_spatial_lattice(self.h, self.w, sxy, self._dev))
+        self._weights.append(float(compat))
+
+    def addPairwiseBilateral(self, sxy, srgb, rgbim, compat, kernel=None, normalization=None):
+        rgbim = np.asarray(rgbim)
+        if rgbim.dtype != np.uint8 or not rgbim.flags.c_contiguous or rgbim.shape != (self.h, self.w, 3):
+            raise ValueError("Bad shape for pairwise bilateral (Need (%d, %d, 3) uint8 C-contiguous)" % (self.h, self.w))
+        rgb = torch.from_numpy(rgbim).to(self._dev).unsqueeze(0).contiguous()
+        self._lattices.append(ops.build_lattice(self.h, self.w, sxy, rgb=rgb, srgb=srgb))
+        self._weights.append(float(compat))
+
+    def inference(self, n):
+        if self._unary is None:
+            raise RuntimeError("setUnaryEnergy was not called")
+        Q, _ = ops.crf_inference(self._lattices, self._weights, self._unary, self.c, int(n), want_labels=False)
+        return ops.crf_unpack(Q, self.c)[0].cpu().numpy()
+
+
+def densecrf(image, mask, n_iter=10, pos_w=7, pos_xy_std=3, bi_w=10, bi_xy_std=50, bi_rgb_std=5, return_q=False):
+    """DRV:1030-1074.  image uint8 [H,W,3]; mask [C',H,W] (tensor or ndarray, raw channel scores).
+    Returns the float32 [H,W] argmax map (and Q [C',H,W] when return_q), as numpy like the reference."""
+    dev = _device()
+    m = _to_dev(mask)
+    C, H, W = m.shape
+    image = np.ascontiguousarray(image)
+    if image.dtype != np.uint8 or image.shape != (H, W, 3):
+        raise ValueError("image must be uint8 [H,W,3] matching the mask")
+    rgb = torch.from_numpy(image).to(dev).unsqueeze(0).contiguous()
+    U = ops.crf_unary_from_maps(m.view(1, C, H * W))  # softmax over channels + unary_from_softmax, fused
+    lat_s = _spatial_lattice(H, W, pos_xy_std, dev)
+    lat_b = ops.build_lattice(H, W, bi_xy_std, rgb=rgb, srgb=bi_rgb_std)
+    Q, labels = ops.crf_inference([lat_s, lat_b], [pos_w, bi_w], U, C, n_iter, want_labels=True)
+    MAP = labels.view(H, W).to(torch.float32).cpu().numpy()
+    if return_q:
+        return MAP, ops.crf_unpack(Q, C)[0].view(C, H, W).cpu().numpy()
+    return MAP
+
+
+# ------------------------------------------------------------------------------------------------- postprocess
+def postprocess(args, final_pred_wbackground, org_img_list, label_trues, img):
+    """DRV:1002-1028: `args.postprocess` substring tests select blur, crf or blur+crf; returns a numpy label map."""
+    mode = args.postprocess
+    x = _to_dev(final_pred_wbackground)
+    C, H, W = x.shape
+    img_shape = (label_trues[img].shape[0], label_trues[img].shape[1])
+    if "blur" in mode:
+        x, _ = ops.gaussian_blur(x, 0.05 * max(img_shape), normalize=True)
+    if "crf" in mode:
+        return densecrf(org_img_list[img], x)
+    if "blur" in mode:
+        return ops.argmax_channels(x.view(1, C, H * W)).view(H, W).to(torch.int64).cpu().numpy()
+    raise PnpError("postprocess mode %r selects neither blur nor crf" % (mode,))
+
+
+# ------------------------------------------------------------------------------------------------- a10: confusion matrix
+def _fast_hist(label_true, label_pred, n_class):
+    """DRV:1106-1112 on flat arrays; returns an int64 [n,n] numpy array."""
+    gt = _to_dev(np.asarray(label_true, dtype=np.float32).reshape(1, -1))
+    pred = _to_dev(np.asarray(label_pred).reshape(1, -1), dtype=torch.int32)
+    hist = torch.zeros((n_class, n_class), dtype=torch.int64, device=gt.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=gt.device)
+    ops.confusion_accumulate(pred, gt, n_class, hist, bad_count=bad)
+    if int(bad.item()):
+        raise ValueError("predicted label outside [0, n_class) (np.bincount(...).reshape would fail in the reference)")
+    return hist.cpu().numpy()
+
+
+def scores(label_trues, label_preds, cats=None, n_class=None):
+    """DRV:1115-1146.  Returns ({...metrics...}, hist float64 [n,n]); the histogram is accumulated on the GPU."""
+    dev = _device()
+    hist = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    for lt, lp in zip(label_trues, label_preds):
+        gt = _to_dev(np.asarray(lt, dtype=np.float32).reshape(1, -1))
+        pred = _to_dev(np.asarray(lp).reshape(1, -1), dtype=torch.int32)
+        ops.confusion_accumulate(pred, gt, n_class, hist, bad_count=bad)
+    if int(bad.item()):
+        raise ValueError("predicted label outside [0, n_class)")
+    return metrics_from_hist(hist.cpu().numpy().astype(np.float64))
+
+
+def metrics_from_hist(hist):
+    """The derived statistics of DRV:1121-1146 / Calculate_mIoU.py:221-256 (host arithmetic on the [n,n] matrix)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        acc = np.diag(hist).sum() / hist.sum()
+        acc_cls = np.nanmean(np.diag(hist) / hist.sum(axis=1))
+        iu = np.diag(hist) / (hist.sum(axis=1) + hist.sum(axis=0) - np.diag(hist))
+        valid = hist.sum(axis=1) > 0
+        mean_iu = np.nanmean(iu[valid])
+        freq = hist.sum(axis=1) / hist.sum()
+        fwavacc = (freq[freq > 0] * iu[freq > 0]).sum()
+    return {"Pixel Accuracy": acc, "Mean Accuracy": acc_cls, "Frequency Weighted IoU": fwavacc, "Mean IoU": mean_iu,
+            "Class IoU": iu}, hist
+
+
+# ------------------------------------------------------------------------------------------------- a3: token merge
+def Mean_over_filtered_label_tokens(model_textloc, txt_tokens_filtered, gradcam_filtered, class_filtered_list, img_num):
+    """DRV:810-853.  gradcam_filtered [T-1,P,P] of image img_num -> [C,P,P] (on the GPU; .cpu() it if needed)."""
+    tokenizer = model_textloc.module.tokenizer if hasattr(model_textloc, "module") else model_textloc.tokenizer
+    toks = host.token_strings(txt_tokens_filtered.input_ids[img_num].tolist(), tokenizer.decode)
+    n_classes = len(class_filtered_list[img_num])
+    segs = host.build_token_segments(toks, n_classes)
+    g = _to_dev(gradcam_filtered).unsqueeze(0)
+    dev = g.device
+    start = torch.tensor([[s[0] for s in segs]], dtype=torch.int32, device=dev)
+    length = torch.tensor([[s[1] for s in segs]], dtype=torch.int32, device=dev)
+    div = torch.tensor([[s[2] for s in segs]], dtype=torch.float32, device=dev)
+    return ops.token_merge(g, start, length, div, row_offset=3)[0]
+
+
+# ------------------------------------------------------------------------------------------------- a1/a2/a4
+def compute_gradcam_ensemble(args, model, visual_input, text_input, tokenized_text, drop_iter=0):
+    """BITM:386-457.  Returns (blocklist, [], itm_output) where blocklist[layer][head] -> [B,T-1,P,P].
+
+    Only blocklist[max_att_block_num-1][prune_att_head] is ever read by the drivers (DRV:572-574, 619-621), so the
+    list materialises exactly that entry, from the fused softmax-backward/GradCAM kernel of the model's block-8
+    cross-attention (pnp_ovss_b200.blip_itm.BlipITM.gradcam); every other entry raises if touched."""
+    layer = int(args.max_att_block_num) - 1
+    head = int(args.prune_att_head)
+    gradcam, output = model.gradcam(visual_input, text_input, tokenized_text, layer=layer, head=head)
+    return _LazyBlocklist(layer, head, gradcam), [], output
+
+
+class _LazyBlocklist:
+    def __init__(self, layer, head, value):
+        self._layer, self._head, self._value = layer, head, value
+
+    def __getitem__(self, layer):
+        if layer != self._layer:
+            raise PnpError("only block %d was captured (the reference drivers read just that one)" % self._layer)
+        return _LazyHeadlist(self._head, self._value)
+
+
+class _LazyHeadlist:
+    def __init__(self, head, value):
+        self._head, self._value = head, value
+
+    def __getitem__(self, head):
+        if head != self._head:
+            raise PnpError("only head %d was captured" % self._head)
+        return self._value
+
+
+def Inference_BLIP_filteredcaption(args, model_textloc, txt_tokens_filtered, imgs_in, norm_imgs, img_ids,
+                                   caption_filtered_list, class_filtered_list, rank):
+    """DRV:564-722.  Returns (gradcam_0 [B,T-1,P,P], gradcam_agg or None), both CUDA tensors."""
+    from .pipeline import salience_dropout_loop
+    model = model_textloc.module if hasattr(model_textloc, "module") else model_textloc
+    imgs = _to_dev(imgs_in).clone()
+    norm = _to_dev(norm_imgs).clone() if norm_imgs is not None else None
+    tokens = txt_tokens_filtered
+
+    def gradcam_fn(x):
+        return compute_gradcam_ensemble(args, model, x, caption_filtered_list, tokens)[0][int(args.max_att_block_num) - 1][
+            int(args.prune_att_head)]
+
+    g0, agg, _ = salience_dropout_loop(gradcam_fn, imgs, norm, int(args.drop_iter), int(int(args.img_size) / 16))
+    return g0, agg

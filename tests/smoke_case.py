@@ -1,0 +1,73 @@
+"""Small end-to-end cases shared by __graft_entry__.smoke() and the GPU tests: the CUDA pipeline and the CPU
+oracle run the same seeded DRIVER_CASES inputs (tests/golden/make_golden_cases.py) and are compared."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.dirname(HERE), os.path.join(HERE, "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import synth  # noqa: E402
+from make_golden_cases import DRIVER_CASES, VOC_NMS  # noqa: E402
+
+
+def case_inputs(tag):
+    """Everything a DRIVER_CASES entry needs, loaded from the committed golden fixture."""
+    g = np.load(os.path.join(HERE, "golden", "reference_golden.npz"), allow_pickle=False)
+    coco, data_type, class_lists, R = DRIVER_CASES[tag]
+    S, P, H, W, T, R_, n_cats = (int(v) for v in g["drv_%s_meta" % tag])
+    tok = synth.SyntheticWordPieceTokenizer()
+    caps = ["A picture of " + " ".join(cl) for cl in class_lists]
+    tt = tok(caps, padding="max_length", max_length=500)
+    return dict(coco=coco, data_type=data_type, class_lists=class_lists, R=R, S=S, P=P, H=H, W=W, T=T, n_class=n_cats + 1,
+                tok=tok, tokens=tt, rows=torch.from_numpy(g["drv_%s_rows" % tag]),
+                imgs=torch.from_numpy(g["drv_%s_imgs" % tag]), gts=list(g["drv_%s_gt" % tag]),
+                guides=list(g["drv_%s_guide" % tag]),
+                ids=[[VOC_NMS.index(c) + 1 for c in cl] for cl in class_lists], golden=g)
+
+
+def run_oracle(tag, mode):
+    from oracle import hotpath as O
+    c = case_inputs(tag)
+    fn = synth.SynthGradcamFn(31, len(c["class_lists"]), c["T"], c["P"])
+    with np.errstate(all="ignore"):
+        h0, hagg, chosen = O.batch_confusion(lambda x: fn(x, c["rows"]), c["imgs"], c["tokens"].input_ids, c["tok"].decode,
+                                             c["class_lists"], c["ids"], c["gts"], c["guides"], drop_iter=c["R"],
+                                             patch_num=c["P"], threshold=0.15, data_type=c["data_type"], mode=mode,
+                                             n_class=c["n_class"], coco=c["coco"], argsort_kind="stable")
+    return h0, hagg
+
+
+def run_gpu(tag, mode, dev):
+    from pnp_ovss_b200 import pipeline
+    c = case_inputs(tag)
+    fn = synth.SynthGradcamFn(31, len(c["class_lists"]), c["T"], c["P"])
+    h0, hagg, chosen = pipeline.batch_confusion(lambda x: fn(x.cpu(), c["rows"]).to(dev), c["imgs"].clone().to(dev),
+                                                c["tokens"].input_ids.tolist(), c["tok"].decode, c["class_lists"], c["ids"],
+                                                c["gts"], c["guides"], drop_iter=c["R"], patch_num=c["P"], threshold=0.15,
+                                                data_type=c["data_type"], mode=mode, n_class=c["n_class"], coco=c["coco"])
+    to_np = lambda h: None if h is None else h.cpu().numpy()
+    return to_np(h0), to_np(hagg)
+
+
+def disagreement(h_gpu, h_ref):
+    """Fraction of pixels counted in a different (gt, pred) bin."""
+    return float(np.abs(h_gpu.astype(np.float64) - h_ref).sum() / 2.0 / max(h_ref.sum(), 1.0))
+
+
+def run(dev):
+    """smoke(): one DropOut + blur + CRF batch on the GPU against the oracle."""
+    report = {}
+    for mode in ("blur", "blur+crf"):
+        g0, gagg = run_gpu("voc_r4", mode, dev)
+        o0, oagg = run_oracle("voc_r4", mode)
+        assert g0.sum() == o0.sum() and gagg.sum() == oagg.sum(), "pixel totals differ"
+        d0, dagg = disagreement(g0, o0), disagreement(gagg, oagg)
+        report[mode] = (d0, dagg)
+        limit = 0.0 if mode == "blur" else 0.01
+        assert d0 <= limit and dagg <= limit, "GPU vs oracle pixel disagreement %g / %g in mode %s" % (d0, dagg, mode)
+    return report

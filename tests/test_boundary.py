@@ -1,0 +1,91 @@
+"""CPU: the C-ABI boundary.  The library loads, exports every symbol include/pnp_ovss_b200.h declares, the ctypes
+table covers exactly those symbols, argument validation works without a GPU, and nothing in the product imports
+the oracle or falls back to the CPU."""
+import ast
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pnp_ovss_b200.h")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pnp_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    from pnp_ovss_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        g.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from pnp_ovss_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), "library does not export %s" % name
+    assert sorted(_lib.SIGNATURES) == declared
+
+
+def test_abi_version_and_arch(lib):
+    assert lib.pnp_abi_version() == 1
+    assert lib.pnp_compiled_sm() == 100
+    assert lib.pnp_error_string(0) == b"ok"
+    assert b"workspace" in lib.pnp_error_string(-2)
+
+
+def test_argument_validation_without_gpu(lib):
+    null = ctypes.c_void_p(0)
+    assert lib.pnp_xattn_softmax_fwd(null, null, null, 1, 12, 4, 442, 0.125, null) == -1
+    assert lib.pnp_argmax_channels(null, null, 1, 3, 16, null) == -1
+    assert lib.pnp_gaussian_blur_workspace_bytes(3, 336, 336, 0.0) == 0
+    assert lib.pnp_gaussian_blur_workspace_bytes(3, 336, 336, 16.8) > 3 * 336 * 336 * 4
+    assert lib.pnp_lattice_storage_bytes(3, 1, 100) == 0          # only d = 2 and d = 5 exist
+    assert lib.pnp_lattice_storage_bytes(5, 2, 100) > 0
+    assert lib.pnp_threshold_upsample_workspace_bytes(35, 20, 21) >= 35 * 20 * 441 * 4
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    from pnp_ovss_b200 import PnpError, ops
+    with pytest.raises(PnpError):
+        ops.softmax_fwd(torch.zeros(1, 12, 4, 442))
+    with pytest.raises(PnpError):
+        ops.argmax_channels(torch.zeros(1, 3, 16))
+    with pytest.raises(PnpError):
+        ops.gaussian_blur(torch.zeros(1, 8, 8), 1.0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pnp_ovss_b200")
+    for fn in os.listdir(pkg):
+        if not fn.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(pkg, fn)).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            for n in names:
+                assert not n.split(".")[0] in ("oracle", "scipy"), "%s imports %s" % (fn, n)
+    for fn in os.listdir(os.path.join(pkg, "csrc")):
+        if fn.endswith((".cu", ".cuh")):
+            assert "oracle" not in open(os.path.join(pkg, "csrc", fn)).read().replace("CPU oracle", "")
+
+
+def test_header_cites_reference_lines():
+    text = open(HEADER).read()
+    for cite in ("MED:267-283", "BITM:415-433", "DRV:810-853", "DRV:638-647", "DRV:1149-1153", "DRV:1030-1074", "DRV:1106-1112"):
+        assert cite in text

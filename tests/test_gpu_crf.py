@@ -1,0 +1,216 @@
+"""GPU parity tests for (e): permutohedral lattice build, filtering and mean-field inference, against the C
+restatement of densecrf in oracle/ (PARITY UNPINNED upstream, see oracle/densecrf.c), plus end-to-end driver cases."""
+import numpy as np
+import pytest
+import torch
+
+import smoke_case
+import synth
+from make_golden_cases import DRIVER_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def D():
+    from oracle import densecrf
+    densecrf.lib()
+    return densecrf
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pnp_ovss_b200 import ops as _ops
+    return _ops
+
+
+def _features(H, W, sxy, rgb=None, srgb=None):
+    yy, xx = np.mgrid[0:H, 0:W]
+    f = [xx.astype(np.float32) / np.float32(sxy), yy.astype(np.float32) / np.float32(sxy)]
+    if rgb is not None:
+        for c in range(3):
+            f.append(rgb[:, :, c].astype(np.float32) / np.float32(srgb))
+    return np.stack(f, -1).reshape(H * W, -1).astype(np.float32)
+
+
+def _check_lattice(lat, ref, base_vertex=0, lp0=0):
+    """GPU lattice arrays (slice of image starting at lattice pixel lp0) == oracle lattice, up to the vertex base."""
+    a = lat.arrays()
+    n = ref.N
+    off = a["offset"][lp0:lp0 + n].cpu().numpy()
+    assert np.array_equal(off, ref.offset + base_vertex)
+    assert np.array_equal(a["bary"][lp0:lp0 + n].cpu().numpy(), ref.barycentric)
+    nbr = a["nbr"].cpu().numpy()[:, base_vertex:base_vertex + ref.M]
+    n1 = np.where(ref.n1 < 0, 0, ref.n1 + 1 + base_vertex)
+    n2 = np.where(ref.n2 < 0, 0, ref.n2 + 1 + base_vertex)
+    assert np.array_equal(nbr[:, :, 0], n1)
+    assert np.array_equal(nbr[:, :, 1], n2)
+
+
+@pytest.mark.parametrize("shape", [(40, 56), (97, 61)])
+def test_spatial_lattice_matches_oracle(dev, ops, D, shape):
+    H, W = shape
+    lat = ops.build_lattice(H, W, 3.0, device=dev)
+    ref = D.Lattice(_features(H, W, 3.0))
+    assert lat.M == ref.M
+    _check_lattice(lat, ref)
+    # CSR rows hold each vertex's pixels in ascending order
+    a = lat.arrays()
+    rp, pix = a["row_ptr"].cpu().numpy(), a["csr_pix"].cpu().numpy()
+    assert rp[0] == 0 and rp[-1] == H * W * 3
+    for v in (0, 1, lat.M // 2, lat.M - 1):
+        row = pix[rp[v]:rp[v + 1]]
+        assert (np.diff(row) >= 0).all()
+        assert (a["offset"].cpu().numpy()[row] == v).any(axis=1).all()
+
+
+@pytest.mark.parametrize("kind", ["natural", "noise"])
+def test_bilateral_lattice_matches_oracle_batched(dev, ops, D, kind):
+    H, W, B = 48, 64, 3
+    imgs = np.stack([synth.guide_image(40 + b, H, W, kind) for b in range(B)])
+    lat = ops.build_lattice(H, W, 50.0, rgb=torch.from_numpy(imgs).to(dev), srgb=5.0)
+    base = 0
+    for b in range(B):
+        ref = D.Lattice(_features(H, W, 50.0, imgs[b], 5.0))
+        _check_lattice(lat, ref, base_vertex=base, lp0=b * H * W)
+        base += ref.M
+    assert lat.M == base
+
+
+def test_norm_and_filter_match_oracle(dev, ops, D):
+    H, W, C = 48, 64, 5
+    N = H * W
+    img = synth.guide_image(9, H, W, "natural")
+    crf = D.DenseCRF2D(W, H, C)
+    crf.addPairwiseGaussian(3, 7)
+    crf.addPairwiseBilateral(50, 5, img, 10)
+    lat_s = ops.build_lattice(H, W, 3.0, device=dev)
+    lat_b = ops.build_lattice(H, W, 50.0, rgb=torch.from_numpy(img[None]).to(dev), srgb=5.0)
+    rng = np.random.default_rng(1)
+    x = rng.random((C, N)).astype(np.float32)
+    xg = ops.crf_pack(torch.from_numpy(x[None]).to(dev))
+    for k, lat in enumerate((lat_s, lat_b)):
+        assert np.array_equal(lat.arrays()["norm"].cpu().numpy(), crf.kernel_norm(k)), "norm of kernel %d" % k
+        y = ops.crf_unpack(ops.crf_filter(lat, xg, normalized=True), C)[0].cpu().numpy()
+        ref = crf.kernel_apply(k, x)
+        assert np.array_equal(y, ref), "filter %d: max abs diff %g" % (k, np.abs(y - ref).max())
+
+
+def test_filter_batch_matches_single(dev, ops):
+    """Batched lattices (shared spatial / per-image bilateral) give the same bits as one image at a time."""
+    H, W, C, B = 40, 40, 6, 3
+    imgs = torch.from_numpy(np.stack([synth.guide_image(70 + b, H, W) for b in range(B)])).to(dev)
+    x = torch.rand(B, H * W, 8, device=dev)
+    x[:, :, C:] = 0
+    lat_s = ops.build_lattice(H, W, 3.0, device=dev)
+    lat_b = ops.build_lattice(H, W, 50.0, rgb=imgs, srgb=5.0)
+    ys, yb = ops.crf_filter(lat_s, x), ops.crf_filter(lat_b, x)
+    for b in range(B):
+        one = ops.build_lattice(H, W, 50.0, rgb=imgs[b:b + 1].contiguous(), srgb=5.0)
+        assert torch.equal(ops.crf_filter(one, x[b:b + 1].contiguous())[0], yb[b])
+        assert torch.equal(ops.crf_filter(lat_s, x[b:b + 1].contiguous())[0], ys[b])
+
+
+@pytest.mark.parametrize("C,kind", [(4, "natural"), (21, "natural"), (3, "noise")])
+def test_inference_matches_oracle(dev, D, C, kind):
+    from pnp_ovss_b200 import reference_api as R
+    H, W = 50, 44
+    img = synth.guide_image(C, H, W, kind)
+    rng = np.random.default_rng(C)
+    mask = rng.random((C, H, W)).astype(np.float32)
+    mask[0, 10:30, 10:30] += 1.0
+    ref_map, ref_q = D.densecrf(img, torch.from_numpy(mask), return_q=True)
+    got_map, got_q = R.densecrf(img, torch.from_numpy(mask), return_q=True)
+    assert np.allclose(got_q.sum(0), 1.0, atol=1e-5)
+    err = np.abs(got_q - ref_q) / np.maximum(np.abs(ref_q), 1e-6)
+    assert err.max() < 1e-3, "max relative error of the CRF marginals %g" % err.max()
+    assert (got_map != ref_map).mean() <= 1e-3
+
+
+def test_pydensecrf_surface(dev, D):
+    """The DenseCRF2D / unary_from_softmax call sequence of DRV:1063-1072 against the oracle's twin class."""
+    from pnp_ovss_b200 import reference_api as R
+    H, W, C = 36, 52, 3
+    img = synth.guide_image(2, H, W)
+    p = np.random.default_rng(3).random((C, H, W)).astype(np.float32)
+    p /= p.sum(0, keepdims=True)
+    outs = []
+    for mod in (D, R):
+        U = np.ascontiguousarray(mod.unary_from_softmax(p))
+        d = mod.DenseCRF2D(W, H, C)
+        d.setUnaryEnergy(U)
+        d.addPairwiseGaussian(sxy=3, compat=7)
+        d.addPairwiseBilateral(sxy=50, srgb=5, rgbim=img, compat=10)
+        outs.append(np.array(d.inference(10)).reshape(C, H, W))
+    err = np.abs(outs[1] - outs[0]) / np.maximum(np.abs(outs[0]), 1e-6)
+    assert err.max() < 1e-3
+    with pytest.raises(ValueError):
+        R.DenseCRF2D(W, H, C).setUnaryEnergy(np.zeros((C, H * W), np.float64))
+
+
+# ------------------------------------------------------------------------------------------------ driver cases
+@pytest.mark.parametrize("tag", list(DRIVER_CASES))
+def test_driver_cases_blur_vs_reference_golden(dev, golden, tag):
+    """save_img_union_attention of the REAL reference (--postprocess blur) vs the CUDA pipeline: confusion matrices."""
+    h0, hagg = smoke_case.run_gpu(tag, "blur", dev)
+    k0, kagg = "drv_%s_hist_withfiltered_caption" % tag, "drv_%s_all_drop_hist_with_filtered_caption" % tag
+    assert np.array_equal(h0, golden[k0]), "round-0 matrix differs by %g" % smoke_case.disagreement(h0, golden[k0])
+    if hagg is not None:
+        assert np.array_equal(hagg, golden[kagg]), "all-drop matrix differs by %g" % smoke_case.disagreement(hagg, golden[kagg])
+    else:
+        assert kagg not in golden.files
+
+
+@pytest.mark.parametrize("tag", ["voc_r4", "ade_r2"])
+def test_driver_cases_blur_crf_vs_oracle(dev, tag):
+    g0, gagg = smoke_case.run_gpu(tag, "blur+crf", dev)
+    o0, oagg = smoke_case.run_oracle(tag, "blur+crf")
+    assert g0.sum() == o0.sum()
+    assert smoke_case.disagreement(g0, o0) <= 0.005
+    assert smoke_case.disagreement(gagg, oagg) <= 0.005
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties(dev, ops):
+    """BASELINE.json configs[1] shape (B=35, C'=21, 336x336): properties that need no CPU oracle."""
+    from pnp_ovss_b200 import pipeline
+    B, C, P, H, W, n = 35, 20, 21, 336, 336, 21
+    maps = torch.stack([synth.saliency_maps(100 + b, C, P) for b in range(B)]).to(dev)
+    guides = torch.from_numpy(np.stack([synth.guide_image(200 + b, H, W) for b in range(B)])).to(dev)
+    gts = torch.from_numpy(np.stack([synth.gt_labels(300 + b, H, W, n) for b in range(B)])).to(dev)
+    luts = torch.arange(C + 1, dtype=torch.int32, device=dev).repeat(B, 1)
+    hists = []
+    for _ in range(2):
+        hist = torch.zeros((n, n), dtype=torch.int64, device=dev)
+        stats = {}
+        pred = pipeline.postprocess_batch(maps, guides, gts, luts, hist, threshold=0.15, rescale=False, with_background=True,
+                                          mode="blur+crf", n_class=n, return_labels=True, stats=stats)
+        hists.append((hist.clone(), pred.clone()))
+    assert torch.equal(hists[0][0], hists[1][0]) and torch.equal(hists[0][1], hists[1][1])  # run-to-run deterministic
+    valid = ((gts >= 0) & (gts < n)).sum().item()
+    assert hists[0][0].sum().item() == valid                                              # every valid pixel counted once
+    assert 0 <= hists[0][1].min().item() and hists[0][1].max().item() <= C
+    assert stats["M_s"] > 0 and stats["M_b"] >= stats["M_s"]
+    # marginals are a distribution and the filter is linear
+    x = ops.threshold_upsample(maps[:4].contiguous(), H, W, 0.15, False, True)
+    xb, mm = ops.gaussian_blur(x, 0.05 * 336, normalize=False)
+    U = ops.crf_unary_from_maps(xb.view(4, C + 1, H * W), mm)
+    lat_s = ops.build_lattice(H, W, 3.0, device=dev)
+    lat_b = ops.build_lattice(H, W, 50.0, rgb=guides[:4].contiguous(), srgb=5.0)
+    Q, labels = ops.crf_inference([lat_s, lat_b], [7.0, 10.0], U, C + 1, 10)
+    s = Q[:, :, :C + 1].sum(-1)
+    assert torch.allclose(s, torch.ones_like(s), atol=1e-5) and float(Q.min()) >= 0 and float(Q[:, :, C + 1:].abs().max()) == 0
+    assert torch.equal(labels, Q[:, :, :C + 1].argmax(-1).int())
+    a, b2 = torch.rand_like(Q), torch.rand_like(Q)
+    a[:, :, C + 1:] = 0
+    b2[:, :, C + 1:] = 0
+    lhs = ops.crf_filter(lat_b, 2.0 * a + 0.5 * b2)
+    rhs = 2.0 * ops.crf_filter(lat_b, a) + 0.5 * ops.crf_filter(lat_b, b2)
+    assert torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-5)

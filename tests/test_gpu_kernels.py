@@ -1,0 +1,287 @@
+"""GPU parity tests: every CUDA entry point (through the C ABI) against the CPU oracle on the same seeded inputs,
+against the committed golden fixtures, and -- at BASELINE.json sizes -- through size-independent properties.
+
+Tolerances (north_star): integer / index / label work bit-exact; floating point within 1e-3 relative.  Where the
+kernels follow the oracle's fp32 operation order the tests ask for bit equality."""
+import numpy as np
+import pytest
+import torch
+
+import synth
+from make_golden_cases import DRIVER_CASES, MERGE_CASES, VOC_NMS
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-3  # north_star: "within 1e-3 relative (fp32 accumulate)"
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import hotpath
+    return hotpath
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from pnp_ovss_b200 import ops as _ops
+    return _ops
+
+
+def _close(a, b, rtol=RTOL, atol=1e-7):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = ~np.isnan(a)
+    err = np.abs(a[m] - b[m]) - (atol + rtol * np.abs(b[m]))
+    assert (err <= 0).all(), "max violation %g (max abs diff %g)" % (err.max(), np.abs(a[m] - b[m]).max())
+
+
+# ------------------------------------------------------------------------------------------------ (a)
+@pytest.mark.parametrize("K", [442, 785, 1025, 33])
+def test_softmax_fwd(dev, ops, O, K):
+    g = torch.Generator().manual_seed(K)
+    s = torch.randn(3, 12, 7, K, generator=g) * 8
+    ref = O.cross_attention_probs(s, None, head_size=64)
+    out = ops.softmax_fwd(s.to(dev), None, 0.125)
+    _close(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-12)
+    mask = torch.zeros(3, K)
+    mask[:, -5:] = -10000.0
+    ref = O.cross_attention_probs(s, mask.view(3, 1, 1, K), head_size=64)
+    out = ops.softmax_fwd(s.to(dev), mask.to(dev), 0.125)
+    _close(out.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-12)
+    assert torch.allclose(out.sum(-1).cpu(), torch.ones(3, 12, 7), atol=1e-5)
+
+
+def test_softmax_fwd_golden(dev, ops, golden):
+    s = torch.from_numpy(golden["gc_scores_scaled"]).to(dev)
+    out = ops.softmax_fwd(s.contiguous(), None, 1.0)
+    _close(out.cpu().numpy(), golden["gc_probs"], rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("K,T", [(442, 9), (785, 5)])
+def test_softmax_bwd_gradcam(dev, ops, O, K, T):
+    g = torch.Generator().manual_seed(7 * K + T)
+    B, h = 4, 12
+    probs = torch.softmax(torch.randn(B, h, T, K, generator=g), -1)
+    dprobs = torch.randn(B, h, T, K, generator=g) * 1e-3
+    mask = torch.zeros(B, 500, dtype=torch.int64)
+    for b in range(B):
+        mask[b, :T - b] = 1
+    P = int(round((K - 1) ** 0.5))
+    ref_cam = O.gradcam_head(probs, dprobs, mask, P, 9)
+    ref_ds = O.softmax_backward(probs, dprobs)
+    ds, cam = ops.softmax_bwd_gradcam(probs.to(dev), dprobs.to(dev), mask.to(dev), 9, 0.125, True, True)
+    assert np.array_equal(cam.cpu().numpy().reshape(ref_cam.shape), ref_cam.numpy())  # same products, same order
+    _close(ds.cpu().numpy(), ref_ds.numpy(), rtol=1e-4, atol=1e-10)
+    ds2, cam2 = ops.softmax_bwd_gradcam(probs.to(dev), dprobs.to(dev), mask.to(dev), 9, 0.125, False, True)
+    assert ds2 is None and torch.equal(cam2, cam)
+    ds3, cam3 = ops.softmax_bwd_gradcam(probs.to(dev), dprobs.to(dev), None, 0, 0.125, True, False)
+    assert cam3 is None and torch.equal(ds3, ds)
+
+
+def test_gradcam_golden(dev, ops, golden):
+    probs = torch.from_numpy(golden["gc_probs"]).to(dev)
+    dprobs = torch.from_numpy(golden["gc_dprobs"]).to(dev)
+    m500 = torch.from_numpy(golden["gc_mask500"]).to(dev)
+    for head in (9, 0):
+        _, cam = ops.softmax_bwd_gradcam(probs, dprobs, m500, head, 0.5, False, True)
+        want = golden["gc_head%d" % head]
+        assert np.array_equal(cam.cpu().numpy().reshape(want.shape), want)
+
+
+def test_softmax_autograd_function_matches_torch(dev):
+    """The autograd.Function used inside the model's block-8 cross-attention: forward and both gradients."""
+    from pnp_ovss_b200.blip_itm import FusedXattnSoftmax, GradcamCapture
+    g = torch.Generator().manual_seed(5)
+    B, h, T, K = 2, 12, 6, 442
+    s = torch.randn(B, h, T, K, generator=g).to(dev).requires_grad_(True)
+    v = torch.randn(B, h, K, 64, generator=g).to(dev)
+    mask = torch.ones(B, 500, dtype=torch.int64, device=dev)
+    cap = GradcamCapture(head=9, token_mask=mask)
+    p = FusedXattnSoftmax.apply(s, None, 0.125, cap)
+    loss = (p @ v).square().sum()
+    loss.backward()
+    s2 = s.detach().clone().requires_grad_(True)
+    p2 = torch.softmax(s2 * 0.125, -1)
+    p2.retain_grad()
+    ((p2 @ v).square().sum()).backward()
+    _close(p.detach().cpu().numpy(), p2.detach().cpu().numpy(), rtol=1e-5, atol=1e-12)
+    _close(s.grad.cpu().numpy(), s2.grad.cpu().numpy(), rtol=1e-3, atol=1e-6)
+    want = (p2.detach()[:, 9, 1:, 1:] * p2.grad[:, 9, 1:, 1:].clamp(0))
+    _close(cap.gradcam.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ (b)
+def test_token_merge_golden(dev, ops, O, golden):
+    from pnp_ovss_b200 import host
+    tok = synth.SyntheticWordPieceTokenizer()
+    for class_lists in MERGE_CASES.values():
+        for cl in class_lists:
+            tok("A picture of " + " ".join(cl))
+    for name, class_lists in MERGE_CASES.items():
+        ids = golden["merge_%s_ids" % name]
+        g = torch.from_numpy(golden["merge_%s_g" % name]).to(dev)
+        B = len(class_lists)
+        Cmax = max(len(c) for c in class_lists)
+        start = np.zeros((B, Cmax), np.int32)
+        length = np.zeros((B, Cmax), np.int32)
+        div = np.ones((B, Cmax), np.float32)
+        for b, cl in enumerate(class_lists):
+            segs = host.build_token_segments(host.token_strings(ids[b], tok.decode), len(cl))
+            for c, (s, l, d) in enumerate(segs):
+                start[b, c], length[b, c], div[b, c] = s, l, d
+        out = ops.token_merge(g, torch.from_numpy(start).to(dev), torch.from_numpy(length).to(dev), torch.from_numpy(div).to(dev))
+        for b, cl in enumerate(class_lists):
+            assert np.array_equal(out[b, :len(cl)].cpu().numpy(), golden["merge_%s_out%d" % (name, b)]), (name, b)
+
+
+# ------------------------------------------------------------------------------------------------ (c)
+def _gpu_dropout(dev, fn, rows, imgs, R, P):
+    from pnp_ovss_b200.pipeline import salience_dropout_loop
+    x = imgs.clone().to(dev)
+    return salience_dropout_loop(lambda t: fn(t.cpu(), rows).to(dev), x, None, R, P), x
+
+
+def test_dropout_loop_golden(dev, golden):
+    imgs = torch.from_numpy(golden["drop_imgs"])
+    rows = torch.from_numpy(golden["drop_rows"])
+    T = int(golden["drop_T"])
+    B, P = imgs.shape[0], 6
+    for R in (1, 4):
+        fn = synth.SynthGradcamFn(21, B, T, P)
+        (g0, agg, chosen), _ = _gpu_dropout(dev, fn, rows, imgs, R, P)
+        assert np.array_equal(g0.cpu().numpy(), golden["drop_R%d_g0" % R])
+        if R > 1:
+            assert np.array_equal(agg.cpu().numpy(), golden["drop_R%d_agg" % R])
+            assert chosen.shape == (B, 10 * R) and int(chosen.min()) >= 0
+
+
+@pytest.mark.parametrize("P,S", [(21, 336), (28, 448)])
+def test_dropout_loop_vs_oracle(dev, O, P, S):
+    B, T, R = 3, 9, 4
+    g = torch.Generator().manual_seed(P)
+    imgs = torch.randn(B, 3, S, S, generator=g)
+    rows = torch.ones(B, T - 1)
+    rows[1, -2:] = 0  # a shorter caption: its SEP row stays in the score (quirk a4)
+    fn_o = synth.SynthGradcamFn(3, B, T, P)
+    g0_o, agg_o, chosen_o, dropped_o = O.salience_dropout(lambda x: fn_o(x, rows), imgs, R, P, argsort_kind="stable")
+    fn_g = synth.SynthGradcamFn(3, B, T, P)
+    (g0, agg, chosen), x = _gpu_dropout(dev, fn_g, rows, imgs, R, P)
+    assert np.array_equal(g0.cpu().numpy(), g0_o.numpy())
+    assert np.array_equal(agg.cpu().numpy(), agg_o.numpy())
+    ch = chosen.cpu().numpy()
+    for b in range(B):
+        for r in range(R):  # same set per round (order inside a round is ascending score in both)
+            assert sorted(ch[b, 10 * r:10 * r + 10].tolist()) == sorted(chosen_o[b][10 * r:10 * r + 10]), (b, r)
+    # after the last round the image carries every chosen block zeroed (the reference re-zeroes at the next round start)
+    want = dropped_o[-1].clone()
+    for b in range(B):
+        for idx in chosen_o[b][-10:]:
+            want[b, :, (idx // P) * 16:(idx // P) * 16 + 16, (idx % P) * 16:(idx % P) * 16 + 16] = 0
+    assert torch.equal(x.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------------ (d)
+@pytest.mark.parametrize("rescale", [False, True])
+@pytest.mark.parametrize("bg", [False, True])
+@pytest.mark.parametrize("shape", [(21, 336, 336), (21, 375, 500), (28, 97, 131)])
+def test_threshold_upsample(dev, ops, O, rescale, bg, shape):
+    P, H, W = shape
+    C = 5
+    maps = torch.stack([synth.saliency_maps(10 + i, C, P) for i in range(2)])
+    maps[1, 2] = 0  # an all-zero class map: 0/0 min-max -> NaN -> nothing kept (and NaN channel when rescaled)
+    out = ops.threshold_upsample(maps.to(dev), H, W, 0.15, rescale, bg).cpu()
+    for b in range(2):
+        with np.errstate(all="ignore"):
+            ref = O.threshold_upsample(maps[b].clone(), 0.15, (H, W), rescale, bg).float()
+        _close(out[b].numpy(), ref.numpy(), rtol=1e-5, atol=1e-7)
+        if bg:
+            assert np.array_equal(out[b, 0].numpy(), ref[0].numpy())  # the background mask is bit-exact
+
+
+def test_threshold_upsample_single_class(dev, ops, O):
+    maps = synth.saliency_maps(3, 1, 21).unsqueeze(0)
+    out = ops.threshold_upsample(maps.to(dev), 120, 160, 0.15, True, True).cpu()
+    ref = O.threshold_upsample(maps[0].clone(), 0.15, (120, 160), True, True).float()
+    _close(out[0].numpy(), ref.numpy(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape", [(336, 336), (375, 500), (64, 48), (20, 30), (512, 512)])
+def test_gaussian_blur_vs_scipy(dev, ops, O, shape):
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    x = rng.random((3, H, W)).astype(np.float32)
+    x[1] = (x[1] > 0.7).astype(np.float32)  # a binary map like the background channel
+    sigma = 0.05 * max(H, W)
+    out, mm = ops.gaussian_blur(torch.from_numpy(x).to(dev), sigma, normalize=True)
+    raw, mm2 = ops.gaussian_blur(torch.from_numpy(x).to(dev), sigma, normalize=False)
+    for i in range(3):
+        ref = O.blurring(torch.from_numpy(x[i]), (H, W))
+        _close(out[i].cpu().numpy(), ref, rtol=RTOL, atol=2e-6)
+    assert torch.equal(mm, mm2)
+    assert torch.allclose(raw.amin((1, 2)), mm[:, 0]) and torch.allclose(raw.amax((1, 2)), mm[:, 1])
+
+
+def test_gaussian_blur_golden(dev, ops, golden):
+    for tag in ("a", "b"):
+        x = golden["blur_%s_in" % tag]
+        out, _ = ops.gaussian_blur(torch.from_numpy(x).to(dev).unsqueeze(0), 0.05 * max(x.shape), normalize=True)
+        _close(out[0].cpu().numpy(), golden["blur_%s_out" % tag], rtol=RTOL, atol=2e-6)
+
+
+def test_gaussian_blur_constant_map_is_nan(dev, ops):
+    """A constant map blurs to a constant: (y-min)/(max-min) = 0/0 = NaN everywhere, like the reference (DRV:1151-1152)."""
+    x = torch.zeros(1, 64, 64, device=dev)
+    out, _ = ops.gaussian_blur(x, 3.2, normalize=True)
+    assert bool(torch.isnan(out).all())
+
+
+# ------------------------------------------------------------------------------------------------ (f)
+@pytest.mark.parametrize("n_class", [21, 183, 300])
+def test_confusion_matrix(dev, ops, O, n_class):
+    rng = np.random.default_rng(n_class)
+    B, H, W = 3, 120, 97
+    gt = np.stack([synth.gt_labels(5 + b, H, W, n_class) for b in range(B)])
+    gt[0, :3, :3] = -1.0
+    gt[1, 0, 0] = float(n_class)
+    labels = rng.integers(0, 7, (B, H * W)).astype(np.int32)
+    lut = np.stack([rng.permutation(n_class)[:7] for _ in range(B)]).astype(np.int32)
+    hist = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
+    pred = torch.empty((B, H * W), dtype=torch.float32, device=dev)
+    ops.confusion_accumulate(torch.from_numpy(labels).to(dev), torch.from_numpy(gt).view(B, -1).to(dev), n_class, hist,
+                             lut=torch.from_numpy(lut).to(dev), pred_out=pred)
+    want = np.zeros((n_class, n_class), dtype=np.int64)
+    for b in range(B):
+        p = lut[b][labels[b]]
+        want += O.fast_hist(gt[b].flatten(), p.astype(np.float32), n_class)
+        assert np.array_equal(pred[b].cpu().numpy(), p.astype(np.float32))
+    assert np.array_equal(hist.cpu().numpy(), want)
+
+
+def test_confusion_golden(dev, golden):
+    from pnp_ovss_b200 import reference_api as R
+    n = int(golden["hist_n"])
+    gt, pred = golden["hist_gt"], golden["hist_pred"]
+    assert np.array_equal(R._fast_hist(gt.flatten(), pred.flatten(), n), golden["hist_out"])
+    table, hist = R.scores([gt, gt.T.copy()], [pred, pred.T.copy()], None, n)
+    assert np.array_equal(hist, golden["scores_hist"])
+    assert table["Mean IoU"] == float(golden["scores_miou"])
+
+
+def test_argmax_channels(dev, ops):
+    rng = np.random.default_rng(0)
+    for N in (336 * 336, 1001):
+        x = rng.random((2, 21, N)).astype(np.float32)
+        x[0, 3, :50] = x[0, 7, :50] = 2.0     # ties: first wins
+        x[1, 5, 10:20] = np.nan               # NaN counts as the maximum
+        x[1, 2, 15:20] = np.nan               # ... and the first NaN wins
+        out = ops.argmax_channels(torch.from_numpy(x).to(dev)).cpu().numpy()
+        assert np.array_equal(out, np.argmax(x, axis=1).astype(np.int32))

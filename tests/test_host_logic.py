@@ -1,0 +1,132 @@
+"""CPU: host-side logic of the product (token segment tables, relabel LUT, sharding, metric arithmetic) against the
+oracle and the reference-generated golden fixtures; and the 2-rank confusion-matrix all-reduce over gloo."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from make_golden_cases import MERGE_CASES
+from oracle import hotpath as O
+from pnp_ovss_b200 import host
+
+
+def _emulate_merge(g, segs):
+    """What pnp_token_merge computes, in numpy fp32 (sequential adds, one division)."""
+    rows = g[3:-1] if False else g[3:]
+    out = np.zeros((len(segs),) + g.shape[1:], np.float32)
+    for c, (s, l, d) in enumerate(segs):
+        if l == 0:
+            continue
+        acc = rows[s].copy()
+        for i in range(1, l):
+            acc = (acc + rows[s + i]).astype(np.float32)
+        out[c] = acc / np.float32(d) if d != 1.0 else acc
+    return out
+
+
+def test_token_segments_reproduce_reference_merge(golden):
+    tok = synth.SyntheticWordPieceTokenizer()
+    for class_lists in MERGE_CASES.values():
+        for cl in class_lists:
+            tok("A picture of " + " ".join(cl))
+    for name, class_lists in MERGE_CASES.items():
+        ids = golden["merge_%s_ids" % name]
+        g = golden["merge_%s_g" % name]
+        for b, cl in enumerate(class_lists):
+            toks = host.token_strings(ids[b], tok.decode)
+            assert toks == O.token_strings(ids[b], tok.decode)
+            segs = host.build_token_segments(toks, len(cl))
+            assert max(s + l for s, l, _ in segs) <= g.shape[1] - 4   # stays inside the [3:-1] slice
+            assert np.array_equal(_emulate_merge(g[b], segs), golden["merge_%s_out%d" % (name, b)]), (name, b)
+
+
+def test_token_segments_quirks():
+    # split word last: summed, never divided (DRV:844-847)
+    assert host.build_token_segments(["dog", "aero", "##plan", "##e"], 2) == [(0, 1, 1.0), (1, 3, 1.0)]
+    # split word followed by another word: averaged
+    assert host.build_token_segments(["aero", "##plan", "##e", "dog"], 2) == [(0, 3, 3.0), (3, 1, 1.0)]
+    # as many pieces as classes: rows taken as they are (DRV:852), even if some are continuations
+    assert host.build_token_segments(["pot", "##ted"], 2) == [(0, 1, 1.0), (1, 1, 1.0)]
+    with pytest.raises(IndexError):
+        host.build_token_segments(["a", "b", "c", "d"], 2)
+
+
+def test_relabel_lut_matches_sequential_relabel():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        C = int(rng.integers(1, 7))
+        ids = [int(v) for v in rng.integers(1, 9, C)]
+        for with_bg in (True, False):
+            n = C + (1 if with_bg else 0)
+            m = rng.integers(0, n, (6, 7)).astype(np.float32)
+            want = O.relabel_sequential(m.copy(), ids, with_bg)
+            lut = host.relabel_lut(ids, with_bg)
+            assert np.array_equal(np.asarray(lut, np.float32)[m.astype(int)], want)
+    assert host.relabel_lut([2, 1], True) == [0, 2, 2]  # the aliasing quirk (a9)
+
+
+def test_background_rule_and_sharding():
+    assert host.add_background_rule("voc", 5) and host.add_background_rule("coco_object", 9)
+    assert host.add_background_rule("ade20k", 2) and not host.add_background_rule("ade20k", 3)
+    assert not host.add_background_rule("coco_stuff", 4) and host.add_background_rule("psc", 1)
+    for n, w in ((35, 8), (7, 2), (3, 4), (1449, 8)):
+        spans = [host.shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))            # contiguous, nothing counted twice
+        assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+
+
+def test_metrics_from_hist_matches_reference(golden):
+    from pnp_ovss_b200.reference_api import metrics_from_hist
+    table, _ = metrics_from_hist(golden["scores_hist"])
+    assert table["Mean IoU"] == float(golden["scores_miou"])
+    assert table["Pixel Accuracy"] == float(golden["scores_acc"])
+    assert table["Frequency Weighted IoU"] == float(golden["scores_fwiou"])
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    from pnp_ovss_b200 import pipeline
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    n = 21
+    rng = np.random.default_rng(100 + rank)
+    s, e = host.shard_range(7, rank, world)
+    hist = torch.zeros((n, n), dtype=torch.int64)
+    for img in range(s, e):
+        gt = synth.gt_labels(img, 40, 36, n)
+        pred = np.random.default_rng(img).integers(0, n, gt.shape)
+        hist += torch.from_numpy(O.fast_hist(gt.flatten(), pred.flatten(), n))
+    pipeline.allreduce_hist(hist)
+    if rank == 0:
+        np.save(out, hist.numpy())
+    dist.destroy_process_group()
+
+
+def test_allreduce_hist_two_ranks_gloo(tmp_path):
+    """N>1 path on CPU: two ranks shard 7 images, all-reduce their int64 matrices, rank 0 holds the global matrix."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "hist.npy")
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    n = 21
+    want = np.zeros((n, n), np.int64)
+    for img in range(7):
+        gt = synth.gt_labels(img, 40, 36, n)
+        pred = np.random.default_rng(img).integers(0, n, gt.shape)
+        want += O.fast_hist(gt.flatten(), pred.flatten(), n)
+    assert np.array_equal(np.load(out), want)
+
+
+def test_save_hist_npy_layout(tmp_path):
+    from pnp_ovss_b200 import pipeline
+    h = torch.arange(9, dtype=torch.int64).view(3, 3)
+    p = pipeline.save_hist_npy(h, str(tmp_path), "all_drop_hist_with_filtered_caption", "2007_000033", 8, 9)
+    assert p.endswith("all_drop_hist_with_filtered_caption/img_2007_000033_max_blocknum_8_atthead_9.npy")
+    back = np.load(p)
+    assert back.dtype == np.float64 and np.array_equal(back, h.numpy())
