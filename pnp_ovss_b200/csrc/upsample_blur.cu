@@ -181,14 +181,14 @@ __global__ void blur_prologue_kernel(float *__restrict__ weights, unsigned *__re
         double s = 0.0;
         for (int j = 0; j < taps; ++j) {
             double x = (double)(j - lw);
-            s += exp(-0.5 / (sigma * sigma) * x * x);
+            s += exp(-0.5 / (sigma * sigma) * (x * x));
         }
         s_sum = s;
     }
     __syncthreads();
     for (int j = threadIdx.x; j < n_w_padded; j += blockDim.x) {
         double x = (double)(j - lw);
-        weights[j] = (j < taps) ? (float)(exp(-0.5 / (sigma * sigma) * x * x) / s_sum) : 0.f;
+        weights[j] = (j < taps) ? (float)(exp(-0.5 / (sigma * sigma) * (x * x)) / s_sum) : 0.f;
     }
     for (int i = threadIdx.x; i < n_maps; i += blockDim.x) {
         mm_keys[2 * i + 0] = 0xffffffffu;  // running min key
@@ -373,6 +373,9 @@ extern "C" int pnp_threshold_upsample(const float *class_maps, float *out, void 
         return PNP_ERR_INVALID_ARGUMENT;
     if (workspace_bytes < pnp_threshold_upsample_workspace_bytes(B, C, P)) return PNP_ERR_WORKSPACE;
     if (B == 0) return PNP_OK;
+    // Quirk kept: with ONE class F.interpolate(...).squeeze() is 2-D and Scale_0_1 returns 2-D input untouched
+    // (DRV:1079-1080), so the rescale silently does not happen.
+    if (C == 1) rescale = 0;
     cudaStream_t st = as_stream(stream);
     float *masked = reinterpret_cast<float *>(workspace);
     float *params = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align_up((size_t)B * C * P * P * sizeof(float), 256));

@@ -223,9 +223,14 @@ def test_gaussian_blur_vs_scipy(dev, ops, O, shape):
     sigma = 0.05 * max(H, W)
     out, mm = ops.gaussian_blur(torch.from_numpy(x).to(dev), sigma, normalize=True)
     raw, mm2 = ops.gaussian_blur(torch.from_numpy(x).to(dev), sigma, normalize=False)
+    from scipy.ndimage import gaussian_filter
     for i in range(3):
+        # raw blur: fp32 accumulation over up to 205 taps against scipy's float64 accumulators
+        _close(raw[i].cpu().numpy(), gaussian_filter(x[i], sigma), rtol=5e-6, atol=1e-7)
+        # after (y-min)/(max-min) the same absolute error is divided by the map's dynamic range (tiny for iid noise),
+        # so the normalised map is compared at 1e-3 relative plus 1e-4 of its unit range
         ref = O.blurring(torch.from_numpy(x[i]), (H, W))
-        _close(out[i].cpu().numpy(), ref, rtol=RTOL, atol=2e-6)
+        _close(out[i].cpu().numpy(), ref, rtol=RTOL, atol=1e-4)
     assert torch.equal(mm, mm2)
     assert torch.allclose(raw.amin((1, 2)), mm[:, 0]) and torch.allclose(raw.amax((1, 2)), mm[:, 1])
 
