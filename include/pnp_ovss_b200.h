@@ -205,6 +205,20 @@ int pnp_confusion_accumulate(const int32_t *labels, const float *gt, const int32
                              float *pred_out, int64_t *hist, int32_t *bad_count, int B, int N, int n_class,
                              pnp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * In-situ kernel timing for bench.py's roofline (the one piece of process-global state in the library):
+ * between start and stop, every launch of a kernel class whose bit is set in kernel_mask is bracketed by
+ * CUDA events recorded on the launch's own stream.  Kernel ids: 1 softmax_fwd, 2 softmax_bwd_gradcam,
+ * 3 token_merge, 4 salience_dropout_round, 5 threshold_prep, 6 upsample_write, 7 blur_vertical,
+ * 8 blur_horizontal, 9 blur_normalize, 10 lattice_build (all of it), 11 crf_unary, 12 crf_splat_bilateral,
+ * 13 crf_blur_axis_bilateral, 14 crf_meanfield_update, 15 argmax_channels, 16 confusion, 17 crf_splat_spatial,
+ * 18 crf_blur_axis_spatial.
+ * ---------------------------------------------------------------------------------------------------- */
+int pnp_profile_start(unsigned kernel_mask);
+/* Waits for the recorded events; total_ms[id] / n_launches[id] for id < n_ids (host arrays). */
+int pnp_profile_stop(float *total_ms, int *n_launches, int n_ids);
+const char *pnp_profile_kernel_name(int kernel_id);
+
 #ifdef __cplusplus
 }
 #endif

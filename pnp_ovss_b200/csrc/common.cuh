@@ -63,4 +63,29 @@ __device__ __forceinline__ unsigned f2key_min(float f) { return (f != f) ? 0u : 
 __device__ __forceinline__ float nan_min(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fminf(a, b); }
 __device__ __forceinline__ float nan_max(float a, float b) { return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b); }
 
+
+// ---- optional in-situ kernel timing (pnp_profile_*): bench.py brackets the launches of selected kernel classes
+// with CUDA events on their own stream, inside the timed region.  Off (mask 0) it costs one predictable branch.
+enum KernelId {
+    kSoftmaxFwd = 1, kSoftmaxBwdGradcam = 2, kTokenMerge = 3, kDropoutRound = 4, kThresholdPrep = 5, kUpsampleWrite = 6,
+    kBlurVertical = 7, kBlurHorizontal = 8, kBlurNormalize = 9, kLatticeBuild = 10, kCrfUnary = 11, kSplatBilateral = 12,
+    kBlurAxisBilateral = 13, kMeanfieldUpdate = 14, kArgmax = 15, kConfusion = 16, kSplatSpatial = 17, kBlurAxisSpatial = 18,
+    kNumKernelIds = 19
+};
+namespace prof {
+extern unsigned g_mask;
+void begin(int id, cudaStream_t st);
+void end(int id, cudaStream_t st);
+}  // namespace prof
+#define PNP_LAUNCH(id, st, ...)                         \
+    do {                                                \
+        if (pnp::prof::g_mask & (1u << (id))) {         \
+            pnp::prof::begin((id), (st));               \
+            __VA_ARGS__;                                \
+            pnp::prof::end((id), (st));                 \
+        } else {                                        \
+            __VA_ARGS__;                                \
+        }                                               \
+    } while (0)
+
 }  // namespace pnp

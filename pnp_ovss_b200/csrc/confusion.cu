@@ -123,11 +123,11 @@ extern "C" int pnp_argmax_channels(const float *maps, int32_t *labels, int B, in
     if (vec) {
         long long total4 = (long long)B * (N / 4);
         int grid = (int)min((long long)kNumSMs * 16, (total4 + 255) / 256);
-        argmax_channels_vec4<<<grid, 256, 0, st>>>(maps, labels, C, N / 4, total4);
+        PNP_LAUNCH(kArgmax, st, argmax_channels_vec4<<<grid, 256, 0, st>>>(maps, labels, C, N / 4, total4));
     } else {
         long long total = (long long)B * N;
         int grid = (int)min((long long)kNumSMs * 16, (total + 255) / 256);
-        argmax_channels_scalar<<<grid, 256, 0, st>>>(maps, labels, C, N, total);
+        PNP_LAUNCH(kArgmax, st, argmax_channels_scalar<<<grid, 256, 0, st>>>(maps, labels, C, N, total));
     }
     return launch_status();
 }
@@ -147,13 +147,13 @@ extern "C" int pnp_confusion_accumulate(const int32_t *labels, const float *gt, 
             if (e != cudaSuccess) return cuda_err(e);
             grid = (int)min((long long)kNumSMs, (total + 511) / 512);
         }
-        confusion_kernel<true><<<grid, 512, smem, st>>>(labels, gt, lut, lut_stride, pred_out,
+        PNP_LAUNCH(kConfusion, st, confusion_kernel<true><<<grid, 512, smem, st>>>(labels, gt, lut, lut_stride, pred_out,
                                                          reinterpret_cast<unsigned long long *>(hist), bad_count, N, total,
-                                                         n_class);
+                                                         n_class));
     } else {
-        confusion_kernel<false><<<grid, 512, 0, st>>>(labels, gt, lut, lut_stride, pred_out,
+        PNP_LAUNCH(kConfusion, st, confusion_kernel<false><<<grid, 512, 0, st>>>(labels, gt, lut, lut_stride, pred_out,
                                                       reinterpret_cast<unsigned long long *>(hist), bad_count, N, total,
-                                                      n_class);
+                                                      n_class));
     }
     return launch_status();
 }

@@ -295,10 +295,12 @@ static const float *run_splat_blur(const LatticeView &L, const float *x, float *
     const int nch = Cp / 4;
     const int gy = L.shared ? B : 1;
     const int gx = std::max(1, grid_for((long long)(L.M + 1) * nch, 256) / (L.shared ? std::min(B, 8) : 1));
-    splat_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, x, va, Cp, normalized);
+    const int id_splat = L.shared ? kSplatSpatial : kSplatBilateral;
+    const int id_blur = L.shared ? kBlurAxisSpatial : kBlurAxisBilateral;
+    PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, x, va, Cp, normalized));
     float *src = va, *dst = vb;
     for (int j = 0; j < L.Dp1; ++j) {
-        blur_axis_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, src, dst, j, Cp);
+        PNP_LAUNCH(id_blur, st, blur_axis_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, src, dst, j, Cp));
         std::swap(src, dst);
     }
     return src;
@@ -375,16 +377,16 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
     // Q0 = softmax(-U)
     P.n_kernels = 0;
     if (n_iter == 0 && labels)
-        meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp);
+        PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
     else
-        meanfield_update_kernel<false><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp);
+        PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<false><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
     for (int it = 0; it < n_iter; ++it) {
         for (int k = 0; k < n_kernels; ++k) P.values[k] = run_splat_blur(P.lat[k], Q, va[k], vb[k], B, Cp, 1, st);
         P.n_kernels = n_kernels;
         if (it == n_iter - 1 && labels)
-            meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp);
+            PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
         else
-            meanfield_update_kernel<false><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp);
+            PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<false><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
     }
     return launch_status();
 }
@@ -397,7 +399,8 @@ extern "C" int pnp_crf_unary_from_maps(const float *maps, const float *minmax, f
     if (smem > 200 * 1024) return PNP_ERR_INVALID_ARGUMENT;
     cudaError_t e = cudaFuncSetAttribute(unary_from_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_err(e);
-    unary_from_maps_kernel<<<dim3(ceil_div(N, kUnaryPix), B), kUnaryPix, smem, as_stream(stream)>>>(maps, minmax, unary, C, Cp, N);
+    cudaStream_t st = as_stream(stream);
+    PNP_LAUNCH(kCrfUnary, st, unary_from_maps_kernel<<<dim3(ceil_div(N, kUnaryPix), B), kUnaryPix, smem, st>>>(maps, minmax, unary, C, Cp, N));
     return launch_status();
 }
 

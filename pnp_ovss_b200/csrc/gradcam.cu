@@ -99,8 +99,9 @@ extern "C" int pnp_token_merge(const float *gradcam, const int32_t *seg_start, c
         return PNP_ERR_INVALID_ARGUMENT;
     if (B == 0 || C == 0) return PNP_OK;
     if (B > 65535) return PNP_ERR_INVALID_ARGUMENT;
-    token_merge_kernel<<<dim3(C, B), 256, 0, as_stream(stream)>>>(gradcam, seg_start, seg_len, seg_div, class_maps, Tm, PP, C,
-                                                                  row_offset);
+    cudaStream_t st = as_stream(stream);
+    PNP_LAUNCH(kTokenMerge, st, token_merge_kernel<<<dim3(C, B), 256, 0, st>>>(gradcam, seg_start, seg_len, seg_div, class_maps, Tm, PP,
+                                                                               C, row_offset));
     return launch_status();
 }
 
@@ -112,8 +113,9 @@ extern "C" int pnp_salience_dropout_round(const float *gradcam, float *ensemble_
         save_len > P * P || n_prev < 0 || n_prev + save_len > chosen_stride || row_lo < 0 || row_hi > Tm || round < 0)
         return PNP_ERR_INVALID_ARGUMENT;
     if (B == 0) return PNP_OK;
-    salience_dropout_round_kernel<<<B, 512, 0, as_stream(stream)>>>(gradcam, ensemble_r, agg, chosen, chosen_stride, n_prev,
-                                                                    imgs, norm_imgs, Tm, P, patch, row_lo, row_hi, save_len,
-                                                                    round);
+    cudaStream_t st = as_stream(stream);
+    PNP_LAUNCH(kDropoutRound, st, salience_dropout_round_kernel<<<B, 512, 0, st>>>(gradcam, ensemble_r, agg, chosen, chosen_stride,
+                                                                                   n_prev, imgs, norm_imgs, Tm, P, patch, row_lo,
+                                                                                   row_hi, save_len, round));
     return launch_status();
 }

@@ -601,6 +601,8 @@ static int build_impl(pnp_lattice *lat, const uint8_t *rgb, int H, int W, float 
     auto *vb = reinterpret_cast<float *>(ws + L.off_vb);
 
     cudaError_t e;
+    const bool timed = (prof::g_mask & (1u << kLatticeBuild)) != 0;
+    if (timed) prof::begin(kLatticeBuild, st);
     if ((e = cudaMemsetAsync(table, 0xFF, slots * 8, st)) != cudaSuccess) return cuda_err(e);
     if ((e = cudaMemsetAsync(first, 0x7F, slots * 4, st)) != cudaSuccess) return cuda_err(e);
     if ((e = cudaMemsetAsync(lat->counters, 0, 256, st)) != cudaSuccess) return cuda_err(e);
@@ -647,6 +649,7 @@ static int build_impl(pnp_lattice *lat, const uint8_t *rgb, int H, int W, float 
     const float alpha = 1.0f / (1 + powf(2, -D));
     norm_slice_kernel<<<(int)std::min<long long>((n_lp + 255) / 256, (long long)kNumSMs * 32), 256, 0, st>>>(
         src, lat->offset, lat->bary, lat->norm, n_lp, D + 1, alpha);
+    if (timed) prof::end(kLatticeBuild, st);
     return launch_status();
 }
 

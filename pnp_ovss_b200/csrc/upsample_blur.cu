@@ -379,16 +379,16 @@ extern "C" int pnp_threshold_upsample(const float *class_maps, float *out, void 
     cudaStream_t st = as_stream(stream);
     float *masked = reinterpret_cast<float *>(workspace);
     float *params = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align_up((size_t)B * C * P * P * sizeof(float), 256));
-    threshold_prep_kernel<<<dim3(C, B), 256, 0, st>>>(class_maps, masked, params, C, P, H, W, threshold, rescale);
+    PNP_LAUNCH(kThresholdPrep, st, threshold_prep_kernel<<<dim3(C, B), 256, 0, st>>>(class_maps, masked, params, C, P, H, W, threshold, rescale));
     int rc = launch_status();
     if (rc != PNP_OK) return rc;
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     if (vec) {
         int gx = max(1, min(ceil_div((long long)H * (W / 4), 256), ceil_div(kNumSMs * 8, B)));
-        upsample_write_kernel<4><<<dim3(gx, B), 256, 0, st>>>(masked, params, out, C, P, H, W, rescale, with_background);
+        PNP_LAUNCH(kUpsampleWrite, st, upsample_write_kernel<4><<<dim3(gx, B), 256, 0, st>>>(masked, params, out, C, P, H, W, rescale, with_background));
     } else {
         int gx = max(1, min(ceil_div((long long)H * W, 256), ceil_div(kNumSMs * 8, B)));
-        upsample_write_kernel<1><<<dim3(gx, B), 256, 0, st>>>(masked, params, out, C, P, H, W, rescale, with_background);
+        PNP_LAUNCH(kUpsampleWrite, st, upsample_write_kernel<1><<<dim3(gx, B), 256, 0, st>>>(masked, params, out, C, P, H, W, rescale, with_background));
     }
     return launch_status();
 }
@@ -449,15 +449,15 @@ extern "C" int pnp_gaussian_blur(const float *in, float *out, float *minmax, voi
     e = cudaFuncSetAttribute(blur_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_h);
     if (e != cudaSuccess) return cuda_err(e);
     blur_prologue_kernel<<<1, 256, 0, st>>>(weights, keys, n_maps, p.lw, p.n_w_padded, sigma);
-    blur_vertical_kernel<<<dim3(ceil_div(W, kVCols), ceil_div(H, p.tile_rows), n_maps), kVCols * kVGroups, p.smem_v, st>>>(
-        in, tmp, weights, H, W, p.lw, p.tile_rows, p.n_w_padded);
-    blur_horizontal_kernel<<<dim3(ceil_div(W, p.tile_cols), ceil_div(H, kHRows), n_maps), kHRows * kHGroups, p.smem_h, st>>>(
-        tmp, out, weights, keys, H, W, p.lw, p.tile_cols, p.pitch, p.n_w_padded);
+    PNP_LAUNCH(kBlurVertical, st, blur_vertical_kernel<<<dim3(ceil_div(W, kVCols), ceil_div(H, p.tile_rows), n_maps), kVCols * kVGroups, p.smem_v, st>>>(
+        in, tmp, weights, H, W, p.lw, p.tile_rows, p.n_w_padded));
+    PNP_LAUNCH(kBlurHorizontal, st, blur_horizontal_kernel<<<dim3(ceil_div(W, p.tile_cols), ceil_div(H, kHRows), n_maps), kHRows * kHGroups, p.smem_h, st>>>(
+        tmp, out, weights, keys, H, W, p.lw, p.tile_cols, p.pitch, p.n_w_padded));
     blur_minmax_decode_kernel<<<ceil_div(n_maps, 256), 256, 0, st>>>(keys, minmax, n_maps);
     if (normalize) {
         long long total = (long long)n_maps * H * W;
         int grid = (int)std::min<long long>((long long)kNumSMs * 16, (total + 255) / 256);
-        blur_normalize_kernel<<<grid, 256, 0, st>>>(out, minmax, (long long)H * W, total);
+        PNP_LAUNCH(kBlurNormalize, st, blur_normalize_kernel<<<grid, 256, 0, st>>>(out, minmax, (long long)H * W, total));
     }
     return launch_status();
 }

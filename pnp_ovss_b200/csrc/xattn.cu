@@ -123,9 +123,9 @@ extern "C" int pnp_xattn_softmax_fwd(const float *scores, const float *key_mask,
     cudaStream_t st = as_stream(stream);
     int grid = (int)min((long long)kNumSMs * 8, (n_rows + 7) / 8);
     if (K <= 32 * 16)
-        softmax_fwd_kernel<16><<<grid, 256, 0, st>>>(scores, key_mask, probs, n_rows, heads * T, K, scale);
+        PNP_LAUNCH(kSoftmaxFwd, st, softmax_fwd_kernel<16><<<grid, 256, 0, st>>>(scores, key_mask, probs, n_rows, heads * T, K, scale));
     else
-        softmax_fwd_kernel<36><<<grid, 256, 0, st>>>(scores, key_mask, probs, n_rows, heads * T, K, scale);
+        PNP_LAUNCH(kSoftmaxFwd, st, softmax_fwd_kernel<36><<<grid, 256, 0, st>>>(scores, key_mask, probs, n_rows, heads * T, K, scale));
     return launch_status();
 }
 
@@ -143,18 +143,18 @@ extern "C" int pnp_xattn_softmax_bwd_gradcam(const float *probs, const float *dp
     const bool small = K <= 32 * 16;
     if (full) {
         if (small)
-            softmax_bwd_gradcam_kernel<16, true><<<grid, 256, 0, st>>>(probs, dprobs, dscores, token_mask, token_mask_stride,
-                                                                       gradcam, n_rows, heads, T, K, scale, head);
+            PNP_LAUNCH(kSoftmaxBwdGradcam, st, softmax_bwd_gradcam_kernel<16, true><<<grid, 256, 0, st>>>(probs, dprobs, dscores, token_mask, token_mask_stride,
+                                                                       gradcam, n_rows, heads, T, K, scale, head));
         else
-            softmax_bwd_gradcam_kernel<36, true><<<grid, 256, 0, st>>>(probs, dprobs, dscores, token_mask, token_mask_stride,
-                                                                       gradcam, n_rows, heads, T, K, scale, head);
+            PNP_LAUNCH(kSoftmaxBwdGradcam, st, softmax_bwd_gradcam_kernel<36, true><<<grid, 256, 0, st>>>(probs, dprobs, dscores, token_mask, token_mask_stride,
+                                                                       gradcam, n_rows, heads, T, K, scale, head));
     } else {
         if (small)
-            softmax_bwd_gradcam_kernel<16, false><<<grid, 256, 0, st>>>(probs, dprobs, dscores, token_mask, token_mask_stride,
-                                                                        gradcam, n_rows, heads, T, K, scale, head);
+            PNP_LAUNCH(kSoftmaxBwdGradcam, st, softmax_bwd_gradcam_kernel<16, false><<<grid, 256, 0, st>>>(probs, dprobs, dscores, token_mask, token_mask_stride,
+                                                                        gradcam, n_rows, heads, T, K, scale, head));
         else
-            softmax_bwd_gradcam_kernel<36, false><<<grid, 256, 0, st>>>(probs, dprobs, dscores, token_mask, token_mask_stride,
-                                                                        gradcam, n_rows, heads, T, K, scale, head);
+            PNP_LAUNCH(kSoftmaxBwdGradcam, st, softmax_bwd_gradcam_kernel<36, false><<<grid, 256, 0, st>>>(probs, dprobs, dscores, token_mask, token_mask_stride,
+                                                                        gradcam, n_rows, heads, T, K, scale, head));
     }
     return launch_status();
 }

@@ -71,77 +71,110 @@ class SpatialLatticeCache:
 _SPATIAL = SpatialLatticeCache()
 
 
+def _mark(stats, name):
+    """Stage timing for bench.py: record a CUDA event on the current stream when stats carries an 'events' list."""
+    if stats is not None and "events" in stats:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        stats["events"].append((name, ev))
+
+
 def postprocess_batch(class_maps, guides, gts, luts, hist, *, threshold, rescale, with_background, mode, n_class,
-                      crf=None, bad_count=None, return_labels=False, stats=None):
+                      crf=None, bad_count=None, return_labels=False, stats=None, bilateral=None):
     """class_maps [B,C,P,P] -> labels -> hist (accumulated in place).  guides uint8 [B,H,W,3]; gts float32 [B,H,W];
-    luts int32 [B,C'] (composed relabel tables).  mode: the --postprocess string ('', 'blur', 'crf', 'blur+crf')."""
+    luts int32 [B,C'] (composed relabel tables).  mode: the --postprocess string ('', 'blur', 'crf', 'blur+crf').
+    bilateral: a lattice already built over `guides` (the two reference passes of one batch share it)."""
     B, C = class_maps.shape[:2]
     H, W = gts.shape[1:]
     N = H * W
     x = ops.threshold_upsample(class_maps.contiguous(), H, W, threshold, rescale, with_background)
+    _mark(stats, "upsample")
     Cc = x.shape[1]
     minmax = None
     use_blur = bool(mode) and "blur" in mode
     use_crf = bool(mode) and "crf" in mode
     if use_blur:
         x, minmax = ops.gaussian_blur(x, BLUR_SCALE * max(H, W), normalize=not use_crf)
+        _mark(stats, "blur")
     if use_crf:
         p = dict(CRF_DEFAULTS)
         p.update(crf or {})
         U = ops.crf_unary_from_maps(x.view(B, Cc, N), minmax if use_blur else None)
         del x
+        _mark(stats, "unary")
         lat_s = _SPATIAL.get(H, W, p["pos_xy_std"], U.device)
-        lat_b = ops.build_lattice(H, W, p["bi_xy_std"], rgb=guides, srgb=p["bi_rgb_std"])
+        lat_b = bilateral if bilateral is not None else ops.build_lattice(H, W, p["bi_xy_std"], rgb=guides, srgb=p["bi_rgb_std"])
         if stats is not None:
             stats["M_s"], stats["M_b"], stats["max_row_b"] = lat_s.M, lat_b.M, lat_b.struct.max_row
+        _mark(stats, "lattice")
         _, labels = ops.crf_inference([lat_s, lat_b], [p["pos_w"], p["bi_w"]], U, Cc, p["n_iter"], want_labels=True)
+        _mark(stats, "crf")
     else:
         labels = ops.argmax_channels(x.view(B, Cc, N))
     pred = torch.empty((B, N), dtype=torch.float32, device=labels.device) if return_labels else None
     ops.confusion_accumulate(labels, gts.view(B, N), n_class, hist, lut=luts, pred_out=pred, bad_count=bad_count)
+    _mark(stats, "confusion")
     return pred.view(B, H, W) if return_labels else None
+
+
+def _as_device_batch(items, members, dtype, dev):
+    """items: a device tensor [B,...] (used as is / index-selected) or a list of host arrays (stacked + uploaded)."""
+    if isinstance(items, torch.Tensor) and items.is_cuda:
+        if len(members) == items.shape[0]:
+            return items
+        return items[torch.as_tensor(members, device=dev)].contiguous()
+    return torch.stack([torch.as_tensor(np.ascontiguousarray(items[b])).to(dtype) for b in members]).to(dev)
 
 
 def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_ids, gts, guides, *, drop_iter, patch_num,
                     threshold, data_type, mode, n_class, coco=False, crf=None, norm_imgs=None, stats=None):
-    """One batch of save_img_union_attention: returns (hist_round0 or None, hist_all_drop or None) as int64 CUDA
-    tensors [n,n] -- the matrices the reference saves to hist_withfiltered_caption/ and
+    """One batch of save_img_union_attention: returns (hist_round0 or None, hist_all_drop or None, chosen) with the
+    matrices as int64 CUDA tensors [n,n] -- what the reference saves to hist_withfiltered_caption/ and
     all_drop_hist_with_filtered_caption/ (DRV:495-520).  `coco` selects the COCO driver's deltas (DRVC:420, 527, 602).
 
-    imgs [B,3,S,S] cuda (modified in place by the DropOut rounds); gts list/array of float32 [H,W]; guides list/array
-    of uint8 [H,W,3]; dataset_ids[b][i] = id written for local class i."""
+    imgs [B,3,S,S] cuda (modified in place by the DropOut rounds); gts: float32 [H,W] arrays (list) or one CUDA tensor
+    [B,H,W]; guides: uint8 [H,W,3] arrays (list) or one CUDA tensor [B,H,W,3]; dataset_ids[b][i] = id written for
+    local class i."""
     dev = imgs.device
+    _mark(stats, "start")
     g0, agg, chosen = salience_dropout_loop(gradcam_fn, imgs, norm_imgs, drop_iter, patch_num)
+    _mark(stats, "model+gradcam+dropout")
     B = imgs.shape[0]
     # bucket images by everything a launch must share
     buckets = {}
     for b in range(B):
         C = len(class_lists[b])
         with_bg = host.add_background_rule(data_type, C)
-        key = (C, with_bg, tuple(np.asarray(gts[b]).shape))
+        key = (C, with_bg, tuple(gts[b].shape))
         buckets.setdefault(key, []).append(b)
 
-    def run(gmaps, rescale):
-        hist = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
-        bad = torch.zeros(1, dtype=torch.int32, device=dev)
-        per_image = merge_tokens_batch(gmaps, token_ids, decode, class_lists)
-        for (C, with_bg, (H, W)), members in buckets.items():
-            cm = torch.stack([per_image[b] for b in members]).contiguous()
-            gt = torch.stack([torch.as_tensor(np.asarray(gts[b], dtype=np.float32)) for b in members]).to(dev)
-            gd = torch.stack([torch.as_tensor(np.ascontiguousarray(guides[b])) for b in members]).to(dev)
-            lut = torch.tensor([host.relabel_lut(dataset_ids[b], with_bg) for b in members], dtype=torch.int32, device=dev)
-            postprocess_batch(cm, gd, gt, lut, hist, threshold=threshold, rescale=rescale, with_background=with_bg, mode=mode,
-                              n_class=n_class, crf=crf, bad_count=bad, stats=stats)
-        if int(bad.item()):
-            raise PnpError("a relabelled id fell outside [0, n_class)")
-        return hist
-
-    hist0 = hist_agg = None
+    passes = []  # (name, maps, rescale): the reference scores the round-0 map and the accumulated map
     if not coco or drop_iter < 3:
-        hist0 = run(g0, True)           # 1-round path applies Scale_0_1 (DRV:362)
+        passes.append(("round0", g0, True))      # 1-round path applies Scale_0_1 (DRV:362)
     if agg is not None:
-        hist_agg = run(agg, coco)       # N-round path: only the COCO driver rescales (DRV:438 vs DRVC:527)
-    return hist0, hist_agg, chosen
+        passes.append(("all_drop", agg, coco))   # N-round path: only the COCO driver rescales (DRV:438 vs DRVC:527)
+    hists = {name: torch.zeros((n_class, n_class), dtype=torch.int64, device=dev) for name, _, _ in passes}
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    merged = {name: merge_tokens_batch(gm, token_ids, decode, class_lists) for name, gm, _ in passes}
+    _mark(stats, "merge")
+    use_crf = bool(mode) and "crf" in mode
+    for (C, with_bg, (H, W)), members in buckets.items():
+        gt = _as_device_batch(gts, members, torch.float32, dev)
+        gd = _as_device_batch(guides, members, torch.uint8, dev)
+        lut = torch.tensor([host.relabel_lut(dataset_ids[b], with_bg) for b in members], dtype=torch.int32, device=dev)
+        lat_b = None
+        if use_crf:  # one bilateral lattice per bucket, shared by both passes (the guide images are the same)
+            p = dict(CRF_DEFAULTS)
+            p.update(crf or {})
+            lat_b = ops.build_lattice(H, W, p["bi_xy_std"], rgb=gd, srgb=p["bi_rgb_std"])
+            _mark(stats, "lattice")
+        for name, _, rescale in passes:
+            cm = torch.stack([merged[name][b] for b in members]).contiguous()
+            postprocess_batch(cm, gd, gt, lut, hists[name], threshold=threshold, rescale=rescale, with_background=with_bg,
+                              mode=mode, n_class=n_class, crf=crf, bad_count=bad, stats=stats, bilateral=lat_b)
+    if int(bad.item()):
+        raise PnpError("a relabelled id fell outside [0, n_class)")
+    return hists.get("round0"), hists.get("all_drop"), chosen
 
 
 # ---------------------------------------------------------------------------------------------- multi-GPU + files
