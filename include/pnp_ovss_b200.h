@@ -131,7 +131,7 @@ typedef struct pnp_lattice {
     int n_vertices;    /* M: filled by pnp_lattice_finish (host copy of the device count) */
     int max_row;       /* longest CSR row, filled by pnp_lattice_finish (statistics) */
     int vertex_stride; /* allocated vertex capacity = n_images*n_pixels*(d+1) */
-    int reserved;
+    int width;         /* image width W (n_pixels = H*W), filled by pnp_lattice_build */
     /* device arrays */
     int32_t *offset;   /* [n_images*n_pixels, d+1] vertex id, 0-based, numbered in first-touch order */
     float *bary;       /* [n_images*n_pixels, d+1] barycentric weights */

@@ -46,12 +46,30 @@ __global__ void __launch_bounds__(256) splat_kernel(LatticeView L, const float *
             continue;
         }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int end = L.row_ptr[v + 1];
-        for (int k = L.row_ptr[v]; k < end; ++k) {
-            const int lp = L.csr_pix[k];
-            const float w = L.csr_w[k];
-            float4 xv = *reinterpret_cast<const float4 *>(xb + (long long)lp * Cp + 4 * ch);
-            if (normalized) xv = f4_mul(xv, L.norm[lp]);
+        const int end = __ldg(L.row_ptr + v + 1);
+        int k = __ldg(L.row_ptr + v);
+        for (; k + 4 <= end; k += 4) {  // four gathers in flight, accumulated in entry order
+            int lp[4];
+            float w[4], nr[4];
+            float4 xv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { lp[i] = __ldg(L.csr_pix + k + i); w[i] = __ldg(L.csr_w + k + i); }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xv[i] = *reinterpret_cast<const float4 *>(xb + (size_t)lp[i] * Cp + 4 * ch);
+                nr[i] = normalized ? __ldg(L.norm + lp[i]) : 1.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (normalized) xv[i] = f4_mul(xv[i], nr[i]);
+                acc = f4_add(acc, f4_mul(xv[i], w[i]));
+            }
+        }
+        for (; k < end; ++k) {
+            const int lp = __ldg(L.csr_pix + k);
+            const float w = __ldg(L.csr_w + k);
+            float4 xv = *reinterpret_cast<const float4 *>(xb + (size_t)lp * Cp + 4 * ch);
+            if (normalized) xv = f4_mul(xv, __ldg(L.norm + lp));
             acc = f4_add(acc, f4_mul(xv, w));
         }
         *reinterpret_cast<float4 *>(vb + (long long)(v + 1) * Cp + 4 * ch) = acc;
@@ -83,20 +101,34 @@ __global__ void __launch_bounds__(256) blur_axis_kernel(LatticeView L, const flo
     }
 }
 
-// slice one lattice at (pixel gp of image b, chunk ch): sum_j (w_j * values[o_j]) * alpha, optionally * norm
+// slice one lattice at (pixel gp of image b, chunk ch): sum_j (w_j * values[o_j]) * alpha, optionally * norm.
+// DP1 = d+1 is a template parameter so the d+1 gathers are all in flight before the (ordered) accumulation.
+template <int DP1>
+__device__ __forceinline__ float4 slice_pixel_t(const LatticeView &L, const float *__restrict__ values, int b, int pix, int gp, int ch,
+                                                int Cp, bool normalized) {
+    const int lp = L.shared ? pix : gp;
+    const float *vb = L.shared ? values + (size_t)b * (L.M + 1) * Cp : values;
+    int o[DP1];
+    float w[DP1];
+    float4 v[DP1];
+#pragma unroll
+    for (int j = 0; j < DP1; ++j) {
+        o[j] = __ldg(L.offset + (size_t)lp * DP1 + j) + 1;
+        w[j] = __ldg(L.bary + (size_t)lp * DP1 + j);
+    }
+#pragma unroll
+    for (int j = 0; j < DP1; ++j) v[j] = *reinterpret_cast<const float4 *>(vb + (size_t)o[j] * Cp + 4 * ch);
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < DP1; ++j) out = f4_add(out, f4_mul(f4_mul(v[j], w[j]), L.alpha));
+    if (normalized) out = f4_mul(out, __ldg(L.norm + lp));
+    return out;
+}
+
 __device__ __forceinline__ float4 slice_pixel(const LatticeView &L, const float *__restrict__ values, int b, int pix, long long gp,
                                               int ch, int Cp, bool normalized) {
-    const long long lp = L.shared ? pix : gp;
-    const float *vb = L.shared ? values + (long long)b * (L.M + 1) * Cp : values;
-    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < L.Dp1; ++j) {
-        const int o = L.offset[lp * L.Dp1 + j] + 1;
-        const float w = L.bary[lp * L.Dp1 + j];
-        const float4 v = *reinterpret_cast<const float4 *>(vb + (long long)o * Cp + 4 * ch);
-        out = f4_add(out, f4_mul(f4_mul(v, w), L.alpha));
-    }
-    if (normalized) out = f4_mul(out, L.norm[lp]);
-    return out;
+    if (L.Dp1 == 3) return slice_pixel_t<3>(L, values, b, pix, (int)gp, ch, Cp, normalized);
+    return slice_pixel_t<6>(L, values, b, pix, (int)gp, ch, Cp, normalized);
 }
 
 __global__ void __launch_bounds__(256) slice_kernel(LatticeView L, const float *__restrict__ values, float *__restrict__ y, int B, int Cp,
@@ -196,6 +228,90 @@ __global__ void __launch_bounds__(256) meanfield_update_kernel(MeanFieldParams P
             }
         }
         __syncthreads();
+    }
+}
+
+// Warp-level variant for Cp <= 128 (nch <= 32 chunks): the nch lanes of a pixel sit in one warp, so the softmax
+// reductions are shuffles -- no shared memory, no block barrier, warps never wait for each other's gathers.
+// A CTA owns whole 16x16 pixel tiles, so the lattice rows its pixels share stay in L1 between its sub-iterations.
+constexpr int kTile = 16;
+
+template <bool kLabels>
+__global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldParams P, const float *__restrict__ unary,
+                                                                    float *__restrict__ Q, int32_t *__restrict__ labels, int B, int H,
+                                                                    int W, int C, int Cp) {
+    const int nch = Cp >> 2;
+    const int PW = 32 / nch;                       // pixels per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pl = lane / nch, ch = lane - pl * nch;
+    const int base_lane = pl * nch;
+    const bool lane_used = pl < PW;
+    const int N = H * W;
+    const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile;
+    const int tiles_per_image = tiles_x * tiles_y;
+    const int n_tiles = B * tiles_per_image;
+    const int pix_per_iter = (blockDim.x >> 5) * PW;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_image;
+        const int t = tile - b * tiles_per_image;
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        for (int sub = 0; sub < kTile * kTile; sub += pix_per_iter) {
+            const int within = sub + warp * PW + pl;
+            const int y = ty * kTile + within / kTile, x = tx * kTile + (within % kTile);
+            const bool active = lane_used && within < kTile * kTile && y < H && x < W;
+            const int pix = y * W + x;
+            const int gp = b * N + pix;
+            float t4[4] = {0.f, 0.f, 0.f, 0.f};
+            float mx = -INFINITY;
+            if (active) {
+                const float4 u = ldg_stream4(unary + (size_t)gp * Cp + 4 * ch);
+                float4 acc = make_float4(-u.x, -u.y, -u.z, -u.w);
+                for (int k = 0; k < P.n_kernels; ++k) {
+                    float4 s = slice_pixel(P.lat[k], P.values[k], b, pix, gp, ch, Cp, true);
+                    acc = f4_add(acc, f4_mul(s, P.weight[k]));  // tmp1 -= (-w * K Q)
+                }
+                t4[0] = acc.x; t4[1] = acc.y; t4[2] = acc.z; t4[3] = acc.w;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (4 * ch + i < C) mx = fmaxf(mx, t4[i]);
+            }
+            float m = -INFINITY;
+            for (int k = 0; k < nch; ++k) m = fmaxf(m, __shfl_sync(0xffffffffu, mx, base_lane + k));
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+            float part = 0.f;
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (4 * ch + i < C) {
+                        e[i] = expf(t4[i] - m);
+                        part += e[i];
+                    }
+            }
+            float sum = 0.f;
+            for (int k = 0; k < nch; ++k) sum += __shfl_sync(0xffffffffu, part, base_lane + k);
+            float q[4] = {0.f, 0.f, 0.f, 0.f};
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (4 * ch + i < C) q[i] = __fdiv_rn(e[i], sum);
+                *reinterpret_cast<float4 *>(Q + (size_t)gp * Cp + 4 * ch) = make_float4(q[0], q[1], q[2], q[3]);
+            }
+            if (kLabels) {
+                float best = q[0];
+                int bi = 4 * ch;
+#pragma unroll
+                for (int i = 1; i < 4; ++i)
+                    if (4 * ch + i < C) argmax_first(q[i], 4 * ch + i, best, bi);
+                float rb = __shfl_sync(0xffffffffu, best, base_lane);
+                int ri = __shfl_sync(0xffffffffu, bi, base_lane);
+                for (int k = 1; k < nch; ++k) {
+                    float ob = __shfl_sync(0xffffffffu, best, base_lane + k);
+                    int oi = __shfl_sync(0xffffffffu, bi, base_lane + k);
+                    argmax_first(ob, oi, rb, ri);
+                }
+                if (active && ch == 0) labels[gp] = ri;
+            }
+        }
     }
 }
 
@@ -373,20 +489,31 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
     const int TP = 256 / (Cp / 4);
     const long long n_tiles = ((long long)B * N + TP - 1) / TP;
     const int grid = (int)std::max<long long>(1, std::min<long long>(n_tiles, (long long)kNumSMs * 8));
+    const int Wimg = lattices[0]->width, Himg = Wimg > 0 ? N / Wimg : 0;
+    const bool warp_path = Cp <= 128 && Wimg > 0 && (long long)Himg * Wimg == N && (long long)B * N < (1ll << 31) / Cp;
+    const int grid_w = (int)std::max<long long>(
+        1, std::min<long long>((long long)B * ((Himg + kTile - 1) / kTile) * ((Wimg + kTile - 1) / kTile), (long long)kNumSMs * 8));
+    auto update = [&](bool with_labels) {
+        if (warp_path) {
+            if (with_labels)
+                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<true><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
+            else
+                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<false><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
+        } else {
+            if (with_labels)
+                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
+            else
+                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<false><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
+        }
+    };
 
     // Q0 = softmax(-U)
     P.n_kernels = 0;
-    if (n_iter == 0 && labels)
-        PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
-    else
-        PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<false><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
+    update(n_iter == 0 && labels != nullptr);
     for (int it = 0; it < n_iter; ++it) {
         for (int k = 0; k < n_kernels; ++k) P.values[k] = run_splat_blur(P.lat[k], Q, va[k], vb[k], B, Cp, 1, st);
         P.n_kernels = n_kernels;
-        if (it == n_iter - 1 && labels)
-            PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
-        else
-            PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<false><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
+        update(it == n_iter - 1 && labels != nullptr);
     }
     return launch_status();
 }

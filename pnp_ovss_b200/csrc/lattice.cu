@@ -567,7 +567,7 @@ extern "C" int pnp_lattice_init(pnp_lattice *lat, void *storage, size_t storage_
     lat->n_vertices = -1;
     lat->max_row = -1;
     lat->vertex_stride = (int)n_entries;
-    lat->reserved = 0;
+    lat->width = 0;
     lat->offset = reinterpret_cast<int32_t *>(take(n_entries * 4));
     lat->bary = reinterpret_cast<float *>(take(n_entries * 4));
     lat->nbr = reinterpret_cast<int32_t *>(take((size_t)(d + 1) * n_entries * 2 * 4));
@@ -662,6 +662,7 @@ extern "C" int pnp_lattice_build(pnp_lattice *lat, const uint8_t *rgb, int H, in
     if (workspace_bytes < pnp_lattice_build_workspace_bytes(lat->d, lat->n_images, lat->n_pixels)) return PNP_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return PNP_ERR_INVALID_ARGUMENT;
     char *ws = reinterpret_cast<char *>(workspace);
+    lat->width = W;
     if (lat->d == 2) return build_impl<2>(lat, rgb, H, W, sx, sy, sr, sg, sb, ws, as_stream(stream));
     return build_impl<5>(lat, rgb, H, W, sx, sy, sr, sg, sb, ws, as_stream(stream));
 }
