@@ -114,7 +114,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------- roofline bookkeeping
-LATTICE_LAUNCHES = {2: 21, 5: 24}  # kernels inside one pnp_lattice_build (see lattice.cu build_impl)
+LATTICE_LAUNCHES = {2: 22, 5: 25}  # kernels inside one pnp_lattice_build (see lattice.cu build_impl)
 
 
 def algorithmic_bytes(kernel, w, stats, T):

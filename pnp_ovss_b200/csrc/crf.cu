@@ -25,54 +25,70 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
     return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // rows of a value buffer that one image (shared lattice) or the whole batch (batched lattice) occupies
 __host__ __device__ __forceinline__ long long value_rows(const LatticeView &L, int B) {
     return L.shared ? (long long)B * (L.M + 1) : (long long)L.M + 1;
 }
 
 // ------------------------------------------------------------------------------------------ splat
-// grid.y = image for shared lattices (1 otherwise)
+// grid.y = image for shared lattices (1 otherwise).  One thread owns one float4 chunk of one vertex row and walks the
+// vertex's CSR entries (pixels in ascending order) eight at a time: the eight row gathers go through cp.async into the
+// thread's private smem slots, so they are all in flight together without costing registers, and are then added in
+// entry order with separately rounded mul/add (bit-identical to the sequential reference).
+constexpr int kSplatBatch = 8;
+constexpr int kSplatSmem = kSplatBatch * 256 * 16;
+
 __global__ void __launch_bounds__(256) splat_kernel(LatticeView L, const float *__restrict__ x, float *__restrict__ values, int Cp,
                                                     int normalized) {
+    extern __shared__ float4 s_rows[];  // [kSplatBatch][256]
     const int nch = Cp >> 2;
     const int b = blockIdx.y;
-    const float *xb = L.shared ? x + (long long)b * L.N * Cp : x;
-    float *vb = L.shared ? values + (long long)b * (L.M + 1) * Cp : values;
+    const float *xb = L.shared ? x + (size_t)b * L.N * Cp : x;
+    float *vb = L.shared ? values + (size_t)b * (L.M + 1) * Cp : values;
     const long long total = (long long)(L.M + 1) * nch;
+    float4 *slot = s_rows + threadIdx.x;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int v = (int)(idx / nch), ch = (int)(idx - (long long)v * nch);
-        if (v == L.M) {  // sentinel row 0 stays zero
+        const int pos = (int)(idx / nch), ch = (int)(idx - (long long)pos * nch);
+        if (pos == L.M) {  // sentinel row 0 stays zero
             *reinterpret_cast<float4 *>(vb + 4 * ch) = make_float4(0.f, 0.f, 0.f, 0.f);
             continue;
         }
+        const int v = __ldg(L.perm + pos);  // window-local descending row-length order
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const int end = __ldg(L.row_ptr + v + 1);
-        int k = __ldg(L.row_ptr + v);
-        for (; k + 4 <= end; k += 4) {  // four gathers in flight, accumulated in entry order
-            int lp[4];
-            float w[4], nr[4];
-            float4 xv[4];
+        for (int k = __ldg(L.row_ptr + v); k < end; k += kSplatBatch) {
+            const int n = min(kSplatBatch, end - k);
+            float w[kSplatBatch], nr[kSplatBatch];
+            int lp[kSplatBatch];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { lp[i] = __ldg(L.csr_pix + k + i); w[i] = __ldg(L.csr_w + k + i); }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                xv[i] = *reinterpret_cast<const float4 *>(xb + (size_t)lp[i] * Cp + 4 * ch);
-                nr[i] = normalized ? __ldg(L.norm + lp[i]) : 1.f;
+            for (int i = 0; i < kSplatBatch; ++i) {  // index / weight loads first (sequential in CSR order) ...
+                const int kk = min(k + i, end - 1);
+                lp[i] = __ldg(L.csr_pix + kk);
+                w[i] = __ldg(L.csr_w + kk);
+                nr[i] = normalized ? __ldg(L.csr_norm + kk) : 1.f;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (normalized) xv[i] = f4_mul(xv[i], nr[i]);
-                acc = f4_add(acc, f4_mul(xv[i], w[i]));
+            for (int i = 0; i < kSplatBatch; ++i)    // ... then all row gathers back to back
+                if (i < n) cp_async16(slot + i * 256, xb + (size_t)lp[i] * Cp + 4 * ch);
+            cp_async_wait_all();
+#pragma unroll
+            for (int i = 0; i < kSplatBatch; ++i) {
+                if (i < n) {
+                    float4 xv = slot[i * 256];
+                    if (normalized) xv = f4_mul(xv, nr[i]);
+                    acc = f4_add(acc, f4_mul(xv, w[i]));
+                }
             }
         }
-        for (; k < end; ++k) {
-            const int lp = __ldg(L.csr_pix + k);
-            const float w = __ldg(L.csr_w + k);
-            float4 xv = *reinterpret_cast<const float4 *>(xb + (size_t)lp * Cp + 4 * ch);
-            if (normalized) xv = f4_mul(xv, __ldg(L.norm + lp));
-            acc = f4_add(acc, f4_mul(xv, w));
-        }
-        *reinterpret_cast<float4 *>(vb + (long long)(v + 1) * Cp + 4 * ch) = acc;
+        *reinterpret_cast<float4 *>(vb + (size_t)(v + 1) * Cp + 4 * ch) = acc;
     }
 }
 
@@ -231,15 +247,18 @@ __global__ void __launch_bounds__(256) meanfield_update_kernel(MeanFieldParams P
     }
 }
 
+constexpr int kGatherSmem = 9 * 256 * 16;  // fast path: 9 float4 slots per thread
+
 // Warp-level variant for Cp <= 128 (nch <= 32 chunks): the nch lanes of a pixel sit in one warp, so the softmax
 // reductions are shuffles -- no shared memory, no block barrier, warps never wait for each other's gathers.
 // A CTA owns whole 16x16 pixel tiles, so the lattice rows its pixels share stay in L1 between its sub-iterations.
 constexpr int kTile = 16;
 
-template <bool kLabels>
+template <bool kLabels, bool kFast>
 __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldParams P, const float *__restrict__ unary,
                                                                     float *__restrict__ Q, int32_t *__restrict__ labels, int B, int H,
                                                                     int W, int C, int Cp) {
+    extern __shared__ float4 s_gather[];           // [9][256], fast path only
     const int nch = Cp >> 2;
     const int PW = 32 / nch;                       // pixels per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -263,7 +282,66 @@ __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldPar
             const int gp = b * N + pix;
             float t4[4] = {0.f, 0.f, 0.f, 0.f};
             float mx = -INFINITY;
-            if (active) {
+            if (kFast) {
+                // [spatial d=2 shared, bilateral d=5 batched].  Loads are unconditional (idle lanes read pixel 0) and
+                // separated from the arithmetic by a warp barrier, so all 9 offsets and then all 9 gathers are in
+                // flight together; alpha, norm and the kernel weight are folded into the barycentric weights (the
+                // exactly-ordered variant lives in slice_pixel_t / pnp_crf_filter).
+                const int spix = active ? pix : 0, sgp = active ? gp : 0, sb = active ? b : 0, sch = lane_used ? ch : 0;
+                const LatticeView &A = P.lat[0];
+                const LatticeView &Bl = P.lat[1];
+                const float *va = P.values[0] + (size_t)sb * (A.M + 1) * Cp + 4 * sch;
+                const float *vbp = P.values[1] + 4 * sch;
+                const float4 u = ldg_stream4(unary + (size_t)sgp * Cp + 4 * sch);
+                int oa[3], ob[6];
+                float wa[3], wb[6];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { oa[j] = __ldg(A.offset + (size_t)spix * 3 + j) + 1; wa[j] = __ldg(A.bary + (size_t)spix * 3 + j); }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {  // 6 ints / 6 floats per pixel, 8-byte aligned
+                    const int2 o2 = __ldg(reinterpret_cast<const int2 *>(Bl.offset + (size_t)sgp * 6) + j);
+                    const float2 w2 = __ldg(reinterpret_cast<const float2 *>(Bl.bary + (size_t)sgp * 6) + j);
+                    ob[2 * j] = o2.x + 1; ob[2 * j + 1] = o2.y + 1;
+                    wb[2 * j] = w2.x; wb[2 * j + 1] = w2.y;
+                }
+                const float ca = A.alpha * __ldg(A.norm + spix) * P.weight[0];
+                const float cb = Bl.alpha * __ldg(Bl.norm + sgp) * P.weight[1];
+                // the 9 row gathers go through cp.async into this thread's private smem slots: all of them are in
+                // flight at once by construction (ptxas otherwise serialises register gathers to save registers)
+                float4 *slot = s_gather + threadIdx.x;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) cp_async16(slot + j * 256, va + (size_t)oa[j] * Cp);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) cp_async16(slot + (3 + j) * 256, vbp + (size_t)ob[j] * Cp);
+                // keep the plain loads (unary, barycentric weights, norms) ahead of the wait, not behind it
+                asm volatile("" ::"f"(u.x), "f"(u.y), "f"(u.z), "f"(u.w), "f"(wa[0]), "f"(wa[1]), "f"(wa[2]), "f"(wb[0]), "f"(wb[1]),
+                             "f"(wb[2]), "f"(wb[3]), "f"(wb[4]), "f"(wb[5]), "f"(ca), "f"(cb));
+                cp_async_wait_all();
+                float4 ga[3], gb[6];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) ga[j] = slot[j * 256];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) gb[j] = slot[(3 + j) * 256];
+                float4 acc = make_float4(-u.x, -u.y, -u.z, -u.w);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float w = wa[j] * ca;
+                    acc.x = fmaf(ga[j].x, w, acc.x); acc.y = fmaf(ga[j].y, w, acc.y);
+                    acc.z = fmaf(ga[j].z, w, acc.z); acc.w = fmaf(ga[j].w, w, acc.w);
+                }
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const float w = wb[j] * cb;
+                    acc.x = fmaf(gb[j].x, w, acc.x); acc.y = fmaf(gb[j].y, w, acc.y);
+                    acc.z = fmaf(gb[j].z, w, acc.z); acc.w = fmaf(gb[j].w, w, acc.w);
+                }
+                t4[0] = acc.x; t4[1] = acc.y; t4[2] = acc.z; t4[3] = acc.w;
+                if (active) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (4 * ch + i < C) mx = fmaxf(mx, t4[i]);
+                }
+            } else if (active) {
                 const float4 u = ldg_stream4(unary + (size_t)gp * Cp + 4 * ch);
                 float4 acc = make_float4(-u.x, -u.y, -u.z, -u.w);
                 for (int k = 0; k < P.n_kernels; ++k) {
@@ -283,7 +361,7 @@ __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldPar
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (4 * ch + i < C) {
-                        e[i] = expf(t4[i] - m);
+                        e[i] = kFast ? __expf(t4[i] - m) : expf(t4[i] - m);
                         part += e[i];
                     }
             }
@@ -291,9 +369,10 @@ __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldPar
             for (int k = 0; k < nch; ++k) sum += __shfl_sync(0xffffffffu, part, base_lane + k);
             float q[4] = {0.f, 0.f, 0.f, 0.f};
             if (active) {
+                const float rs = __frcp_rn(sum);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (4 * ch + i < C) q[i] = __fdiv_rn(e[i], sum);
+                    if (4 * ch + i < C) q[i] = kFast ? e[i] * rs : __fdiv_rn(e[i], sum);
                 *reinterpret_cast<float4 *>(Q + (size_t)gp * Cp + 4 * ch) = make_float4(q[0], q[1], q[2], q[3]);
             }
             if (kLabels) {
@@ -413,7 +492,7 @@ static const float *run_splat_blur(const LatticeView &L, const float *x, float *
     const int gx = std::max(1, grid_for((long long)(L.M + 1) * nch, 256) / (L.shared ? std::min(B, 8) : 1));
     const int id_splat = L.shared ? kSplatSpatial : kSplatBilateral;
     const int id_blur = L.shared ? kBlurAxisSpatial : kBlurAxisBilateral;
-    PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, x, va, Cp, normalized));
+    PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx, gy), 256, kSplatSmem, st>>>(L, x, va, Cp, normalized));
     float *src = va, *dst = vb;
     for (int j = 0; j < L.Dp1; ++j) {
         PNP_LAUNCH(id_blur, st, blur_axis_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, src, dst, j, Cp));
@@ -494,11 +573,17 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
     const int grid_w = (int)std::max<long long>(
         1, std::min<long long>((long long)B * ((Himg + kTile - 1) / kTile) * ((Wimg + kTile - 1) / kTile), (long long)kNumSMs * 8));
     auto update = [&](bool with_labels) {
-        if (warp_path) {
+        const bool fast = warp_path && P.n_kernels == 2 && P.lat[0].Dp1 == 3 && P.lat[0].shared && P.lat[1].Dp1 == 6 && !P.lat[1].shared;
+        if (fast) {
             if (with_labels)
-                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<true><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
+                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<true, true><<<grid_w, 256, kGatherSmem, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
             else
-                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<false><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
+                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<false, true><<<grid_w, 256, kGatherSmem, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
+        } else if (warp_path) {
+            if (with_labels)
+                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<true, false><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
+            else
+                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<false, false><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
         } else {
             if (with_labels)
                 PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
