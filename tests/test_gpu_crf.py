@@ -118,7 +118,7 @@ def test_filter_batch_matches_single(dev, ops):
         assert torch.equal(ops.crf_filter(lat_s, x[b:b + 1].contiguous())[0], ys[b])
 
 
-@pytest.mark.parametrize("C,kind", [(4, "natural"), (21, "natural"), (3, "noise")])
+@pytest.mark.parametrize("C,kind", [(4, "natural"), (21, "natural"), (3, "noise"), (150, "natural"), (171, "noise")])
 def test_inference_matches_oracle(dev, D, C, kind):
     from pnp_ovss_b200 import reference_api as R
     H, W = 50, 44
@@ -214,3 +214,41 @@ def test_full_size_properties(dev, ops):
     lhs = ops.crf_filter(lat_b, 2.0 * a + 0.5 * b2)
     rhs = 2.0 * ops.crf_filter(lat_b, a) + 0.5 * ops.crf_filter(lat_b, b2)
     assert torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,C,S,with_bg", [("ade20k_150", 150, 336, False), ("coco_stuff_171_512", 171, 512, False),
+                                              ("coco_object_81_448", 80, 448, True)])
+def test_other_baseline_configs_properties(dev, ops, name, C, S, with_bg):
+    """BASELINE.json configs[2..4] shapes (2 images each): the channel counts that take the non-warp update path
+    (Cp > 128), 512x512 CRF, the 448 grid.  Oracle-free properties + determinism."""
+    from pnp_ovss_b200 import pipeline
+    B, P, n = 2, S // 16 if S != 512 else 21, C + 12
+    maps = torch.stack([synth.saliency_maps(500 + b, C, P) for b in range(B)])
+    maps[:, :, :5, :5] = 0  # a corner no class claims, so the background channel is not empty (an empty one is 0/0 = NaN)
+    maps = maps.to(dev)
+    guides = torch.from_numpy(np.stack([synth.guide_image(600 + b, S, S) for b in range(B)])).to(dev)
+    gts = torch.from_numpy(np.stack([synth.gt_labels(700 + b, S, S, n) for b in range(B)])).to(dev)
+    Cc = C + (1 if with_bg else 0)
+    luts = (torch.arange(Cc, dtype=torch.int32, device=dev) + (0 if with_bg else 1)).repeat(B, 1)
+    out = []
+    for _ in range(2):
+        hist = torch.zeros((n, n), dtype=torch.int64, device=dev)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        pred = pipeline.postprocess_batch(maps, guides, gts, luts, hist, threshold=0.15, rescale=True, with_background=with_bg,
+                                          mode="blur+crf", n_class=n, return_labels=True, bad_count=bad)
+        out.append((hist.clone(), pred.clone()))
+        assert int(bad.item()) == 0
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert out[0][0].sum().item() == ((gts >= 0) & (gts < n)).sum().item()
+    # the fused path agrees with the step-by-step entry points (pack -> inference -> unpack -> argmax)
+    x = ops.threshold_upsample(maps, S, S, 0.15, True, with_bg)
+    xb, mm = ops.gaussian_blur(x, 0.05 * S, normalize=False)
+    U = ops.crf_unary_from_maps(xb.view(B, Cc, S * S), mm)
+    lat_s = ops.build_lattice(S, S, 3.0, device=dev)
+    lat_b = ops.build_lattice(S, S, 50.0, rgb=guides, srgb=5.0)
+    Q, labels = ops.crf_inference([lat_s, lat_b], [7.0, 10.0], U, Cc, 10)
+    q_cn = ops.crf_unpack(Q, Cc)
+    assert torch.allclose(q_cn.sum(1), torch.ones(B, S * S, device=dev), atol=1e-4)
+    assert torch.equal(ops.argmax_channels(q_cn), labels)
+    lut_l = luts[0].long()
+    assert torch.equal(out[0][1].view(B, -1), lut_l[labels.long()].float())

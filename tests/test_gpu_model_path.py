@@ -1,0 +1,122 @@
+"""GPU: rows a1+a2 through a real (tiny) model pass, and the reference-named entry points of reference_api, against
+the CPU restatement of the reference's own procedure (oracle/reference_arm.py: torch softmax + hooks + full backward)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _tiny_model(tok):
+    from pnp_ovss_b200.blip_itm import BlipITM
+    torch.manual_seed(11)
+    m = BlipITM(img_size=96, tokenizer=tok, vocab=30524, hidden=128, layers=3, heads=2, inter=256, vit_dim=64, vit_depth=2,
+                vit_heads=2, max_pos=64).eval()
+    with torch.no_grad():  # random init at std 0.02 gives near-uniform attention; widen it so the maps have structure
+        for p in m.parameters():
+            p.mul_(2.0)
+    return m
+
+
+class _Args:
+    max_att_block_num, prune_att_head, drop_iter, img_size = 2, 1, 3, 96
+
+
+def test_gradcam_through_model_matches_reference_procedure(dev):
+    from oracle import reference_arm as RA
+    from pnp_ovss_b200 import reference_api as R
+    tok = synth.SyntheticWordPieceTokenizer()
+    caps = ["A picture of cat aeroplane", "A picture of dog"]
+    tokens = tok(caps, padding="max_length", max_length=500)
+    g = torch.Generator().manual_seed(3)
+    imgs = torch.randn(2, 3, 96, 96, generator=g)
+    model = _tiny_model(tok)
+    ref_model = RA.install_reference_capture(copy.deepcopy(model))
+    blocks, _, out_ref = RA.compute_gradcam_ensemble_reference(ref_model, imgs, caps, tokens)
+    want = blocks[1][1]                                           # [layer][head] as DRV:572-574 reads it
+    gm = model.to(dev)
+    for full in (False, True):
+        if full:
+            gm.requires_grad_(True)
+        else:
+            gm.requires_grad_(False)
+        cam, out = gm.gradcam(imgs.to(dev), caps, tokens.to(dev), layer=1, head=1, full_backward=full)
+        assert cam.shape == want.shape
+        scale = float(want.abs().max())
+        assert scale > 0
+        err = (cam.cpu() - want).abs().max().item()
+        assert err <= 1e-3 * scale, "GradCAM differs: %g (scale %g, full=%s)" % (err, scale, full)
+        assert torch.allclose(out.cpu(), out_ref, rtol=1e-3, atol=1e-5)
+    # the reference-named entry point, lazily materialising only [layer][head]
+    gm.requires_grad_(False)
+    lst, empty, out = R.compute_gradcam_ensemble(_Args, gm, imgs.to(dev), caps, tokens.to(dev))
+    assert empty == [] and torch.allclose(lst[1][1].cpu(), want, atol=1e-3 * scale)
+    with pytest.raises(Exception):
+        lst[0][0]
+
+
+def test_inference_blip_filteredcaption_matches_oracle_loop(dev):
+    """Inference_BLIP_filteredcaption (DRV:564-722) with the tiny model vs the oracle's DropOut loop around the
+    reference-procedure GradCAM (same weights, CPU)."""
+    from oracle import hotpath as O
+    from oracle import reference_arm as RA
+    from pnp_ovss_b200 import reference_api as R
+    tok = synth.SyntheticWordPieceTokenizer()
+    caps = ["A picture of cat aeroplane", "A picture of dog"]
+    tokens = tok(caps, padding="max_length", max_length=500)
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.randn(2, 3, 96, 96, generator=g)
+    model = _tiny_model(tok)
+    ref_model = RA.install_reference_capture(copy.deepcopy(model))
+    g0_o, agg_o, chosen_o, _ = O.salience_dropout(
+        lambda x: RA.compute_gradcam_ensemble_reference(ref_model, x, caps, tokens)[0][1][1], imgs, 3, 6, argsort_kind="stable")
+    gm = model.to(dev).requires_grad_(False)
+
+    class Wrap:  # the drivers pass a DDP-wrapped model (model_textloc.module)
+        module = gm
+
+    g0, agg = R.Inference_BLIP_filteredcaption(_Args, Wrap, tokens.to(dev), imgs, None, ["a", "b"], caps, [["cat", "aeroplane"], ["dog"]], 0)
+    scale = float(agg_o.abs().max())
+    assert (g0.cpu() - g0_o).abs().max().item() <= 1e-3 * float(g0_o.abs().max())
+    assert (agg.cpu() - agg_o).abs().max().item() <= 1e-3 * scale
+    # token merge entry point on the accumulated map of image 0
+    cm = R.Mean_over_filtered_label_tokens(Wrap, tokens, agg[0], [["cat", "aeroplane"], ["dog"]], 0)
+    toks = O.token_strings(tokens.input_ids[0], tok.decode)
+    want = O.mean_over_filtered_label_tokens(toks, agg[0].cpu(), 2)
+    assert torch.equal(cm.cpu(), want)
+
+
+def test_postprocess_entry_points_match_oracle(dev):
+    from oracle import hotpath as O
+    from pnp_ovss_b200 import reference_api as R
+    H, W, C = 60, 52, 4
+    rng = np.random.default_rng(8)
+    x = torch.from_numpy(rng.random((C, H, W)).astype(np.float32))
+    x[0] = (x[1:].max(0)[0] < 0.6).float()
+    img = synth.guide_image(4, H, W)
+    gts = [np.zeros((H, W), np.float32)]
+
+    class A:
+        postprocess = "blur"
+    got = R.postprocess(A, x.clone(), [img], gts, 0)
+    want = O.postprocess("blur", x.clone(), img, (H, W))
+    assert got.dtype == want.dtype and np.array_equal(got, want)
+    A.postprocess = "blur+crf"
+    got = R.postprocess(A, x.clone(), [img], gts, 0)
+    want = O.postprocess("blur+crf", x.clone(), img, (H, W))
+    assert got.dtype == np.float32 and (got != want).mean() <= 2e-3
+    b = R.blurring(x[1], (H, W))
+    assert np.allclose(b, O.blurring(x[1], (H, W)), rtol=1e-3, atol=1e-4)
+    s = R.Scale_0_1(x.clone().to(dev))
+    assert torch.equal(s.cpu(), O.scale_0_1(x.clone()))
