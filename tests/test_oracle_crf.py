@@ -1,0 +1,87 @@
+"""CPU: property tests of the dense-CRF restatement (oracle/densecrf.c).  pydensecrf is not available to diff against
+(PARITY UNPINNED, see the file header), so the oracle is held to the properties the published algorithm has."""
+import numpy as np
+import torch
+
+import synth
+from oracle import densecrf as D
+
+
+def _crf(H, W, C, img):
+    d = D.DenseCRF2D(W, H, C)
+    d.addPairwiseGaussian(3, 7)
+    d.addPairwiseBilateral(50, 5, img, 10)
+    return d
+
+
+def test_marginals_are_distributions_and_iter0_is_softmax():
+    H, W, C = 40, 36, 5
+    img = synth.guide_image(1, H, W)
+    rng = np.random.default_rng(0)
+    p = rng.random((C, H, W)).astype(np.float32)
+    p /= p.sum(0, keepdims=True)
+    U = D.unary_from_softmax(p)
+    d = _crf(H, W, C, img)
+    d.setUnaryEnergy(np.ascontiguousarray(U))
+    Q0 = d.inference(0)
+    assert np.allclose(Q0, p.reshape(C, -1), rtol=1e-5, atol=1e-7)      # softmax(-U) = softmax(log p) = p
+    Q = d.inference(10)
+    assert Q.min() >= 0 and np.allclose(Q.sum(0), 1.0, atol=1e-5)
+
+
+def test_filter_is_linear_and_symmetric():
+    H, W, C = 32, 32, 3
+    d = _crf(H, W, C, synth.guide_image(2, H, W))
+    rng = np.random.default_rng(1)
+    x, y = rng.random((C, H * W)).astype(np.float32), rng.random((C, H * W)).astype(np.float32)
+    for k in (0, 1):
+        Kx, Ky = d.kernel_apply(k, x), d.kernel_apply(k, y)
+        assert np.allclose(d.kernel_apply(k, 2 * x + 0.5 * y), 2 * Kx + 0.5 * Ky, rtol=1e-4, atol=1e-5)
+        a, b = float((y.astype(np.float64) * Kx).sum()), float((Ky.astype(np.float64) * x).sum())
+        # splat and slice are transposes and each axis blur is symmetric; the axis blurs only commute approximately,
+        # so K is symmetric to ~1e-3 (densecrf's `reverse` order exists for exactly this reason)
+        assert abs(a - b) <= 1e-2 * abs(a)
+
+
+def test_norm_is_inverse_sqrt_of_K_ones():
+    H, W = 24, 30
+    lat = D.Lattice(np.stack(np.meshgrid(np.arange(W) / 3.0, np.arange(H) / 3.0), -1).reshape(-1, 2).astype(np.float32))
+    K1 = lat.compute(np.ones((H * W, 1), np.float32))[:, 0]
+    d = D.DenseCRF2D(W, H, 2)
+    d.addPairwiseGaussian(3, 1)
+    assert np.allclose(d.kernel_norm(0), 1.0 / np.sqrt(K1 + 1e-20), rtol=1e-6)
+    assert K1.min() > 0
+
+
+def test_spatial_filter_approximates_a_gaussian():
+    """The d=2 lattice filter is an approximation of the Gaussian exp(-|p-q|^2 / (2 sxy^2)) (Adams et al. 2010)."""
+    H = W = 32
+    sxy = 3.0
+    yy, xx = np.mgrid[0:H, 0:W]
+    feat = np.stack([xx / sxy, yy / sxy], -1).reshape(-1, 2).astype(np.float32)
+    lat = D.Lattice(feat)
+    x = np.zeros((H * W, 1), np.float32)
+    x[16 * W + 16] = 1.0                                           # impulse in the middle
+    got = lat.compute(x)[:, 0].reshape(H, W)
+    want = np.exp(-((xx - 16) ** 2 + (yy - 16) ** 2) / (2 * sxy ** 2))
+    got, want = got / got.sum(), want / want.sum()
+    assert np.abs(got - want).sum() < 0.25                          # total-variation distance of the two kernels
+    cy, cx = (got * yy).sum(), (got * xx).sum()
+    assert abs(cy - 16) < 0.5 and abs(cx - 16) < 0.5               # centred
+
+
+def test_strong_pairwise_term_smooths_the_labelling():
+    H, W, C = 48, 48, 2
+    img = np.full((H, W, 3), 128, np.uint8)
+    rng = np.random.default_rng(3)
+    p = np.full((C, H, W), 0.5, np.float32)
+    p[0, :, :24] = 0.7
+    p[0, :, 24:] = 0.3
+    p[0] += rng.normal(0, 0.25, (H, W)).astype(np.float32)          # noisy unary around a clean left/right split
+    p[0] = np.clip(p[0], 0.02, 0.98)
+    p[1] = 1 - p[0]
+    noisy = np.argmax(p, 0)
+    lab = D.densecrf(img, torch.log(torch.from_numpy(p)))
+    truth = np.zeros((H, W), np.int64)
+    truth[:, 24:] = 1
+    assert (lab != truth).mean() < 0.5 * (noisy != truth).mean()
