@@ -25,6 +25,11 @@ __device__ __forceinline__ float4 f4_add(float4 a, float4 b) {
     return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
 
+__device__ __forceinline__ float4 ld_gather4(const float *p) {  // ordered (volatile) 128-bit gather through L1
+    float4 r;
+    asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
@@ -40,21 +45,18 @@ __host__ __device__ __forceinline__ long long value_rows(const LatticeView &L, i
 
 // ------------------------------------------------------------------------------------------ splat
 // grid.y = image for shared lattices (1 otherwise).  One thread owns one float4 chunk of one vertex row and walks the
-// vertex's CSR entries (pixels in ascending order) eight at a time: the eight row gathers go through cp.async into the
-// thread's private smem slots, so they are all in flight together without costing registers, and are then added in
-// entry order with separately rounded mul/add (bit-identical to the sequential reference).
-constexpr int kSplatBatch = 8;
-constexpr int kSplatSmem = kSplatBatch * 256 * 16;
+// vertex's CSR entries (pixels in ascending order) four at a time (four row gathers in flight), adding them in entry
+// order with separately rounded mul/add (bit-identical to the sequential reference).  ncu: the kernel is bound by L1
+// wavefronts of the row gathers, so staging through shared memory (cp.async) only adds to that pipe.
+constexpr int kSplatBatch = 4;
 
 __global__ void __launch_bounds__(256) splat_kernel(LatticeView L, const float *__restrict__ x, float *__restrict__ values, int Cp,
                                                     int normalized) {
-    extern __shared__ float4 s_rows[];  // [kSplatBatch][256]
     const int nch = Cp >> 2;
     const int b = blockIdx.y;
     const float *xb = L.shared ? x + (size_t)b * L.N * Cp : x;
     float *vb = L.shared ? values + (size_t)b * (L.M + 1) * Cp : values;
     const long long total = (long long)(L.M + 1) * nch;
-    float4 *slot = s_rows + threadIdx.x;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int pos = (int)(idx / nch), ch = (int)(idx - (long long)pos * nch);
         if (pos == L.M) {  // sentinel row 0 stays zero
@@ -64,29 +66,30 @@ __global__ void __launch_bounds__(256) splat_kernel(LatticeView L, const float *
         const int v = __ldg(L.perm + pos);  // window-local descending row-length order
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const int end = __ldg(L.row_ptr + v + 1);
-        for (int k = __ldg(L.row_ptr + v); k < end; k += kSplatBatch) {
-            const int n = min(kSplatBatch, end - k);
-            float w[kSplatBatch], nr[kSplatBatch];
+        int k = __ldg(L.row_ptr + v);
+        for (; k + kSplatBatch <= end; k += kSplatBatch) {  // kSplatBatch gathers in flight, accumulated in entry order
             int lp[kSplatBatch];
-#pragma unroll
-            for (int i = 0; i < kSplatBatch; ++i) {  // index / weight loads first (sequential in CSR order) ...
-                const int kk = min(k + i, end - 1);
-                lp[i] = __ldg(L.csr_pix + kk);
-                w[i] = __ldg(L.csr_w + kk);
-                nr[i] = normalized ? __ldg(L.csr_norm + kk) : 1.f;
-            }
-#pragma unroll
-            for (int i = 0; i < kSplatBatch; ++i)    // ... then all row gathers back to back
-                if (i < n) cp_async16(slot + i * 256, xb + (size_t)lp[i] * Cp + 4 * ch);
-            cp_async_wait_all();
+            float w[kSplatBatch], nr[kSplatBatch];
+            float4 xv[kSplatBatch];
 #pragma unroll
             for (int i = 0; i < kSplatBatch; ++i) {
-                if (i < n) {
-                    float4 xv = slot[i * 256];
-                    if (normalized) xv = f4_mul(xv, nr[i]);
-                    acc = f4_add(acc, f4_mul(xv, w[i]));
-                }
+                lp[i] = __ldg(L.csr_pix + k + i);
+                w[i] = __ldg(L.csr_w + k + i);
+                nr[i] = normalized ? __ldg(L.csr_norm + k + i) : 1.f;
             }
+#pragma unroll
+            for (int i = 0; i < kSplatBatch; ++i) xv[i] = *reinterpret_cast<const float4 *>(xb + (size_t)lp[i] * Cp + 4 * ch);
+#pragma unroll
+            for (int i = 0; i < kSplatBatch; ++i) {
+                if (normalized) xv[i] = f4_mul(xv[i], nr[i]);
+                acc = f4_add(acc, f4_mul(xv[i], w[i]));
+            }
+        }
+        for (; k < end; ++k) {
+            const int lp = __ldg(L.csr_pix + k);
+            float4 xv = *reinterpret_cast<const float4 *>(xb + (size_t)lp * Cp + 4 * ch);
+            if (normalized) xv = f4_mul(xv, __ldg(L.csr_norm + k));
+            acc = f4_add(acc, f4_mul(xv, __ldg(L.csr_w + k)));
         }
         *reinterpret_cast<float4 *>(vb + (size_t)(v + 1) * Cp + 4 * ch) = acc;
     }
@@ -258,7 +261,6 @@ template <bool kLabels, bool kFast>
 __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldParams P, const float *__restrict__ unary,
                                                                     float *__restrict__ Q, int32_t *__restrict__ labels, int B, int H,
                                                                     int W, int C, int Cp) {
-    extern __shared__ float4 s_gather[];           // [9][256], fast path only
     const int nch = Cp >> 2;
     const int PW = 32 / nch;                       // pixels per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -306,34 +308,26 @@ __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldPar
                 }
                 const float ca = A.alpha * __ldg(A.norm + spix) * P.weight[0];
                 const float cb = Bl.alpha * __ldg(Bl.norm + sgp) * P.weight[1];
-                // the 9 row gathers go through cp.async into this thread's private smem slots: all of them are in
-                // flight at once by construction (ptxas otherwise serialises register gathers to save registers)
-                float4 *slot = s_gather + threadIdx.x;
-#pragma unroll
-                for (int j = 0; j < 3; ++j) cp_async16(slot + j * 256, va + (size_t)oa[j] * Cp);
-#pragma unroll
-                for (int j = 0; j < 6; ++j) cp_async16(slot + (3 + j) * 256, vbp + (size_t)ob[j] * Cp);
-                // keep the plain loads (unary, barycentric weights, norms) ahead of the wait, not behind it
-                asm volatile("" ::"f"(u.x), "f"(u.y), "f"(u.z), "f"(u.w), "f"(wa[0]), "f"(wa[1]), "f"(wa[2]), "f"(wb[0]), "f"(wb[1]),
-                             "f"(wb[2]), "f"(wb[3]), "f"(wb[4]), "f"(wb[5]), "f"(ca), "f"(cb));
-                cp_async_wait_all();
+                // The 9 row gathers are volatile (ordered) loads and the accumulation chain STARTS with the gather issued
+                // last, so all nine are in flight before the first FFMA can retire (ptxas otherwise interleaves
+                // load/FFMA pairs to save registers and serialises the L2 latencies).
                 float4 ga[3], gb[6];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) ga[j] = slot[j * 256];
+                for (int j = 0; j < 3; ++j) ga[j] = ld_gather4(va + (size_t)oa[j] * Cp);
 #pragma unroll
-                for (int j = 0; j < 6; ++j) gb[j] = slot[(3 + j) * 256];
+                for (int j = 0; j < 6; ++j) gb[j] = ld_gather4(vbp + (size_t)ob[j] * Cp);
                 float4 acc = make_float4(-u.x, -u.y, -u.z, -u.w);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const float w = wa[j] * ca;
-                    acc.x = fmaf(ga[j].x, w, acc.x); acc.y = fmaf(ga[j].y, w, acc.y);
-                    acc.z = fmaf(ga[j].z, w, acc.z); acc.w = fmaf(ga[j].w, w, acc.w);
-                }
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
+                for (int j = 5; j >= 0; --j) {
                     const float w = wb[j] * cb;
                     acc.x = fmaf(gb[j].x, w, acc.x); acc.y = fmaf(gb[j].y, w, acc.y);
                     acc.z = fmaf(gb[j].z, w, acc.z); acc.w = fmaf(gb[j].w, w, acc.w);
+                }
+#pragma unroll
+                for (int j = 2; j >= 0; --j) {
+                    const float w = wa[j] * ca;
+                    acc.x = fmaf(ga[j].x, w, acc.x); acc.y = fmaf(ga[j].y, w, acc.y);
+                    acc.z = fmaf(ga[j].z, w, acc.z); acc.w = fmaf(ga[j].w, w, acc.w);
                 }
                 t4[0] = acc.x; t4[1] = acc.y; t4[2] = acc.z; t4[3] = acc.w;
                 if (active) {
@@ -492,7 +486,7 @@ static const float *run_splat_blur(const LatticeView &L, const float *x, float *
     const int gx = std::max(1, grid_for((long long)(L.M + 1) * nch, 256) / (L.shared ? std::min(B, 8) : 1));
     const int id_splat = L.shared ? kSplatSpatial : kSplatBilateral;
     const int id_blur = L.shared ? kBlurAxisSpatial : kBlurAxisBilateral;
-    PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx, gy), 256, kSplatSmem, st>>>(L, x, va, Cp, normalized));
+    PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, x, va, Cp, normalized));
     float *src = va, *dst = vb;
     for (int j = 0; j < L.Dp1; ++j) {
         PNP_LAUNCH(id_blur, st, blur_axis_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, src, dst, j, Cp));
@@ -576,9 +570,9 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
         const bool fast = warp_path && P.n_kernels == 2 && P.lat[0].Dp1 == 3 && P.lat[0].shared && P.lat[1].Dp1 == 6 && !P.lat[1].shared;
         if (fast) {
             if (with_labels)
-                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<true, true><<<grid_w, 256, kGatherSmem, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
+                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<true, true><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
             else
-                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<false, true><<<grid_w, 256, kGatherSmem, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
+                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<false, true><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
         } else if (warp_path) {
             if (with_labels)
                 PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<true, false><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
