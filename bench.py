@@ -329,12 +329,15 @@ def run_reference_steps(w, n_images, steps, warmup):
     pool = RA.make_pool(min(cores, 2 * n))
     pool.map(abs, range(min(cores, 2 * n)))  # spin the workers up outside the timed region
     times = []
+    timings = {}
     for i in range(warmup + steps):
+        if i == warmup:
+            timings.clear()
         t0 = time.perf_counter()
         RA.reference_batch_confusion(model, w["imgs"][:n].clone(), w["captions"][:n], tokens, tok.decode, w["class_lists"][:n],
                                      w["dataset_ids"][:n], list(w["gts"][:n]), list(w["guides"][:n]),
                                      drop_iter=w["drop_iter"], layer=w["layer"], head=w["head"], threshold=w["threshold"],
-                                     data_type=w["data_type"], mode=w["mode"], n_class=w["n_class"], pool=pool)
+                                     data_type=w["data_type"], mode=w["mode"], n_class=w["n_class"], pool=pool, timings=timings)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     pool.close()
@@ -344,7 +347,8 @@ def run_reference_steps(w, n_images, steps, warmup):
             "sample": "%d of the %d images of one batch per step (same seeds), model pass as BITM:386-457 in torch-CPU fp32 "
                       "(12-block capture, full backward), post-processing as DRV:424-481 via oracle/ (scipy gaussian_filter, "
                       "C restatement of pydensecrf), both reference passes; %.1f s per step" % (n, w["B"], sec),
-            "sec_per_step": sec}
+            "sec_per_step": sec, "model_sec_per_step": timings.get("model_s", 0.0) / len(times),
+            "post_sec_per_step": timings.get("post_s", 0.0) / len(times), "post_workers": min(cores, 2 * n)}
 
 
 def run_reference(args):

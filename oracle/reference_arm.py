@@ -96,7 +96,7 @@ def _post_one(args):
 
 
 def reference_batch_confusion(model, imgs, captions, tokens, decode, class_lists, dataset_ids, gts, guides, *, drop_iter,
-                              layer, head, threshold, data_type, mode, n_class, coco=False, pool=None):
+                              layer, head, threshold, data_type, mode, n_class, coco=False, pool=None, timings=None):
     """One batch of save_img_union_attention on the CPU (DRV:290-521).  Images' post-processing is fanned over
     `pool` (a multiprocessing pool) when given -- the reference itself does it in one Python loop."""
     P = model.patch_num
@@ -104,7 +104,10 @@ def reference_batch_confusion(model, imgs, captions, tokens, decode, class_lists
     def gradcam_fn(x):
         return compute_gradcam_ensemble_reference(model, x, captions, tokens)[0][layer][head]
 
+    import time
+    t0 = time.perf_counter()
     g0, agg, chosen, _ = O.salience_dropout(gradcam_fn, imgs, drop_iter, P)
+    t_model = time.perf_counter() - t0
     B = imgs.shape[0]
     passes = []
     if not coco or drop_iter < 3:
@@ -121,6 +124,9 @@ def reference_batch_confusion(model, imgs, captions, tokens, decode, class_lists
         preds = pool.map(_post_one, jobs) if pool is not None else [_post_one(j) for j in jobs]
         _, hist = O.scores(gts, preds, n_class)
         hists.append(hist)
+    if timings is not None:
+        timings["model_s"] = timings.get("model_s", 0.0) + t_model
+        timings["post_s"] = timings.get("post_s", 0.0) + (time.perf_counter() - t0 - t_model)
     return hists
 
 

@@ -11,6 +11,8 @@
 //           (y-min)/(max-min) costs 2 scalars per channel in the consumer instead of another pass over HBM.
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pnp {
@@ -248,6 +250,95 @@ __global__ void __launch_bounds__(kVCols *kVGroups) blur_vertical_kernel(const f
     }
 }
 
+// ---- pass V, TMA variant: the strip (with its reflected halo rows) is brought in by 1-D bulk async copies
+// (cp.async.bulk, one 128-byte row segment each, source row = reflect(y)) that complete on an mbarrier, so no thread
+// spends issue slots or registers on the tile load; 32-column strips keep the tile at <= 72 KB -> 3 CTAs per SM whose
+// load and FMA phases overlap each other.  Needs W % 4 == 0 and 16-byte aligned maps (else the plain kernel runs).
+constexpr int kTCols = 32;
+constexpr int kTGroups = 8;  // 256 threads
+
+__device__ __forceinline__ void mbar_init(unsigned long long *mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(mbar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(mbar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(mbar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(mbar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kTCols *kTGroups) blur_vertical_tma_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                                             const float *__restrict__ weights, int H, int W, int lw,
+                                                                             int tile_rows, int n_w_padded) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    float *s_w = smem;                // [n_w_padded]  (a multiple of 8 floats: the tile stays 32-byte aligned)
+    float *s_in = smem + n_w_padded;  // [tile_rows + 2*lw + kTapPad + kVRows][kTCols]
+    const int map = blockIdx.z;
+    const int x_base = blockIdx.x * kTCols;
+    const int y_base = blockIdx.y * tile_rows;
+    const int rows_here = min(tile_rows, H - y_base);
+    const int n_virtual = rows_here + 2 * lw;
+    const int n_alloc = tile_rows + 2 * lw + kTapPad + kVRows;
+    const int cols_here = min(kTCols, W - x_base);  // multiple of 4
+    const float *src = in + (long long)map * H * W;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // warp 0 programs the bulk copies
+        if (threadIdx.x == 0) mbar_expect_tx(&s_mbar, (unsigned)(n_virtual * cols_here * 4));
+        __syncwarp();
+        for (int r = threadIdx.x; r < n_virtual; r += 32)
+            bulk_copy_g2s(s_in + r * kTCols, src + (long long)reflect_index(y_base - lw + r, H) * W + x_base, (unsigned)(cols_here * 4),
+                          &s_mbar);
+    }
+    // everything the copies do not write: weights, padding rows, columns past the image edge
+    for (int j = threadIdx.x; j < n_w_padded; j += blockDim.x) s_w[j] = weights[j];
+    const int cx = threadIdx.x % kTCols;
+    for (int r = threadIdx.x / kTCols; r < n_alloc; r += kTGroups)
+        if (r >= n_virtual || cx >= cols_here) s_in[r * kTCols + cx] = 0.f;
+    __syncthreads();
+    mbar_wait(&s_mbar, 0);
+    float *dst = out + (long long)map * H * W;
+    const int grp = threadIdx.x / kTCols;
+    const int gx = x_base + cx;
+    for (int yl = grp * kVRows; yl < rows_here; yl += kTGroups * kVRows) {
+        float acc[kVRows];
+#pragma unroll
+        for (int r = 0; r < kVRows; ++r) acc[r] = 0.f;
+        for (int jc = 0; jc < 2 * lw + 1; jc += 8) {
+            float vv[kVRows + 7], ww[8];
+#pragma unroll
+            for (int i = 0; i < kVRows + 7; ++i) vv[i] = s_in[(yl + jc + i) * kTCols + cx];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ww[i] = s_w[jc + i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int r = 0; r < kVRows; ++r) acc[r] = fmaf(ww[i], vv[i + r], acc[r]);
+        }
+        if (gx < W) {
+#pragma unroll
+            for (int r = 0; r < kVRows; ++r)
+                if (yl + r < rows_here) dst[(long long)(y_base + yl + r) * W + gx] = acc[r];
+        }
+    }
+}
+
 constexpr int kHRows = 32;    // rows per CTA in pass H (one per lane)
 constexpr int kHCols = 16;    // output columns per thread per sweep
 constexpr int kHGroups = 16;  // column groups per CTA (32 * 16 = 512 threads)
@@ -395,8 +486,8 @@ extern "C" int pnp_threshold_upsample(const float *class_maps, float *out, void 
 
 namespace {
 struct BlurPlan {
-    int lw, n_w_padded, tile_rows, tile_cols, pitch;
-    size_t smem_v, smem_h;
+    int lw, n_w_padded, tile_rows, tile_cols, pitch, tile_rows_tma;
+    size_t smem_v, smem_h, smem_v_tma;
     size_t off_keys, off_tmp, total;
 };
 constexpr size_t kSmemBudget = 200 * 1024;
@@ -412,6 +503,13 @@ bool make_blur_plan(int n_maps, int H, int W, double sigma, BlurPlan &p) {
     if (max_rows <= fixed_rows + kVRows) return false;
     p.tile_rows = (int)std::min<size_t>((size_t)H, (max_rows - fixed_rows) / kVRows * kVRows);
     p.smem_v = (p.n_w_padded + (p.tile_rows + fixed_rows) * kVCols) * sizeof(float);
+    // pass V, TMA variant: 32-column strips, <= 72 KB per CTA so that three CTAs share an SM
+    {
+        const size_t budget = 72 * 1024;
+        size_t rows_max = (budget - p.n_w_padded * sizeof(float)) / (kTCols * sizeof(float));
+        p.tile_rows_tma = rows_max > fixed_rows + kVRows ? (int)std::min<size_t>((size_t)H, (rows_max - fixed_rows) / kVRows * kVRows) : 0;
+        p.smem_v_tma = (p.n_w_padded + (p.tile_rows_tma + fixed_rows) * kTCols) * sizeof(float);
+    }
     // pass H: full rows if they fit, else column tiles
     size_t out_floats = (size_t)kHRows * (kHGroups * kHCols + 1);
     size_t max_pitch = (kSmemBudget - (p.n_w_padded + out_floats) * sizeof(float)) / (kHRows * sizeof(float));
@@ -449,8 +547,16 @@ extern "C" int pnp_gaussian_blur(const float *in, float *out, float *minmax, voi
     e = cudaFuncSetAttribute(blur_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_h);
     if (e != cudaSuccess) return cuda_err(e);
     blur_prologue_kernel<<<1, 256, 0, st>>>(weights, keys, n_maps, p.lw, p.n_w_padded, sigma);
-    PNP_LAUNCH(kBlurVertical, st, blur_vertical_kernel<<<dim3(ceil_div(W, kVCols), ceil_div(H, p.tile_rows), n_maps), kVCols * kVGroups, p.smem_v, st>>>(
-        in, tmp, weights, H, W, p.lw, p.tile_rows, p.n_w_padded));
+    const bool tma_ok = p.tile_rows_tma > 0 && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+    if (tma_ok) {
+        e = cudaFuncSetAttribute(blur_vertical_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_v_tma);
+        if (e != cudaSuccess) return cuda_err(e);
+        PNP_LAUNCH(kBlurVertical, st, blur_vertical_tma_kernel<<<dim3(ceil_div(W, kTCols), ceil_div(H, p.tile_rows_tma), n_maps), kTCols * kTGroups, p.smem_v_tma, st>>>(
+            in, tmp, weights, H, W, p.lw, p.tile_rows_tma, p.n_w_padded));
+    } else {
+        PNP_LAUNCH(kBlurVertical, st, blur_vertical_kernel<<<dim3(ceil_div(W, kVCols), ceil_div(H, p.tile_rows), n_maps), kVCols * kVGroups, p.smem_v, st>>>(
+            in, tmp, weights, H, W, p.lw, p.tile_rows, p.n_w_padded));
+    }
     PNP_LAUNCH(kBlurHorizontal, st, blur_horizontal_kernel<<<dim3(ceil_div(W, p.tile_cols), ceil_div(H, kHRows), n_maps), kHRows * kHGroups, p.smem_h, st>>>(
         tmp, out, weights, keys, H, W, p.lw, p.tile_cols, p.pitch, p.n_w_padded));
     blur_minmax_decode_kernel<<<ceil_div(n_maps, 256), 256, 0, st>>>(keys, minmax, n_maps);
