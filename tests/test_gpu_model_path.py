@@ -120,3 +120,49 @@ def test_postprocess_entry_points_match_oracle(dev):
     assert np.allclose(b, O.blurring(x[1], (H, W)), rtol=1e-3, atol=1e-4)
     s = R.Scale_0_1(x.clone().to(dev))
     assert torch.equal(s.cpu(), O.scale_0_1(x.clone()))
+
+
+def test_config0_full_size_model_single_image(dev):
+    """BASELINE.json configs[0]: one 336x336 image, BLIP ITM-large shape (random init), VOC 20 classes, drop_iter 1,
+    blur only -- the reference's CPU-runnable case.  CPU: the reference procedure (torch-CPU model pass with hooks and
+    full backward, then oracle post-processing).  GPU: the product pipeline with the SAME weights."""
+    import copy
+    from oracle import hotpath as O
+    from oracle import reference_arm as RA
+    from pnp_ovss_b200 import pipeline
+    from pnp_ovss_b200.blip_itm import BlipITM
+    voc = ["aeroplane", "bicycle", "bird", "boat", "bottle", "bus", "car", "cat", "chair", "cow", "table", "dog", "horse",
+           "motorbike", "person", "plant", "sheep", "sofa", "train", "television"]
+    tok = synth.SyntheticWordPieceTokenizer()
+    caps = ["A picture of " + " ".join(voc)]
+    tokens = tok(caps, padding="max_length", max_length=500)
+    torch.manual_seed(2024)
+    model = BlipITM(img_size=336, tokenizer=tok).eval()
+    g = torch.Generator().manual_seed(7)
+    imgs = torch.randn(1, 3, 336, 336, generator=g)
+    gts = [synth.gt_labels(3, 336, 336, 21)]
+    guides = [synth.guide_image(3, 336, 336)]
+    ids = [list(range(1, 21))]
+    ref_model = RA.install_reference_capture(copy.deepcopy(model))
+    want = RA.compute_gradcam_ensemble_reference(ref_model, imgs, caps, tokens)[0][7][9]
+    gm = model.to(dev).requires_grad_(False)
+    got, _ = gm.gradcam(imgs.to(dev), caps, tokens.to(dev), layer=7, head=9)
+    scale = float(want.abs().max())
+    assert scale > 0
+    rel = (got.cpu() - want).abs().max().item() / scale
+    assert rel <= 1e-3, "block-8 head-9 GradCAM of the full-size model differs by %g of its max" % rel
+    # post-processing of the SAME map on both sides (drop_iter 1 -> only the round-0 pass, Scale_0_1 on, blur only)
+    with np.errstate(all="ignore"):
+        h_ref, _, _ = O.batch_confusion(lambda x: want, imgs, tokens.input_ids, tok.decode, [voc], ids, gts, guides, drop_iter=1,
+                                        patch_num=21, threshold=0.15, data_type="voc", mode="blur", n_class=21)
+    h_gpu, h_agg, _ = pipeline.batch_confusion(lambda x: want.to(dev), imgs.to(dev), tokens.input_ids.tolist(), tok.decode, [voc], ids,
+                                               gts, guides, drop_iter=1, patch_num=21, threshold=0.15, data_type="voc", mode="blur",
+                                               n_class=21)
+    assert h_agg is None
+    assert np.array_equal(h_gpu.cpu().numpy(), h_ref)          # identical saliency maps in -> bit-exact confusion matrix
+    # and the whole thing end to end from the GPU model's own map: report-level agreement
+    h_e2e, _, _ = pipeline.batch_confusion(lambda x: gm.gradcam(x, caps, tokens.to(dev), layer=7, head=9)[0], imgs.to(dev),
+                                           tokens.input_ids.tolist(), tok.decode, [voc], ids, gts, guides, drop_iter=1, patch_num=21,
+                                           threshold=0.15, data_type="voc", mode="blur", n_class=21)
+    import smoke_case
+    assert smoke_case.disagreement(h_e2e.cpu().numpy(), h_ref) <= 0.02
