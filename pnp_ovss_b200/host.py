@@ -83,3 +83,24 @@ def shard_range(n_items, rank, world_size):
     base, extra = divmod(n_items, world_size)
     start = rank * base + min(rank, extra)
     return start, start + base + (1 if rank < extra else 0)
+
+
+def parse_gpt4o_classes(answer, names, keep_above=70):
+    """The class-list parser of Load_predicted_classes (DRV:726-787): `answer` is GPT-4o's text
+    "[id: name, ...], [p%, ...]"; classes with probability > 70 are kept (ids are 1-based); no answer at all means
+    class 'wall'-at-index-1 per listed item; an empty selection falls back to class 0.
+    Returns (best_class_idx 0-based, class names, caption "A picture of c1 c2 ...")."""
+    parts = (answer.replace(']\n\n[', '], [').replace('],\n\n[', '], [').replace('], \n[', '], [ ').replace(']\n[', '], [ ')
+             .replace('],\n[', '], [ ').strip("][").split("], ["))
+    cls_list = parts[0].split(",")
+    if len(parts) == 1 and parts[0] == '':
+        cls_list = ["1: 'wall'" for _ in range(len(cls_list))]
+        prob_list = [100 for _ in range(len(cls_list))]
+    else:
+        prob_list = [int(p.split(":")[-1].split("%")[0]) for p in parts[1].split(",")]
+    idx = [int(cls_list[i].split(":")[0]) for i, p in enumerate(prob_list) if p > keep_above]
+    best = [i - 1 for i in idx]
+    cls = [names[i - 1] for i in idx]
+    if not best:
+        best, cls = [0], [names[0]]
+    return best, cls, "A picture of " + " ".join(cls)

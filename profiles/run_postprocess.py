@@ -9,7 +9,7 @@ for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
 import numpy as np
 import torch
 
-import synth
+from pnp_ovss_b200 import synthetic as synth
 from pnp_ovss_b200 import ops, pipeline
 
 iters = int(sys.argv[1]) if len(sys.argv) > 1 else 2

@@ -130,3 +130,23 @@ def test_save_hist_npy_layout(tmp_path):
     assert p.endswith("all_drop_hist_with_filtered_caption/img_2007_000033_max_blocknum_8_atthead_9.npy")
     back = np.load(p)
     assert back.dtype == np.float64 and np.array_equal(back, h.numpy())
+
+
+def test_gpt4o_class_list_parser_matches_reference():
+    """host.parse_gpt4o_classes vs the reference's Load_predicted_classes run on its own shipped GPT-4o answers
+    (tests/golden/gpt4o_golden.json, made by tests/golden/make_golden_gpt4o.py)."""
+    import json
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpt4o_golden.json")))
+    n = 0
+    for data_type, blob in cases.items():
+        names = ["name%03d" % i for i in range(blob["n_names"])]
+        for c in blob["cases"]:
+            if "error" in c:
+                with pytest.raises(Exception):
+                    host.parse_gpt4o_classes(c["raw"], names)
+                continue
+            best, cls, cap = host.parse_gpt4o_classes(c["raw"], names)
+            assert best == c["best_class_idx"] and cap == c["caption"], (data_type, c["raw"])
+            n += 1
+    assert n > 300
+    assert host.parse_gpt4o_classes("[3: 'bird'], [60%]", ["a", "b", "c"])[0] == [0]       # nothing above 70 -> class 0
