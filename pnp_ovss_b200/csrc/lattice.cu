@@ -373,7 +373,8 @@ constexpr int kGroup = 8;
 
 __global__ void __launch_bounds__(256) csr_sort_short_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ csr_tmp,
                                                              const float *__restrict__ bary, int32_t *__restrict__ csr_pix,
-                                                             float *__restrict__ csr_w, int32_t *counters, int Dp1) {
+                                                             float *__restrict__ csr_w, int32_t *counters, int32_t *__restrict__ long_rows,
+                                                             int Dp1) {
     const int M = counters[0];
     const int sub = threadIdx.x % kGroup;
     int longest = 0;
@@ -381,7 +382,10 @@ __global__ void __launch_bounds__(256) csr_sort_short_kernel(const int32_t *__re
          v += (long long)gridDim.x * blockDim.x / kGroup) {
         const int beg = row_ptr[v], len = row_ptr[v + 1] - beg;
         longest = max(longest, len);
-        if (len > kShortRow) continue;
+        if (len > kShortRow) {  // left to csr_sort_long_kernel, which walks this compact list
+            if (sub == 0) long_rows[atomicAdd(&counters[3], 1)] = (int)v;
+            continue;
+        }
         for (int i = sub; i < len; i += kGroup) {
             const int e = csr_tmp[beg + i];
             int rank = 0;
@@ -396,11 +400,12 @@ __global__ void __launch_bounds__(256) csr_sort_short_kernel(const int32_t *__re
 
 __global__ void __launch_bounds__(256) csr_sort_long_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ csr_tmp,
                                                             const float *__restrict__ bary, int32_t *__restrict__ csr_pix,
-                                                            float *__restrict__ csr_w, const int32_t *__restrict__ counters, int Dp1) {
-    const int M = counters[0];
-    for (int v = blockIdx.x; v < M; v += gridDim.x) {
+                                                            float *__restrict__ csr_w, const int32_t *__restrict__ counters,
+                                                            const int32_t *__restrict__ long_rows, int Dp1) {
+    const int n_long = counters[3];
+    for (int i_row = blockIdx.x; i_row < n_long; i_row += gridDim.x) {
+        const int v = long_rows[i_row];
         const int beg = row_ptr[v], len = row_ptr[v + 1] - beg;
-        if (len <= kShortRow) continue;
         for (int i = threadIdx.x; i < len; i += blockDim.x) {
             const int e = csr_tmp[beg + i];
             int rank = 0;
@@ -694,10 +699,11 @@ static int build_impl(pnp_lattice *lat, const uint8_t *rgb, int H, int W, float 
     if (rc != PNP_OK) return rc;
     if ((e = cudaMemsetAsync(row_cnt, 0, (size_t)(n_entries + 1) * 4, st)) != cudaSuccess) return cuda_err(e);
     csr_fill_kernel<<<big_grid, 256, 0, st>>>(lat->offset, lat->row_ptr, row_cnt, csr_tmp, n_entries);
+    // rows longer than kShortRow are rare (flat-coloured regions); prefix (free again) holds their compact list
     csr_sort_short_kernel<<<big_grid, 256, 0, st>>>(lat->row_ptr, csr_tmp, lat->bary, lat->csr_pix, lat->csr_w, lat->counters,
-                                                    D + 1);
+                                                    prefix, D + 1);
     csr_sort_long_kernel<<<kNumSMs * 8, 256, 0, st>>>(lat->row_ptr, csr_tmp, lat->bary, lat->csr_pix, lat->csr_w, lat->counters,
-                                                      D + 1);
+                                                      prefix, D + 1);
     lattice_neighbors_kernel<D><<<big_grid, 256, 0, st>>>(keys_dense, table, slot_id, vstart, lat->counters, lat->nbr,
                                                           lat->n_images, cap - 1, lat->vertex_stride);
     rowlen_window_sort_kernel<<<big_grid, 256, 0, st>>>(lat->row_ptr, lat->counters, lat->perm);

@@ -84,6 +84,22 @@ def test_bilateral_lattice_matches_oracle_batched(dev, ops, D, kind):
     assert lat.M == base
 
 
+def test_flat_guide_image_long_csr_rows(dev, ops, D):
+    """A constant-colour guide collapses the bilateral lattice to a coarse spatial one: CSR rows with thousands of
+    entries (the csr_sort_long path) must still reproduce the sequential reference bit for bit."""
+    H, W, C = 96, 80, 3
+    img = np.full((H, W, 3), 77, np.uint8)
+    lat = ops.build_lattice(H, W, 50.0, rgb=torch.from_numpy(img[None]).to(dev), srgb=5.0)
+    ref = D.Lattice(_features(H, W, 50.0, img, 5.0))
+    assert lat.M == ref.M and lat.struct.max_row > 256
+    _check_lattice(lat, ref)
+    crf = D.DenseCRF2D(W, H, C)
+    crf.addPairwiseBilateral(50, 5, img, 10)
+    x = np.random.default_rng(2).random((C, H * W)).astype(np.float32)
+    y = ops.crf_unpack(ops.crf_filter(lat, ops.crf_pack(torch.from_numpy(x[None]).to(dev))), C)[0].cpu().numpy()
+    assert np.array_equal(y, crf.kernel_apply(0, x))
+
+
 def test_norm_and_filter_match_oracle(dev, ops, D):
     H, W, C = 48, 64, 5
     N = H * W
