@@ -220,6 +220,8 @@ int pnp_profile_start(unsigned kernel_mask);
 /* Waits for the recorded events; total_ms[id] / n_launches[id] for id < n_ids (host arrays). */
 int pnp_profile_stop(float *total_ms, int *n_launches, int n_ids);
 const char *pnp_profile_kernel_name(int kernel_id);
+/* enabled != 0: time only launches enqueued on `stream` (kernels overlapped on other streams are skipped). */
+int pnp_profile_filter_stream(pnp_stream_t stream, int enabled);
 
 #ifdef __cplusplus
 }

@@ -58,6 +58,7 @@ SIGNATURES = {
     "pnp_profile_start": (c_int, [ctypes.c_uint]),
     "pnp_profile_stop": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int), c_int]),
     "pnp_profile_kernel_name": (ctypes.c_char_p, [c_int]),
+    "pnp_profile_filter_stream": (c_int, [c_void_p, c_int]),
     "pnp_argmax_channels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pnp_confusion_accumulate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                          c_int, c_void_p]),

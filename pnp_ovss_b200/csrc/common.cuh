@@ -74,12 +74,15 @@ enum KernelId {
 };
 namespace prof {
 extern unsigned g_mask;
+extern bool g_filter;           // when set, only launches on g_filter_stream are timed
+extern cudaStream_t g_filter_stream;
 void begin(int id, cudaStream_t st);
 void end(int id, cudaStream_t st);
+static inline bool on(int id, cudaStream_t st) { return (g_mask & (1u << id)) && (!g_filter || st == g_filter_stream); }
 }  // namespace prof
 #define PNP_LAUNCH(id, st, ...)                         \
     do {                                                \
-        if (pnp::prof::g_mask & (1u << (id))) {         \
+        if (pnp::prof::on((id), (st))) {                \
             pnp::prof::begin((id), (st));               \
             __VA_ARGS__;                                \
             pnp::prof::end((id), (st));                 \

@@ -667,7 +667,7 @@ static int build_impl(pnp_lattice *lat, const uint8_t *rgb, int H, int W, float 
     auto *vb = reinterpret_cast<float *>(ws + L.off_vb);
 
     cudaError_t e;
-    const bool timed = (prof::g_mask & (1u << kLatticeBuild)) != 0;
+    const bool timed = prof::on(kLatticeBuild, st);
     if (timed) prof::begin(kLatticeBuild, st);
     if ((e = cudaMemsetAsync(table, 0xFF, slots * 8, st)) != cudaSuccess) return cuda_err(e);
     if ((e = cudaMemsetAsync(first, 0x7F, slots * 4, st)) != cudaSuccess) return cuda_err(e);

@@ -19,6 +19,8 @@ extern "C" const char *pnp_error_string(int code) {
 namespace pnp {
 namespace prof {
 unsigned g_mask = 0;
+bool g_filter = false;
+cudaStream_t g_filter_stream = nullptr;
 struct Span { int id; cudaEvent_t a, b; };
 static std::vector<Span> g_spans;   // recorded this session
 static std::vector<Span> g_pool;    // reusable event pairs
@@ -80,5 +82,11 @@ extern "C" int pnp_profile_stop(float *total_ms, int *n_launches, int n_ids) {
             if (n_launches) n_launches[s.id] += 1;
         }
     }
+    return PNP_OK;
+}
+
+extern "C" int pnp_profile_filter_stream(pnp_stream_t stream, int enabled) {
+    pnp::prof::g_filter = enabled != 0;
+    pnp::prof::g_filter_stream = pnp::as_stream(stream);
     return PNP_OK;
 }

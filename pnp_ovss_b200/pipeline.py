@@ -14,10 +14,11 @@ SAVE_LEN = 10      # DRV:643
 
 
 # ---------------------------------------------------------------------------------------------- (c) loop
-def salience_dropout_loop(gradcam_fn, imgs, norm_imgs, drop_iter, P, save_len=SAVE_LEN):
+def salience_dropout_loop(gradcam_fn, imgs, norm_imgs, drop_iter, P, save_len=SAVE_LEN, after_round0=None):
     """DRV:564-722.  gradcam_fn(imgs [B,3,S,S] cuda) -> [B,T-1,P,P] stands for
     compute_gradcam_ensemble(...)[layer][head].  imgs / norm_imgs are modified in place (pixel blocks zeroed).
-    Returns (gradcam_0, gradcam_agg or None, chosen int32 [B, save_len*drop_iter] or None)."""
+    after_round0(g0) is called as soon as the round-0 map is final (its post-processing can start while the remaining
+    rounds run).  Returns (gradcam_0, gradcam_agg or None, chosen int32 [B, save_len*drop_iter] or None)."""
     if drop_iter == 1:  # DRV:565-575
         return gradcam_fn(imgs).detach().clone(), None, None
     B, _, S, _ = imgs.shape
@@ -32,14 +33,16 @@ def salience_dropout_loop(gradcam_fn, imgs, norm_imgs, drop_iter, P, save_len=SA
             agg = torch.empty_like(g)
         ops.salience_dropout_round(g, agg, chosen, save_len * r, imgs, norm_imgs, P, patch, 3, Tm - 1, save_len, r,
                                    ensemble_r=g0 if r == 0 else None)
+        if r == 0 and after_round0 is not None:
+            after_round0(g0)
     return g0, agg, chosen
 
 
 # ---------------------------------------------------------------------------------------------- (b) batched merge
-def merge_tokens_batch(gradcam, token_ids, decode, class_lists):
-    """gradcam [B,T-1,P,P]; token_ids [B,>=T] host ints; returns a list of per-image [C_b,P,P] CUDA tensors
-    (one pnp_token_merge launch over the batch, padded to the largest C)."""
-    B = gradcam.shape[0]
+def segment_tensors(token_ids, decode, class_lists, dev):
+    """Host walk of the WordPiece strings (host.build_token_segments) -> the three [B,Cmax] device tables of
+    pnp_token_merge.  Depends on the captions only, so both reference passes of a batch share it."""
+    B = len(class_lists)
     Cmax = max(len(c) for c in class_lists)
     start = np.zeros((B, Cmax), np.int32)
     length = np.zeros((B, Cmax), np.int32)
@@ -48,10 +51,16 @@ def merge_tokens_batch(gradcam, token_ids, decode, class_lists):
         toks = host.token_strings(list(token_ids[b]), decode)
         for c, (s, l, d) in enumerate(host.build_token_segments(toks, len(class_lists[b]))):
             start[b, c], length[b, c], div[b, c] = s, l, d
-    dev = gradcam.device
-    maps = ops.token_merge(gradcam.contiguous(), torch.from_numpy(start).to(dev), torch.from_numpy(length).to(dev),
-                           torch.from_numpy(div).to(dev), row_offset=3)
-    return [maps[b, :len(class_lists[b])] for b in range(B)]
+    return torch.from_numpy(start).to(dev), torch.from_numpy(length).to(dev), torch.from_numpy(div).to(dev)
+
+
+def merge_tokens_batch(gradcam, token_ids, decode, class_lists, segs=None):
+    """gradcam [B,T-1,P,P]; token_ids [B,>=T] host ints; returns a list of per-image [C_b,P,P] CUDA tensors
+    (one pnp_token_merge launch over the batch, padded to the largest C)."""
+    if segs is None:
+        segs = segment_tensors(token_ids, decode, class_lists, gradcam.device)
+    maps = ops.token_merge(gradcam.contiguous(), segs[0], segs[1], segs[2], row_offset=3)
+    return [maps[b, :len(class_lists[b])] for b in range(gradcam.shape[0])]
 
 
 # ---------------------------------------------------------------------------------------------- (d)(e)(f)
@@ -126,52 +135,106 @@ def _as_device_batch(items, members, dtype, dev):
     return torch.stack([torch.as_tensor(np.ascontiguousarray(items[b])).to(dtype) for b in members]).to(dev)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_ids, gts, guides, *, drop_iter, patch_num,
-                    threshold, data_type, mode, n_class, coco=False, crf=None, norm_imgs=None, stats=None):
+                    threshold, data_type, mode, n_class, coco=False, crf=None, norm_imgs=None, stats=None, overlap=True):
     """One batch of save_img_union_attention: returns (hist_round0 or None, hist_all_drop or None, chosen) with the
     matrices as int64 CUDA tensors [n,n] -- what the reference saves to hist_withfiltered_caption/ and
     all_drop_hist_with_filtered_caption/ (DRV:495-520).  `coco` selects the COCO driver's deltas (DRVC:420, 527, 602).
 
     imgs [B,3,S,S] cuda (modified in place by the DropOut rounds); gts: float32 [H,W] arrays (list) or one CUDA tensor
     [B,H,W]; guides: uint8 [H,W,3] arrays (list) or one CUDA tensor [B,H,W,3]; dataset_ids[b][i] = id written for
-    local class i."""
+    local class i.
+
+    overlap: the bilateral lattice build and the whole round-0 pass (which needs only the round-0 map) run on a second
+    CUDA stream while DropOut rounds 1..R-1 (model passes) occupy the main stream; results are identical either way."""
     dev = imgs.device
-    _mark(stats, "start")
-    g0, agg, chosen = salience_dropout_loop(gradcam_fn, imgs, norm_imgs, drop_iter, patch_num)
-    _mark(stats, "model+gradcam+dropout")
     B = imgs.shape[0]
-    # bucket images by everything a launch must share
+    main = torch.cuda.current_stream(dev)
+    round0_scored = not coco or drop_iter < 3
+    timed_stages = stats is not None and "events" in stats
+    use_side = bool(overlap) and drop_iter > 1 and round0_scored and not timed_stages
+    side = _side_stream(dev) if use_side else main
+    use_crf = bool(mode) and "crf" in mode
+    crf_p = dict(CRF_DEFAULTS)
+    crf_p.update(crf or {})
+    _mark(stats, "start")
+
+    # everything that depends on the inputs only: buckets, device copies, relabel LUTs, token segment tables
     buckets = {}
     for b in range(B):
         C = len(class_lists[b])
         with_bg = host.add_background_rule(data_type, C)
-        key = (C, with_bg, tuple(gts[b].shape))
-        buckets.setdefault(key, []).append(b)
-
-    passes = []  # (name, maps, rescale): the reference scores the round-0 map and the accumulated map
-    if not coco or drop_iter < 3:
-        passes.append(("round0", g0, True))      # 1-round path applies Scale_0_1 (DRV:362)
-    if agg is not None:
-        passes.append(("all_drop", agg, coco))   # N-round path: only the COCO driver rescales (DRV:438 vs DRVC:527)
-    hists = {name: torch.zeros((n_class, n_class), dtype=torch.int64, device=dev) for name, _, _ in passes}
+        buckets.setdefault((C, with_bg, tuple(gts[b].shape)), []).append(b)
+    inputs = {}
+    for key, members in buckets.items():
+        with_bg = key[1]
+        inputs[key] = (_as_device_batch(gts, members, torch.float32, dev), _as_device_batch(guides, members, torch.uint8, dev),
+                       torch.tensor([host.relabel_lut(dataset_ids[b], with_bg) for b in members], dtype=torch.int32, device=dev))
+    segs = segment_tensors(token_ids, decode, class_lists, dev)
+    hists = {}
+    if round0_scored:
+        hists["round0"] = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
+    if drop_iter > 1:
+        hists["all_drop"] = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
     bad = torch.zeros(1, dtype=torch.int32, device=dev)
-    merged = {name: merge_tokens_batch(gm, token_ids, decode, class_lists) for name, gm, _ in passes}
-    _mark(stats, "merge")
-    use_crf = bool(mode) and "crf" in mode
-    for (C, with_bg, (H, W)), members in buckets.items():
-        gt = _as_device_batch(gts, members, torch.float32, dev)
-        gd = _as_device_batch(guides, members, torch.uint8, dev)
-        lut = torch.tensor([host.relabel_lut(dataset_ids[b], with_bg) for b in members], dtype=torch.int32, device=dev)
-        lat_b = None
-        if use_crf:  # one bilateral lattice per bucket, shared by both passes (the guide images are the same)
-            p = dict(CRF_DEFAULTS)
-            p.update(crf or {})
-            lat_b = ops.build_lattice(H, W, p["bi_xy_std"], rgb=gd, srgb=p["bi_rgb_std"])
+    ev_inputs = main.record_event() if use_side else None
+    lattices = {}
+    ev_lattices = None
+
+    def build_lattices():  # one bilateral lattice per bucket, shared by both passes (the guide images are the same)
+        if use_crf:
+            for key in buckets:
+                lattices[key] = ops.build_lattice(key[2][0], key[2][1], crf_p["bi_xy_std"], rgb=inputs[key][1], srgb=crf_p["bi_rgb_std"])
+                _SPATIAL.get(key[2][0], key[2][1], crf_p["pos_xy_std"], dev)
             _mark(stats, "lattice")
-        for name, _, rescale in passes:
-            cm = torch.stack([merged[name][b] for b in members]).contiguous()
-            postprocess_batch(cm, gd, gt, lut, hists[name], threshold=threshold, rescale=rescale, with_background=with_bg,
-                              mode=mode, n_class=n_class, crf=crf, bad_count=bad, stats=stats, bilateral=lat_b)
+
+    def run_pass(name, gmaps, rescale):
+        merged = merge_tokens_batch(gmaps, token_ids, decode, class_lists, segs)
+        _mark(stats, "merge")
+        for key, members in buckets.items():
+            gt, gd, lut = inputs[key]
+            cm = torch.stack([merged[b] for b in members]).contiguous()
+            postprocess_batch(cm, gd, gt, lut, hists[name], threshold=threshold, rescale=rescale, with_background=key[1],
+                              mode=mode, n_class=n_class, crf=crf, bad_count=bad, stats=stats, bilateral=lattices.get(key))
+
+    def after_round0(g0):
+        nonlocal ev_lattices
+        if not use_side:
+            return
+        ev_r0 = main.record_event()
+        with torch.cuda.stream(side):
+            side.wait_event(ev_inputs)
+            build_lattices()                       # runs under round 0's model pass; host waits for the build only
+            ev_lattices = side.record_event()
+            side.wait_event(ev_r0)
+            for t in (g0, bad, hists["round0"]) + tuple(x for v in inputs.values() for x in v) + tuple(segs):
+                t.record_stream(side)
+            run_pass("round0", g0, True)           # 1-round path applies Scale_0_1 (DRV:362)
+
+    g0, agg, chosen = salience_dropout_loop(gradcam_fn, imgs, norm_imgs, drop_iter, patch_num, after_round0=after_round0)
+    _mark(stats, "model+gradcam+dropout")
+    if use_side:
+        main.wait_event(ev_lattices)
+        for lat in lattices.values():
+            lat.storage.record_stream(main)
+    else:
+        build_lattices()
+        if round0_scored:
+            run_pass("round0", g0, True)
+    if agg is not None:
+        run_pass("all_drop", agg, coco)            # N-round path: only the COCO driver rescales (DRV:438 vs DRVC:527)
+    if use_side:
+        main.wait_stream(side)
     if int(bad.item()):
         raise PnpError("a relabelled id fell outside [0, n_class)")
     return hists.get("round0"), hists.get("all_drop"), chosen
