@@ -30,14 +30,6 @@ __device__ __forceinline__ float4 ld_gather4(const float *p) {  // ordered (vola
     asm volatile("ld.global.ca.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
 // rows of a value buffer that one image (shared lattice) or the whole batch (batched lattice) occupies
 __host__ __device__ __forceinline__ long long value_rows(const LatticeView &L, int B) {
     return L.shared ? (long long)B * (L.M + 1) : (long long)L.M + 1;
@@ -250,7 +242,6 @@ __global__ void __launch_bounds__(256) meanfield_update_kernel(MeanFieldParams P
     }
 }
 
-constexpr int kGatherSmem = 9 * 256 * 16;  // fast path: 9 float4 slots per thread
 
 // Warp-level variant for Cp <= 128 (nch <= 32 chunks): the nch lanes of a pixel sit in one warp, so the softmax
 // reductions are shuffles -- no shared memory, no block barrier, warps never wait for each other's gathers.

@@ -31,16 +31,19 @@ def _to_dev(x, dtype=torch.float32):
 
 # ------------------------------------------------------------------------------------------------- a5: Scale_0_1
 def Scale_0_1(AA):
-    """DRV:1078-1094.  Per-channel min-max rescale, in place like the reference, on whatever device AA lives.
-    (On the fused path this is folded into pnp_threshold_upsample(rescale=1); this entry point exists for callers
-    that use it standalone and is plain tensor glue, not a kernel.)"""
+    """DRV:1078-1094.  Per-channel min-max rescale, in place like the reference.  Computed on the GPU (host tensors
+    are uploaded and the result is written back into AA); on the fused path it is folded into
+    pnp_threshold_upsample(rescale=1), this entry point exists for callers that use it standalone and is tensor glue
+    around device reductions, not a kernel of its own."""
     if AA.dim() == 2:
         return AA
-    shape = AA.shape
-    flat = AA.view(*shape[:-2], -1)
-    flat -= flat.min(-1, keepdim=True)[0]
-    flat /= flat.max(-1, keepdim=True)[0]
-    return flat.view(shape)
+    x = AA if AA.is_cuda else _to_dev(AA, AA.dtype)
+    shape = x.shape
+    flat = x.reshape(*shape[:-2], -1)
+    flat = flat - flat.min(-1, keepdim=True)[0]
+    flat = flat / flat.max(-1, keepdim=True)[0]
+    AA.copy_(flat.view(shape))
+    return AA
 
 
 # ------------------------------------------------------------------------------------------------- a6: blurring
@@ -55,15 +58,14 @@ def blurring(att_resize, img_shape, scale=0.05):
 
 # ------------------------------------------------------------------------------------------------- a8: pydensecrf surface
 def unary_from_softmax(sm, scale=None, clip=1e-5):
-    """pydensecrf.utils.unary_from_softmax (host numpy, as upstream): -log(clip(p)) as float32 [C, N]."""
-    sm = np.asarray(sm)
-    num_cls = sm.shape[0]
+    """pydensecrf.utils.unary_from_softmax: -log(clip(p)) as float32 [C, N] (numpy in, numpy out, computed on the GPU)."""
+    x = _to_dev(np.asarray(sm), torch.float64 if np.asarray(sm).dtype == np.float64 else torch.float32)
+    num_cls = x.shape[0]
     if scale is not None:
-        uniform = np.ones(sm.shape) / num_cls
-        sm = scale * sm + (1 - scale) * uniform
+        x = scale * x + (1 - scale) / num_cls
     if clip is not None:
-        sm = np.clip(sm, clip, 1.0)
-    return -np.log(sm).reshape([num_cls, -1]).astype(np.float32)
+        x = x.clamp(clip, 1.0)
+    return (-x.log()).reshape(num_cls, -1).to(torch.float32).cpu().numpy()
 
 
 _SPATIAL_CACHE = {}
