@@ -268,3 +268,65 @@ def test_other_baseline_configs_properties(dev, ops, name, C, S, with_bg):
     assert torch.equal(ops.argmax_channels(q_cn), labels)
     lut_l = luts[0].long()
     assert torch.equal(out[0][1].view(B, -1), lut_l[labels.long()].float())
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("order", ["bilateral_only", "gaussian_only", "bilateral_then_gaussian"])
+def test_inference_general_kernel_sets(dev, D, order):
+    """Kernel sets other than [gaussian, bilateral] take the generic (exactly ordered) slice path."""
+    from pnp_ovss_b200 import reference_api as R
+    H, W, C = 33, 47, 3
+    img = synth.guide_image(12, H, W)
+    p = np.random.default_rng(5).random((C, H, W)).astype(np.float32)
+    p /= p.sum(0, keepdims=True)
+    outs = []
+    for mod in (D, R):
+        d = mod.DenseCRF2D(W, H, C)
+        d.setUnaryEnergy(np.ascontiguousarray(mod.unary_from_softmax(p)))
+        if order == "bilateral_only":
+            d.addPairwiseBilateral(sxy=50, srgb=5, rgbim=img, compat=10)
+        elif order == "gaussian_only":
+            d.addPairwiseGaussian(sxy=3, compat=7)
+        else:
+            d.addPairwiseBilateral(sxy=50, srgb=5, rgbim=img, compat=10)
+            d.addPairwiseGaussian(sxy=3, compat=7)
+        outs.append(np.array(d.inference(5)).reshape(C, H, W))
+    err = np.abs(outs[1] - outs[0]) / np.maximum(np.abs(outs[0]), 1e-6)
+    assert err.max() < 1e-3
+
+
+def test_inference_zero_iterations_and_tiny_images(dev, ops, D):
+    from pnp_ovss_b200 import reference_api as R
+    for (H, W, C) in ((8, 8, 2), (5, 19, 1), (17, 4, 6)):
+        img = synth.guide_image(H * W, H, W, "noise")
+        mask = np.random.default_rng(H).random((C, H, W)).astype(np.float32)
+        ref_map, ref_q = D.densecrf(img, torch.from_numpy(mask), return_q=True)
+        got_map, got_q = R.densecrf(img, torch.from_numpy(mask), return_q=True)
+        assert np.abs(got_q - ref_q).max() < 1e-4 and np.array_equal(got_map, ref_map)
+        got_map0, got_q0 = R.densecrf(img, torch.from_numpy(mask), n_iter=0, return_q=True)
+        ref_map0, ref_q0 = D.densecrf(img, torch.from_numpy(mask), n_iter=0, return_q=True)
+        assert np.abs(got_q0 - ref_q0).max() < 1e-6 and np.array_equal(got_map0, ref_map0)
+
+
+def test_nan_channel_propagates_like_the_reference(dev, O=None):
+    """An empty background channel blurs to a constant -> 0/0 = NaN channel -> softmax NaN everywhere -> argmax 0
+    (DRV:1151-1152, DRV:1057, DRV:1073).  The CUDA path must land on the same labels as numpy/torch do."""
+    from oracle import hotpath as Or
+    from pnp_ovss_b200 import reference_api as R
+    H, W = 40, 36
+    rng = np.random.default_rng(9)
+    x = torch.from_numpy(rng.random((3, H, W)).astype(np.float32) + 0.1)
+    x[0] = 0.0                                   # background never fires
+    img = synth.guide_image(1, H, W)
+
+    class A:
+        postprocess = "blur+crf"
+    with np.errstate(all="ignore"):
+        want = Or.postprocess("blur+crf", x.clone(), img, (H, W))
+    got = R.postprocess(A, x.clone(), [img], [np.zeros((H, W), np.float32)], 0)
+    assert np.array_equal(got, want) and (got == 0).all()
+    A.postprocess = "blur"
+    with np.errstate(all="ignore"):
+        want = Or.postprocess("blur", x.clone(), img, (H, W))
+    got = R.postprocess(A, x.clone(), [img], [np.zeros((H, W), np.float32)], 0)
+    assert np.array_equal(got, want) and (got == 0).all()
