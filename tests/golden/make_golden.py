@@ -239,9 +239,11 @@ def golden_dropout_loop(out):
 # --------------------------------------------------------------------------------------------------
 def golden_driver(out, drv_path, tag, data_type, class_lists, nms, drop_iter, n_cats):
     """Run the reference's save_img_union_attention end to end (blur only) and capture the saved hists."""
-    ns = lift(drv_path, ["save_img_union_attention", "Inference_BLIP_filteredcaption",
-                         "Mean_over_filtered_label_tokens", "postprocess", "blurring", "Scale_0_1",
-                         "_fast_hist", "scores"], base_ns())
+    names = ["save_img_union_attention", "Inference_BLIP_filteredcaption", "Mean_over_filtered_label_tokens", "postprocess",
+             "blurring", "Scale_0_1", "_fast_hist", "scores"]
+    if drv_path == DRVC:
+        names.append("getClassName")  # the COCO twin's scores() labels its table through it (DRVC:1315, 1355)
+    ns = lift(drv_path, names, base_ns())
     tok = synth.SyntheticWordPieceTokenizer()
     S, P = 96, 6
     B = len(class_lists)
@@ -260,7 +262,10 @@ def golden_driver(out, drv_path, tag, data_type, class_lists, nms, drop_iter, n_
         g = fn(visual_input, rows)
         return [[g for _ in range(12)] for _ in range(12)], [], None
 
-    def fake_lpc(args, nms_, bl, cl, capl, gtl, ids, img, pred_path=None):
+    def fake_lpc(args, nms_, *rest, pred_path=None):
+        if drv_path == DRVC:  # the COCO twin passes `cats` first (DRVC:858)
+            rest = rest[1:]
+        bl, cl, capl, gtl, ids, img = rest[:6]
         bl.append(list(best_idx[img]))
         cl.append(list(class_lists[img]))
         capl.append(caps[img])
@@ -276,8 +281,11 @@ def golden_driver(out, drv_path, tag, data_type, class_lists, nms, drop_iter, n_
             saved[os.path.basename(os.path.dirname(path))] = np.array(arr)
 
     ns.update(compute_gradcam_ensemble=fake_cge, Load_predicted_classes=fake_lpc,
-              load_OrgImage=lambda a, ids: guides, Load_GroundTruth=lambda a, ids: gts, np=NP(),
-              Draw_Segmentation_map=lambda *a, **k: None)
+              load_OrgImage=lambda a, ids, *ct: guides, Load_GroundTruth=lambda a, ids, *ct: gts, np=NP(),
+              Draw_Segmentation_map=lambda *a, **k: None,
+              # the COCO twin dumps JPEG overlays unconditionally (DRVC:829-844): visualisation stubs, no arithmetic
+              getAttMap=lambda img, att, blur=True: np.zeros((2, 2, 3)),
+              Image=types.SimpleNamespace(fromarray=lambda *a, **k: types.SimpleNamespace(save=lambda *a, **k: None)))
     # Path(...).mkdir writes under /tmp
     layers = [types.SimpleNamespace(crossattention=types.SimpleNamespace(self=types.SimpleNamespace(save_attention=True)))
               for _ in range(12)]
@@ -294,7 +302,8 @@ def golden_driver(out, drv_path, tag, data_type, class_lists, nms, drop_iter, n_
         cats = {i: {"id": 3 * i + 1, "name": n} for i, n in enumerate(nms)}  # sparse ids like COCO
     else:
         cats = {i + 1: n for i, n in enumerate(nms)}
-    ns["save_img_union_attention"](model, imgs, None, args, None, img_ids, drop_iter, norm_imgs, None, cats, nms,
+    lead = (None,) if drv_path == DRVC else ()  # DRVC:338 takes the pycocotools handle first
+    ns["save_img_union_attention"](*lead, model, imgs, None, args, None, img_ids, drop_iter, norm_imgs, None, cats, nms,
                                    tt, "cpu", 9, max_block_num=8)
     for k, v in saved.items():
         out["drv_%s_%s" % (tag, k)] = v

@@ -23,11 +23,17 @@ def case_inputs(tag):
     tok = synth.SyntheticWordPieceTokenizer()
     caps = ["A picture of " + " ".join(cl) for cl in class_lists]
     tt = tok(caps, padding="max_length", max_length=500)
-    return dict(coco=coco, data_type=data_type, class_lists=class_lists, R=R, S=S, P=P, H=H, W=W, T=T, n_class=n_cats + 1,
+    if coco:
+        catids = g["drv_%s_catids" % tag]
+        ids = [[int(catids[VOC_NMS.index(c)]) for c in cl] for cl in class_lists]
+        n_class = 91 if data_type == "coco_object" else 183
+    else:
+        ids = [[VOC_NMS.index(c) + 1 for c in cl] for cl in class_lists]
+        n_class = n_cats + 1
+    return dict(coco=coco, data_type=data_type, class_lists=class_lists, R=R, S=S, P=P, H=H, W=W, T=T, n_class=n_class,
                 tok=tok, tokens=tt, rows=torch.from_numpy(g["drv_%s_rows" % tag]),
                 imgs=torch.from_numpy(g["drv_%s_imgs" % tag]), gts=list(g["drv_%s_gt" % tag]),
-                guides=list(g["drv_%s_guide" % tag]),
-                ids=[[VOC_NMS.index(c) + 1 for c in cl] for cl in class_lists], golden=g)
+                guides=list(g["drv_%s_guide" % tag]), ids=ids, golden=g)
 
 
 def run_oracle(tag, mode):

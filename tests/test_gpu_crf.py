@@ -177,7 +177,10 @@ def test_driver_cases_blur_vs_reference_golden(dev, golden, tag):
     """save_img_union_attention of the REAL reference (--postprocess blur) vs the CUDA pipeline: confusion matrices."""
     h0, hagg = smoke_case.run_gpu(tag, "blur", dev)
     k0, kagg = "drv_%s_hist_withfiltered_caption" % tag, "drv_%s_all_drop_hist_with_filtered_caption" % tag
-    assert np.array_equal(h0, golden[k0]), "round-0 matrix differs by %g" % smoke_case.disagreement(h0, golden[k0])
+    if h0 is None:  # COCO driver, drop_iter >= 3: no round-0 pass (DRVC:420, 602)
+        assert k0 not in golden.files
+    else:
+        assert np.array_equal(h0, golden[k0]), "round-0 matrix differs by %g" % smoke_case.disagreement(h0, golden[k0])
     if hagg is not None:
         assert np.array_equal(hagg, golden[kagg]), "all-drop matrix differs by %g" % smoke_case.disagreement(hagg, golden[kagg])
     else:

@@ -150,3 +150,17 @@ def test_gpt4o_class_list_parser_matches_reference():
             n += 1
     assert n > 300
     assert host.parse_gpt4o_classes("[3: 'bird'], [60%]", ["a", "b", "c"])[0] == [0]       # nothing above 70 -> class 0
+
+
+def test_calculate_miou_reads_the_reference_layout(tmp_path):
+    from pnp_ovss_b200 import calculate_miou, pipeline
+    rng = np.random.default_rng(0)
+    hs = [rng.integers(0, 50, (5, 5)) for _ in range(3)]
+    for i, h in enumerate(hs):  # one file per batch, like the reference writes them (DRV:517-520)
+        pipeline.save_hist_npy(torch.from_numpy(h), str(tmp_path), "all_drop_hist_with_filtered_caption", "img%d" % i, 8, 9)
+    table, hist = calculate_miou.main(["--save_path", str(tmp_path)])
+    assert np.array_equal(hist, sum(hs).astype(np.float64))
+    want, _ = O.scores([np.zeros((1, 1))], [np.zeros((1, 1))], 5)  # just for the key set
+    assert set(want) == set(table)
+    iu = np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
+    assert table["Mean IoU"] == np.nanmean(iu[hist.sum(1) > 0])

@@ -96,10 +96,16 @@ def _run_driver_case(golden, tag, argsort_kind=None):
     gts = list(golden["drv_%s_gt" % tag])
     guides = list(golden["drv_%s_guide" % tag])
     fn = synth.SynthGradcamFn(31, len(caps), T, P)
-    ids = [[VOC_NMS.index(c) + 1 for c in cl] for cl in class_lists]
+    if coco:  # sparse category ids (cats[idx]['id'], DRVC:549-584) and the COCO matrix sizes (DRVC:597-600)
+        catids = golden["drv_%s_catids" % tag]
+        ids = [[int(catids[VOC_NMS.index(c)]) for c in cl] for cl in class_lists]
+        n_class = 91 if data_type == "coco_object" else 183
+    else:
+        ids = [[VOC_NMS.index(c) + 1 for c in cl] for cl in class_lists]
+        n_class = n_cats + 1
     return O.batch_confusion(lambda x: fn(x, rows), imgs, tt.input_ids, tok.decode, class_lists, ids, gts, guides,
                              drop_iter=R, patch_num=P, threshold=0.15, data_type=data_type, mode="blur",
-                             n_class=n_cats + 1, coco=coco, argsort_kind=argsort_kind)
+                             n_class=n_class, coco=coco, argsort_kind=argsort_kind)
 
 
 def test_driver_end_to_end_hists(golden):
@@ -107,7 +113,10 @@ def test_driver_end_to_end_hists(golden):
     for tag in DRIVER_CASES:
         h0, hagg, _ = _run_driver_case(golden, tag)
         k0, kagg = "drv_%s_hist_withfiltered_caption" % tag, "drv_%s_all_drop_hist_with_filtered_caption" % tag
-        assert np.array_equal(h0, golden[k0]), tag
+        if h0 is not None:
+            assert np.array_equal(h0, golden[k0]), tag
+        if h0 is None:  # the COCO driver skips the round-0 pass when drop_iter >= 3 (DRVC:420, 602)
+            assert k0 not in golden.files
         if hagg is not None:
             assert np.array_equal(hagg, golden[kagg]), tag
         else:
