@@ -214,7 +214,7 @@ def test_threshold_upsample_single_class(dev, ops, O):
     _close(out[0].numpy(), ref.numpy(), rtol=1e-5, atol=1e-7)
 
 
-@pytest.mark.parametrize("shape", [(336, 336), (375, 500), (64, 48), (20, 30), (512, 512)])
+@pytest.mark.parametrize("shape", [(336, 336), (375, 500), (64, 48), (20, 30), (512, 512), (10, 200), (200, 12), (1, 64)])
 def test_gaussian_blur_vs_scipy(dev, ops, O, shape):
     H, W = shape
     rng = np.random.default_rng(H * 1000 + W)
