@@ -141,7 +141,6 @@ typedef struct pnp_lattice {
     float *csr_w;      /* [n_images*n_pixels*(d+1)] barycentric weight of each entry */
     float *csr_norm;   /* [n_images*n_pixels*(d+1)] norm[csr_pix] in CSR order (sequential read instead of a gather) */
     float *norm;       /* [n_images*n_pixels] 1/sqrt(K 1 + 1e-20) (NORMALIZE_SYMMETRIC) */
-    int32_t *perm;     /* [vertex_stride] vertex ids in descending CSR-row-length order (splat work order) */
     int32_t *counters; /* [8] device: 0 = M, 1 = key-range overflow flag, 2 = longest row */
 } pnp_lattice;
 

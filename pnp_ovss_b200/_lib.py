@@ -20,7 +20,7 @@ class Lattice(ctypes.Structure):
     _fields_ = [("d", c_int), ("n_images", c_int), ("n_pixels", c_int), ("shared", c_int), ("n_vertices", c_int),
                 ("max_row", c_int), ("vertex_stride", c_int), ("width", c_int),
                 ("offset", c_void_p), ("bary", c_void_p), ("nbr", c_void_p), ("row_ptr", c_void_p), ("csr_pix", c_void_p),
-                ("csr_w", c_void_p), ("csr_norm", c_void_p), ("norm", c_void_p), ("perm", c_void_p), ("counters", c_void_p)]
+                ("csr_w", c_void_p), ("csr_norm", c_void_p), ("norm", c_void_p), ("counters", c_void_p)]
 
 
 _LP = ctypes.POINTER(Lattice)

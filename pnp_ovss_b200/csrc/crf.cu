@@ -50,12 +50,13 @@ __global__ void __launch_bounds__(256) splat_kernel(LatticeView L, const float *
     float *vb = L.shared ? values + (size_t)b * (L.M + 1) * Cp : values;
     const long long total = (long long)(L.M + 1) * nch;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int pos = (int)(idx / nch), ch = (int)(idx - (long long)pos * nch);
-        if (pos == L.M) {  // sentinel row 0 stays zero
+        const int v = (int)(idx / nch), ch = (int)(idx - (long long)v * nch);
+        if (v == L.M) {  // sentinel row 0 stays zero
             *reinterpret_cast<float4 *>(vb + 4 * ch) = make_float4(0.f, 0.f, 0.f, 0.f);
             continue;
         }
-        const int v = __ldg(L.perm + pos);  // window-local descending row-length order
+        // vertices are visited in first-touch order: neighbours in memory are neighbours in the image, which keeps the
+        // row gathers in L1/L2 (sorting vertices by row length to balance warps cost 2x the DRAM traffic: profiles/)
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const int end = __ldg(L.row_ptr + v + 1);
         int k = __ldg(L.row_ptr + v);

@@ -462,56 +462,6 @@ __global__ void __launch_bounds__(256) lattice_neighbors_kernel(const unsigned l
 }
 
 
-// ------------------------------------------------------------------------------------------ splat work order
-// Inside every window of kWindow consecutive vertices (first-touch numbering keeps a window spatially compact, so
-// the gathers of a CTA stay local) the vertices are counting-sorted by CSR row length, longest first: the lanes of
-// a splat warp then loop (nearly) the same number of times.  The order only affects scheduling, never a result.
-constexpr int kLenBins = 1024;
-constexpr int kWindow = 1024;
-
-__global__ void __launch_bounds__(256) rowlen_window_sort_kernel(const int32_t *__restrict__ row_ptr, const int32_t *counters,
-                                                                 int32_t *__restrict__ perm) {
-    __shared__ int s_cnt[kLenBins];
-    __shared__ int s_warp[8];
-    const int M = counters[0];
-    const int n_windows = (M + kWindow - 1) / kWindow;
-    for (int win = blockIdx.x; win < n_windows; win += gridDim.x) {
-        const int base = win * kWindow;
-        for (int i = threadIdx.x; i < kLenBins; i += blockDim.x) s_cnt[i] = 0;
-        __syncthreads();
-        int len[kWindow / 256];
-#pragma unroll
-        for (int k = 0; k < kWindow / 256; ++k) {
-            const int v = base + k * 256 + threadIdx.x;
-            len[k] = -1;
-            if (v < M) {
-                len[k] = min(row_ptr[v + 1] - row_ptr[v], kLenBins - 1);
-                atomicAdd(&s_cnt[len[k]], 1);
-            }
-        }
-        __syncthreads();
-        // exclusive scan over the bins in DESCENDING length order: thread t owns bins [1023-4t-3, 1023-4t]
-        int c[4], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { c[k] = s_cnt[kLenBins - 1 - (4 * threadIdx.x + k)]; sum += c[k]; }
-        int incl = sum;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        int off = incl - sum;
-        for (int w = 0; w < warp; ++w) off += s_warp[w];
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { s_cnt[kLenBins - 1 - (4 * threadIdx.x + k)] = off; off += c[k]; }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kWindow / 256; ++k)
-            if (len[k] >= 0) perm[base + atomicAdd(&s_cnt[len[k]], 1)] = base + k * 256 + threadIdx.x;
-        __syncthreads();
-    }
-}
-
 // ------------------------------------------------------------------------------------------ norm = 1/sqrt(K 1 + 1e-20)
 __global__ void __launch_bounds__(256) norm_splat_kernel(const int32_t *__restrict__ row_ptr, const float *__restrict__ csr_w,
                                                          const int32_t *__restrict__ counters, float *__restrict__ values) {
@@ -604,7 +554,6 @@ extern "C" size_t pnp_lattice_storage_bytes(int d, int n_images, int n_pixels) {
     o += align_up(n_entries * 4, 256);                        // csr_w
     o += align_up(n_entries * 4, 256);                        // csr_norm
     o += align_up((size_t)n_images * n_pixels * 4, 256);      // norm
-    o += align_up(n_entries * 4, 256);                        // perm
     o += 256;                                                 // counters
     return o;
 }
@@ -640,7 +589,6 @@ extern "C" int pnp_lattice_init(pnp_lattice *lat, void *storage, size_t storage_
     lat->csr_w = reinterpret_cast<float *>(take(n_entries * 4));
     lat->csr_norm = reinterpret_cast<float *>(take(n_entries * 4));
     lat->norm = reinterpret_cast<float *>(take((size_t)n_images * n_pixels * 4));
-    lat->perm = reinterpret_cast<int32_t *>(take(n_entries * 4));
     lat->counters = reinterpret_cast<int32_t *>(take(256));
     return PNP_OK;
 }
@@ -706,7 +654,6 @@ static int build_impl(pnp_lattice *lat, const uint8_t *rgb, int H, int W, float 
                                                       prefix, D + 1);
     lattice_neighbors_kernel<D><<<big_grid, 256, 0, st>>>(keys_dense, table, slot_id, vstart, lat->counters, lat->nbr,
                                                           lat->n_images, cap - 1, lat->vertex_stride);
-    rowlen_window_sort_kernel<<<big_grid, 256, 0, st>>>(lat->row_ptr, lat->counters, lat->perm);
     // normalisation: K applied to ones
     norm_splat_kernel<<<big_grid, 256, 0, st>>>(lat->row_ptr, lat->csr_w, lat->counters, va);
     float *src = va, *dst = vb;

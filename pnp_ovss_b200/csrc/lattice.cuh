@@ -13,7 +13,6 @@ struct LatticeView {
     const float *csr_w;      // [n_entries]
     const float *csr_norm;   // [n_entries] norm[csr_pix[k]]
     const float *norm;       // [n_lp]
-    const int32_t *perm;     // [M] vertex ids by descending CSR row length
     int Dp1;                 // d + 1
     int M;                   // vertices
     int vertex_stride;
@@ -32,7 +31,6 @@ static inline LatticeView make_view(const pnp_lattice *lat) {
     v.csr_w = lat->csr_w;
     v.csr_norm = lat->csr_norm;
     v.norm = lat->norm;
-    v.perm = lat->perm;
     v.Dp1 = lat->d + 1;
     v.M = lat->n_vertices;
     v.vertex_stride = lat->vertex_stride;
