@@ -11,6 +11,8 @@
 // contraction), so the filter is bit-identical to the sequential CPU restatement; only expf/logf differ by ulps.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) blur_axis_kernel(LatticeView L, const flo
         const float4 c = *reinterpret_cast<const float4 *>(ob + (long long)(v + 1) * Cp + 4 * ch);
         const float4 a1 = *reinterpret_cast<const float4 *>(ob + (long long)n.x * Cp + 4 * ch);
         const float4 a2 = *reinterpret_cast<const float4 *>(ob + (long long)n.y * Cp + 4 * ch);
-        // new = old + 0.5f * (n1 + n2)
+        // new = old + 0.5f * (n1 + n2)   (plain cached accesses: streaming hints measured 4 % slower, profiles/README.md)
         *reinterpret_cast<float4 *>(nb + (long long)(v + 1) * Cp + 4 * ch) = f4_add(c, f4_mul(f4_add(a1, a2), 0.5f));
     }
 }
@@ -460,8 +462,20 @@ __global__ void __launch_bounds__(kUnaryPix) unpack_nc_to_cn_kernel(const float 
 }
 
 // ------------------------------------------------------------------------------------------ host helpers
-static inline int grid_for(long long work_items, int threads) {
-    return (int)std::max<long long>(1, std::min<long long>((work_items + threads - 1) / threads, (long long)kNumSMs * 16));
+// CTAs per SM of the grid-stride kernels.  Measured on B200 (profiles/sweep_grid.py): the lattice blur is fastest with
+// exactly one resident wave (8 CTAs x 148 SMs: every SM streams one contiguous slice, no tail), the splat with many
+// more CTAs than fit (its CSR rows differ in length, so late CTAs fill the holes), the mean-field update with 8.
+// PNP_GRID_MULT_{BLUR,SPLAT,UPDATE} override for tuning runs.
+static inline int env_mult(const char *name, int dflt) {
+    const char *e = getenv(name);
+    int v = e ? atoi(e) : dflt;
+    return v > 0 ? v : dflt;
+}
+static inline int mult_blur() { static int m = env_mult("PNP_GRID_MULT_BLUR", 8); return m; }
+static inline int mult_splat() { static int m = env_mult("PNP_GRID_MULT_SPLAT", 64); return m; }
+static inline int mult_update() { static int m = env_mult("PNP_GRID_MULT_UPDATE", 8); return m; }
+static inline int grid_for(long long work_items, int threads, int mult = 16) {
+    return (int)std::max<long long>(1, std::min<long long>((work_items + threads - 1) / threads, (long long)kNumSMs * mult));
 }
 
 static bool lattice_ok(const pnp_lattice *lat, int B) {
@@ -475,10 +489,12 @@ static const float *run_splat_blur(const LatticeView &L, const float *x, float *
                                    cudaStream_t st) {
     const int nch = Cp / 4;
     const int gy = L.shared ? B : 1;
-    const int gx = std::max(1, grid_for((long long)(L.M + 1) * nch, 256) / (L.shared ? std::min(B, 8) : 1));
+    const int div = L.shared ? std::min(B, 8) : 1;
+    const int gx_splat = std::max(1, grid_for((long long)(L.M + 1) * nch, 256, mult_splat()) / div);
+    const int gx = std::max(1, grid_for((long long)(L.M + 1) * nch, 256, mult_blur()) / div);
     const int id_splat = L.shared ? kSplatSpatial : kSplatBilateral;
     const int id_blur = L.shared ? kBlurAxisSpatial : kBlurAxisBilateral;
-    PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, x, va, Cp, normalized));
+    PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx_splat, gy), 256, 0, st>>>(L, x, va, Cp, normalized));
     float *src = va, *dst = vb;
     for (int j = 0; j < L.Dp1; ++j) {
         PNP_LAUNCH(id_blur, st, blur_axis_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, src, dst, j, Cp));
@@ -557,7 +573,7 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
     const int Wimg = lattices[0]->width, Himg = Wimg > 0 ? N / Wimg : 0;
     const bool warp_path = Cp <= 128 && Wimg > 0 && (long long)Himg * Wimg == N && (long long)B * N < (1ll << 31) / Cp;
     const int grid_w = (int)std::max<long long>(
-        1, std::min<long long>((long long)B * ((Himg + kTile - 1) / kTile) * ((Wimg + kTile - 1) / kTile), (long long)kNumSMs * 8));
+        1, std::min<long long>((long long)B * ((Himg + kTile - 1) / kTile) * ((Wimg + kTile - 1) / kTile), (long long)kNumSMs * mult_update()));
     auto update = [&](bool with_labels) {
         const bool fast = warp_path && P.n_kernels == 2 && P.lat[0].Dp1 == 3 && P.lat[0].shared && P.lat[1].Dp1 == 6 && !P.lat[1].shared;
         if (fast) {
