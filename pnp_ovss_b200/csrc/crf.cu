@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) splat_kernel(LatticeView L, const float *
     const int nch = Cp >> 2;
     const int b = blockIdx.y;
     const float *xb = L.shared ? x + (size_t)b * L.N * Cp : x;
-    float *vb = L.shared ? values + (size_t)b * (L.M + 1) * Cp : values;
+    float *vb = L.shared ? values + (size_t)b * (L.M + 1) * L.vp : values;
     const long long total = (long long)(L.M + 1) * nch;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const int v = (int)(idx / nch), ch = (int)(idx - (long long)v * nch);
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) splat_kernel(LatticeView L, const float *
             if (normalized) xv = f4_mul(xv, __ldg(L.csr_norm + k));
             acc = f4_add(acc, f4_mul(xv, __ldg(L.csr_w + k)));
         }
-        *reinterpret_cast<float4 *>(vb + (size_t)(v + 1) * Cp + 4 * ch) = acc;
+        *reinterpret_cast<float4 *>(vb + (size_t)(v + 1) * L.vp + 4 * ch) = acc;
     }
 }
 
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) blur_axis_kernel(LatticeView L, const flo
                                                         int Cp) {
     const int nch = Cp >> 2;
     const int b = blockIdx.y;
-    const long long img_off = L.shared ? (long long)b * (L.M + 1) * Cp : 0;
+    const long long img_off = L.shared ? (long long)b * (L.M + 1) * L.vp : 0;
     const float *ob = old_v + img_off;
     float *nb = new_v + img_off;
     const int2 *nbr = reinterpret_cast<const int2 *>(L.nbr) + (size_t)axis * L.vertex_stride;
@@ -107,11 +107,11 @@ __global__ void __launch_bounds__(256) blur_axis_kernel(LatticeView L, const flo
             continue;
         }
         const int2 n = nbr[v];
-        const float4 c = *reinterpret_cast<const float4 *>(ob + (long long)(v + 1) * Cp + 4 * ch);
-        const float4 a1 = *reinterpret_cast<const float4 *>(ob + (long long)n.x * Cp + 4 * ch);
-        const float4 a2 = *reinterpret_cast<const float4 *>(ob + (long long)n.y * Cp + 4 * ch);
+        const float4 c = *reinterpret_cast<const float4 *>(ob + (long long)(v + 1) * L.vp + 4 * ch);
+        const float4 a1 = *reinterpret_cast<const float4 *>(ob + (long long)n.x * L.vp + 4 * ch);
+        const float4 a2 = *reinterpret_cast<const float4 *>(ob + (long long)n.y * L.vp + 4 * ch);
         // new = old + 0.5f * (n1 + n2)   (plain cached accesses: streaming hints measured 4 % slower, profiles/README.md)
-        *reinterpret_cast<float4 *>(nb + (long long)(v + 1) * Cp + 4 * ch) = f4_add(c, f4_mul(f4_add(a1, a2), 0.5f));
+        *reinterpret_cast<float4 *>(nb + (long long)(v + 1) * L.vp + 4 * ch) = f4_add(c, f4_mul(f4_add(a1, a2), 0.5f));
     }
 }
 
@@ -121,7 +121,7 @@ template <int DP1>
 __device__ __forceinline__ float4 slice_pixel_t(const LatticeView &L, const float *__restrict__ values, int b, int pix, int gp, int ch,
                                                 int Cp, bool normalized) {
     const int lp = L.shared ? pix : gp;
-    const float *vb = L.shared ? values + (size_t)b * (L.M + 1) * Cp : values;
+    const float *vb = L.shared ? values + (size_t)b * (L.M + 1) * L.vp : values;
     int o[DP1];
     float w[DP1];
     float4 v[DP1];
@@ -131,7 +131,7 @@ __device__ __forceinline__ float4 slice_pixel_t(const LatticeView &L, const floa
         w[j] = __ldg(L.bary + (size_t)lp * DP1 + j);
     }
 #pragma unroll
-    for (int j = 0; j < DP1; ++j) v[j] = *reinterpret_cast<const float4 *>(vb + (size_t)o[j] * Cp + 4 * ch);
+    for (int j = 0; j < DP1; ++j) v[j] = *reinterpret_cast<const float4 *>(vb + (size_t)o[j] * L.vp + 4 * ch);
     float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < DP1; ++j) out = f4_add(out, f4_mul(f4_mul(v[j], w[j]), L.alpha));
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldPar
                 const int spix = active ? pix : 0, sgp = active ? gp : 0, sb = active ? b : 0, sch = lane_used ? ch : 0;
                 const LatticeView &A = P.lat[0];
                 const LatticeView &Bl = P.lat[1];
-                const float *va = P.values[0] + (size_t)sb * (A.M + 1) * Cp + 4 * sch;
+                const float *va = P.values[0] + (size_t)sb * (A.M + 1) * A.vp + 4 * sch;
                 const float *vbp = P.values[1] + 4 * sch;
                 const float4 u = ldg_stream4(unary + (size_t)sgp * Cp + 4 * sch);
                 int oa[3], ob[6];
@@ -307,9 +307,9 @@ __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldPar
                 // load/FFMA pairs to save registers and serialises the L2 latencies).
                 float4 ga[3], gb[6];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) ga[j] = ld_gather4(va + (size_t)oa[j] * Cp);
+                for (int j = 0; j < 3; ++j) ga[j] = ld_gather4(va + (size_t)oa[j] * A.vp);
 #pragma unroll
-                for (int j = 0; j < 6; ++j) gb[j] = ld_gather4(vbp + (size_t)ob[j] * Cp);
+                for (int j = 0; j < 6; ++j) gb[j] = ld_gather4(vbp + (size_t)ob[j] * Bl.vp);
                 float4 acc = make_float4(-u.x, -u.y, -u.z, -u.w);
 #pragma unroll
                 for (int j = 5; j >= 0; --j) {
@@ -478,6 +478,26 @@ static inline int grid_for(long long work_items, int threads, int mult = 16) {
     return (int)std::max<long long>(1, std::min<long long>((work_items + threads - 1) / threads, (long long)kNumSMs * mult));
 }
 
+// Row pitch of the vertex-value buffers.  Default: rows packed at Cp floats.  PNP_VALUE_PITCH=1 pads rows so that none
+// straddles a 128-byte line (96-byte rows cross a boundary every other row); measured on B200 it does not pay: the
+// gather kernels do not speed up and the HBM-bound lattice blur slows by 9 % (profiles/README.md), so it stays off.
+static inline int value_pitch(int Cp) {
+    static const int padded = env_mult("PNP_VALUE_PITCH", 2) == 1;
+    if (!padded) return Cp;
+    const int bytes = Cp * 4;
+    if (bytes <= 128) {
+        int p = 16;
+        while (p < bytes) p <<= 1;
+        return p / 4;
+    }
+    return (bytes + 127) / 128 * 32;
+}
+static inline LatticeView view_for(const pnp_lattice *lat, int Cp) {
+    LatticeView L = make_view(lat);
+    L.vp = value_pitch(Cp);
+    return L;
+}
+
 static bool lattice_ok(const pnp_lattice *lat, int B) {
     if (!lat || lat->n_vertices < 0 || !lat->offset) return false;
     if (!lat->shared && lat->n_images != B) return false;
@@ -514,8 +534,8 @@ extern "C" size_t pnp_crf_scratch_bytes(const pnp_lattice *const *lattices, int 
     size_t total = 0;
     for (int k = 0; k < n_kernels; ++k) {
         if (!lattice_ok(lattices[k], B)) return 0;
-        LatticeView L = make_view(lattices[k]);
-        total += 2 * align_up((size_t)value_rows(L, B) * Cp * sizeof(float), 256);
+        LatticeView L = view_for(lattices[k], Cp);
+        total += 2 * align_up((size_t)value_rows(L, B) * L.vp * sizeof(float), 256);
     }
     return total;
 }
@@ -526,8 +546,8 @@ extern "C" int pnp_crf_filter(const pnp_lattice *lat, const float *x, float *y, 
     const pnp_lattice *one[1] = {lat};
     if (scratch_bytes < pnp_crf_scratch_bytes(one, 1, B, Cp)) return PNP_ERR_WORKSPACE;
     cudaStream_t st = as_stream(stream);
-    LatticeView L = make_view(lat);
-    size_t buf = align_up((size_t)value_rows(L, B) * Cp * sizeof(float), 256);
+    LatticeView L = view_for(lat, Cp);
+    size_t buf = align_up((size_t)value_rows(L, B) * L.vp * sizeof(float), 256);
     float *va = reinterpret_cast<float *>(scratch);
     float *vb = reinterpret_cast<float *>(reinterpret_cast<char *>(scratch) + buf);
     const float *blurred = run_splat_blur(L, x, va, vb, B, Cp, normalized, st);
@@ -554,9 +574,9 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
     char *p = reinterpret_cast<char *>(scratch);
     for (int k = 0; k < kMaxKernels; ++k) {
         if (k < n_kernels) {
-            P.lat[k] = make_view(lattices[k]);
+            P.lat[k] = view_for(lattices[k], Cp);
             P.weight[k] = weights[k];
-            size_t buf = align_up((size_t)value_rows(P.lat[k], B) * Cp * sizeof(float), 256);
+            size_t buf = align_up((size_t)value_rows(P.lat[k], B) * P.lat[k].vp * sizeof(float), 256);
             va[k] = reinterpret_cast<float *>(p);
             vb[k] = reinterpret_cast<float *>(p + buf);
             p += 2 * buf;

@@ -19,6 +19,7 @@ struct LatticeView {
     int shared;              // 1: one image's lattice applied to every image
     int N;                   // pixels per image
     float alpha;             // 1 / (1 + 2^-d)
+    int vp;                  // floats between consecutive rows of a vertex-value buffer (>= Cp; set per call)
 };
 
 static inline LatticeView make_view(const pnp_lattice *lat) {
@@ -37,6 +38,7 @@ static inline LatticeView make_view(const pnp_lattice *lat) {
     v.shared = lat->shared;
     v.N = lat->n_pixels;
     v.alpha = 1.0f / (1 + powf(2, -lat->d));
+    v.vp = 0;
     return v;
 }
 
