@@ -333,3 +333,28 @@ def test_nan_channel_propagates_like_the_reference(dev, O=None):
         want = Or.postprocess("blur", x.clone(), img, (H, W))
     got = R.postprocess(A, x.clone(), [img], [np.zeros((H, W), np.float32)], 0)
     assert np.array_equal(got, want) and (got == 0).all()
+
+
+def test_inference_is_cuda_graph_capturable(dev, ops):
+    """pnp_crf_inference allocates nothing and never synchronises, so the whole 10-iteration mean-field loop (>120
+    launches) can be captured once in a CUDA graph and replayed -- what a per-image (launch-bound) caller would do."""
+    H, W, C = 64, 80, 5
+    guides = torch.from_numpy(synth.guide_image(5, H, W)[None]).to(dev)
+    lat_s = ops.build_lattice(H, W, 3.0, device=dev)
+    lat_b = ops.build_lattice(H, W, 50.0, rgb=guides, srgb=5.0)
+    U = torch.rand(1, H * W, 8, device=dev)
+    U[:, :, C:] = 0
+    Q_eager, lab_eager = ops.crf_inference([lat_s, lat_b], [7.0, 10.0], U, C, 10)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):     # warm-up on the capture stream
+        ops.crf_inference([lat_s, lat_b], [7.0, 10.0], U, C, 10)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        Q_graph, lab_graph = ops.crf_inference([lat_s, lat_b], [7.0, 10.0], U, C, 10)
+    for _ in range(2):
+        Q_graph.zero_()
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(Q_graph, Q_eager) and torch.equal(lab_graph, lab_eager)
