@@ -62,8 +62,12 @@ def test_gradcam_through_model_matches_reference_procedure(dev):
     gm.requires_grad_(False)
     lst, empty, out = R.compute_gradcam_ensemble(_Args, gm, imgs.to(dev), caps, tokens.to(dev))
     assert empty == [] and torch.allclose(lst[1][1].cpu(), want, atol=1e-3 * scale)
-    with pytest.raises(Exception):
-        lst[0][0]
+    # any other [layer][head] of the reference's 12x12 surface is computed on first access
+    assert len(lst) == 3 and len(lst[0]) == 2
+    other = lst[0][0]
+    assert other.shape == want.shape and torch.allclose(other.cpu(), blocks[0][0], atol=1e-3 * float(blocks[0][0].abs().max()))
+    with pytest.raises(IndexError):
+        lst[5]
 
 
 def test_inference_blip_filteredcaption_matches_oracle_loop(dev):
