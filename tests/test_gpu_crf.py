@@ -358,3 +358,21 @@ def test_inference_is_cuda_graph_capturable(dev, ops):
         g.replay()
     torch.cuda.synchronize()
     assert torch.equal(Q_graph, Q_eager) and torch.equal(lab_graph, lab_eager)
+
+
+def test_inference_matches_oracle_at_full_resolution(dev, D):
+    """One BASELINE configs[1] image (336x336, 21 channels, 10 iterations) against the C restatement directly."""
+    from oracle import hotpath as Or
+    from pnp_ovss_b200 import reference_api as R
+    H = W = 336
+    C = 20
+    maps = synth.saliency_maps(31, C, 21)
+    img = synth.guide_image(31, H, W)
+    with np.errstate(all="ignore"):
+        x = Or.threshold_upsample(maps.clone(), 0.15, (H, W), False, True).float()
+        xb = Or.blur_channels(x, (H, W)).float()
+    ref_map, ref_q = D.densecrf(img, xb, return_q=True)
+    got_map, got_q = R.densecrf(img, xb, return_q=True)
+    err = np.abs(got_q - ref_q) / np.maximum(np.abs(ref_q), 1e-6)
+    assert err.max() < 1e-3, "max relative error of the marginals at 336x336: %g" % err.max()
+    assert (got_map != ref_map).mean() <= 1e-4
