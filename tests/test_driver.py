@@ -1,4 +1,6 @@
 """The driver keeps the reference's CLI (DRV:57-106) and shards images without double counting."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -62,3 +64,28 @@ def test_driver_runs_end_to_end_on_one_gpu(tmp_path, data_type, classes):
     saved = np.load(str(tmp_path / "all_drop_hist_with_filtered_caption" / "img_syn_000000_max_blocknum_8_atthead_9.npy"))
     assert saved.dtype == np.float64 and np.array_equal(saved, hist)
     assert np.array_equal(driver.main(0, 1, a), hist)   # deterministic
+
+
+def _run_driver(world_size, save_path, port):
+    import subprocess
+    import sys
+    cmd = [sys.executable, "-m", "pnp_ovss_b200.driver", "--data_type", "voc", "--img_size", "96", "--batch_size", "2",
+           "--max_att_block_num", "8", "--prune_att_head", "9", "--drop_iter", "2", "--del_patch_num", "sort_thresh005",
+           "--threshold", "0.15", "--postprocess", "blur+crf", "--world_size", str(world_size), "--synthetic_images", "4",
+           "--synthetic_classes", "2", "--save_path", save_path, "--master_port", str(port)]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(cmd, check=True, cwd=root, timeout=600)
+    return np.load(os.path.join(save_path, "all_drop_hist_with_filtered_caption", "img_syn_000000_max_blocknum_8_atthead_9.npy"))
+
+
+@pytest.mark.gpu
+def test_two_gpu_run_gives_the_same_matrix_as_one_gpu(tmp_path):
+    """Data-parallel over images with mp.spawn (DRV:1439) + one NCCL all-reduce: with the same batch membership
+    (4 images, batches of 2: [0,1] [2,3] on one GPU, one batch per rank on two) the all-reduced confusion matrix is
+    bit-identical.  (Batch membership matters in the reference itself: the DropOut score slices rows [3:-1] of the
+    longest caption IN THE BATCH)  Needs two GPUs; skipped on a one-GPU box (run with `gpurun --gpus 2`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    one = _run_driver(1, str(tmp_path / "w1"), 29611)
+    two = _run_driver(2, str(tmp_path / "w2"), 29612)
+    assert one.sum() > 0 and np.array_equal(one, two)
