@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "lattice.cuh"
@@ -251,15 +252,26 @@ __global__ void __launch_bounds__(256) meanfield_update_kernel(MeanFieldParams P
 // A CTA owns whole 16x16 pixel tiles, so the lattice rows its pixels share stay in L1 between its sub-iterations.
 constexpr int kTile = 16;
 
-template <bool kLabels, bool kFast>
+// index-aware argmax merge for out-of-order traversal: larger value wins, equal values -> smaller channel index wins,
+// NaN beats every number and the NaN with the smallest index wins (numpy/torch "first maximum, NaN counts as maximum")
+__device__ __forceinline__ void argmax_merge(float v, int c, float &best, int &bi) {
+    const bool vnan = v != v, bnan = best != best;
+    const bool take = bnan ? (vnan && c < bi) : (vnan || v > best || (v == best && c < bi));
+    if (take) { best = v; bi = c; }
+}
+
+// A pixel's nch float4 chunks are spread over LPP lanes, CPL chunks per lane (chunk = lane_in_pixel + k*LPP), PW = 32/LPP
+// pixels per warp.  The host picks (LPP, CPL) to waste the fewest lanes: 21 channels -> 6 lanes x 1 chunk, 5 pixels per warp;
+// 81 channels (nch 21) -> 7 lanes x 3 chunks, 4 pixels; 150/171 channels (nch 38/43) -> 19/22 lanes x 2 chunks.
+template <bool kLabels, bool kFast, int CPL>
 __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldParams P, const float *__restrict__ unary,
                                                                     float *__restrict__ Q, int32_t *__restrict__ labels, int B, int H,
-                                                                    int W, int C, int Cp) {
+                                                                    int W, int C, int Cp, int LPP) {
     const int nch = Cp >> 2;
-    const int PW = 32 / nch;                       // pixels per warp
+    const int PW = 32 / LPP;                       // pixels per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pl = lane / nch, ch = lane - pl * nch;
-    const int base_lane = pl * nch;
+    const int pl = lane / LPP, li = lane - pl * LPP;
+    const int base_lane = pl * LPP;
     const bool lane_used = pl < PW;
     const int N = H * W;
     const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile;
@@ -276,19 +288,16 @@ __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldPar
             const bool active = lane_used && within < kTile * kTile && y < H && x < W;
             const int pix = y * W + x;
             const int gp = b * N + pix;
-            float t4[4] = {0.f, 0.f, 0.f, 0.f};
+            float t4[CPL][4];
             float mx = -INFINITY;
             if (kFast) {
-                // [spatial d=2 shared, bilateral d=5 batched].  Loads are unconditional (idle lanes read pixel 0) and
-                // separated from the arithmetic by a warp barrier, so all 9 offsets and then all 9 gathers are in
-                // flight together; alpha, norm and the kernel weight are folded into the barycentric weights (the
-                // exactly-ordered variant lives in slice_pixel_t / pnp_crf_filter).
-                const int spix = active ? pix : 0, sgp = active ? gp : 0, sb = active ? b : 0, sch = lane_used ? ch : 0;
+                // [spatial d=2 shared, bilateral d=5 batched].  Loads are unconditional (idle lanes read pixel 0 / chunk 0);
+                // alpha, norm and the kernel weight are folded into the barycentric weights (the exactly-ordered variant
+                // lives in slice_pixel_t / pnp_crf_filter).  Offsets and weights are loaded once per pixel and reused
+                // by the lane's CPL chunks.
+                const int spix = active ? pix : 0, sgp = active ? gp : 0, sb = active ? b : 0;
                 const LatticeView &A = P.lat[0];
                 const LatticeView &Bl = P.lat[1];
-                const float *va = P.values[0] + (size_t)sb * (A.M + 1) * A.vp + 4 * sch;
-                const float *vbp = P.values[1] + 4 * sch;
-                const float4 u = ldg_stream4(unary + (size_t)sgp * Cp + 4 * sch);
                 int oa[3], ob[6];
                 float wa[3], wb[6];
 #pragma unroll
@@ -302,81 +311,114 @@ __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldPar
                 }
                 const float ca = A.alpha * __ldg(A.norm + spix) * P.weight[0];
                 const float cb = Bl.alpha * __ldg(Bl.norm + sgp) * P.weight[1];
-                // The 9 row gathers are volatile (ordered) loads and the accumulation chain STARTS with the gather issued
-                // last, so all nine are in flight before the first FFMA can retire (ptxas otherwise interleaves
-                // load/FFMA pairs to save registers and serialises the L2 latencies).
-                float4 ga[3], gb[6];
 #pragma unroll
-                for (int j = 0; j < 3; ++j) ga[j] = ld_gather4(va + (size_t)oa[j] * A.vp);
+                for (int j = 0; j < 3; ++j) wa[j] *= ca;
 #pragma unroll
-                for (int j = 0; j < 6; ++j) gb[j] = ld_gather4(vbp + (size_t)ob[j] * Bl.vp);
-                float4 acc = make_float4(-u.x, -u.y, -u.z, -u.w);
+                for (int j = 0; j < 6; ++j) wb[j] *= cb;
+                const float *va0 = P.values[0] + (size_t)sb * (A.M + 1) * A.vp;
+                const float *vb0 = P.values[1];
 #pragma unroll
-                for (int j = 5; j >= 0; --j) {
-                    const float w = wb[j] * cb;
-                    acc.x = fmaf(gb[j].x, w, acc.x); acc.y = fmaf(gb[j].y, w, acc.y);
-                    acc.z = fmaf(gb[j].z, w, acc.z); acc.w = fmaf(gb[j].w, w, acc.w);
+                for (int k = 0; k < CPL; ++k) {
+                    const int ch = li + k * LPP;
+                    const int sch = (lane_used && ch < nch) ? ch : 0;
+                    const float4 u = ldg_stream4(unary + (size_t)sgp * Cp + 4 * sch);
+                    // The 9 row gathers are volatile (ordered) loads and the accumulation chain STARTS with the gather
+                    // issued last, so all nine are in flight before the first FFMA can retire (ptxas otherwise
+                    // interleaves load/FFMA pairs to save registers and serialises the L2 latencies).
+                    float4 ga[3], gb[6];
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) ga[j] = ld_gather4(va0 + (size_t)oa[j] * A.vp + 4 * sch);
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) gb[j] = ld_gather4(vb0 + (size_t)ob[j] * Bl.vp + 4 * sch);
+                    float4 acc = make_float4(-u.x, -u.y, -u.z, -u.w);
+#pragma unroll
+                    for (int j = 5; j >= 0; --j) {
+                        acc.x = fmaf(gb[j].x, wb[j], acc.x); acc.y = fmaf(gb[j].y, wb[j], acc.y);
+                        acc.z = fmaf(gb[j].z, wb[j], acc.z); acc.w = fmaf(gb[j].w, wb[j], acc.w);
+                    }
+#pragma unroll
+                    for (int j = 2; j >= 0; --j) {
+                        acc.x = fmaf(ga[j].x, wa[j], acc.x); acc.y = fmaf(ga[j].y, wa[j], acc.y);
+                        acc.z = fmaf(ga[j].z, wa[j], acc.z); acc.w = fmaf(ga[j].w, wa[j], acc.w);
+                    }
+                    t4[k][0] = acc.x; t4[k][1] = acc.y; t4[k][2] = acc.z; t4[k][3] = acc.w;
+                    if (active && ch < nch) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (4 * ch + i < C) mx = fmaxf(mx, t4[k][i]);
+                    }
                 }
+            } else {
 #pragma unroll
-                for (int j = 2; j >= 0; --j) {
-                    const float w = wa[j] * ca;
-                    acc.x = fmaf(ga[j].x, w, acc.x); acc.y = fmaf(ga[j].y, w, acc.y);
-                    acc.z = fmaf(ga[j].z, w, acc.z); acc.w = fmaf(ga[j].w, w, acc.w);
-                }
-                t4[0] = acc.x; t4[1] = acc.y; t4[2] = acc.z; t4[3] = acc.w;
-                if (active) {
+                for (int k = 0; k < CPL; ++k) {
+                    const int ch = li + k * LPP;
+                    t4[k][0] = t4[k][1] = t4[k][2] = t4[k][3] = 0.f;
+                    if (active && ch < nch) {
+                        const float4 u = ldg_stream4(unary + (size_t)gp * Cp + 4 * ch);
+                        float4 acc = make_float4(-u.x, -u.y, -u.z, -u.w);
+                        for (int kk = 0; kk < P.n_kernels; ++kk) {
+                            float4 s = slice_pixel(P.lat[kk], P.values[kk], b, pix, gp, ch, Cp, true);
+                            acc = f4_add(acc, f4_mul(s, P.weight[kk]));  // tmp1 -= (-w * K Q)
+                        }
+                        t4[k][0] = acc.x; t4[k][1] = acc.y; t4[k][2] = acc.z; t4[k][3] = acc.w;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (4 * ch + i < C) mx = fmaxf(mx, t4[i]);
+                        for (int i = 0; i < 4; ++i)
+                            if (4 * ch + i < C) mx = fmaxf(mx, t4[k][i]);
+                    }
                 }
-            } else if (active) {
-                const float4 u = ldg_stream4(unary + (size_t)gp * Cp + 4 * ch);
-                float4 acc = make_float4(-u.x, -u.y, -u.z, -u.w);
-                for (int k = 0; k < P.n_kernels; ++k) {
-                    float4 s = slice_pixel(P.lat[k], P.values[k], b, pix, gp, ch, Cp, true);
-                    acc = f4_add(acc, f4_mul(s, P.weight[k]));  // tmp1 -= (-w * K Q)
-                }
-                t4[0] = acc.x; t4[1] = acc.y; t4[2] = acc.z; t4[3] = acc.w;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (4 * ch + i < C) mx = fmaxf(mx, t4[i]);
             }
             float m = -INFINITY;
-            for (int k = 0; k < nch; ++k) m = fmaxf(m, __shfl_sync(0xffffffffu, mx, base_lane + k));
-            float e[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int k = 0; k < LPP; ++k) m = fmaxf(m, __shfl_sync(0xffffffffu, mx, base_lane + k));
+            float e[CPL][4];
             float part = 0.f;
-            if (active) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (4 * ch + i < C) {
-                        e[i] = kFast ? __expf(t4[i] - m) : expf(t4[i] - m);
-                        part += e[i];
+            for (int k = 0; k < CPL; ++k) {
+                const int ch = li + k * LPP;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    e[k][i] = 0.f;
+                    if (active && ch < nch && 4 * ch + i < C) {
+                        e[k][i] = kFast ? __expf(t4[k][i] - m) : expf(t4[k][i] - m);
+                        part += e[k][i];
                     }
+                }
             }
             float sum = 0.f;
-            for (int k = 0; k < nch; ++k) sum += __shfl_sync(0xffffffffu, part, base_lane + k);
-            float q[4] = {0.f, 0.f, 0.f, 0.f};
-            if (active) {
-                const float rs = __frcp_rn(sum);
+            for (int k = 0; k < LPP; ++k) sum += __shfl_sync(0xffffffffu, part, base_lane + k);
+            const float rs = __frcp_rn(sum);
+            float best = 0.f;
+            int bi = 0x7fffffff;
+            bool have = false;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (4 * ch + i < C) q[i] = kFast ? e[i] * rs : __fdiv_rn(e[i], sum);
-                *reinterpret_cast<float4 *>(Q + (size_t)gp * Cp + 4 * ch) = make_float4(q[0], q[1], q[2], q[3]);
+            for (int k = 0; k < CPL; ++k) {
+                const int ch = li + k * LPP;
+                if (active && ch < nch) {
+                    float q[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        q[i] = 0.f;
+                        if (4 * ch + i < C) {
+                            q[i] = kFast ? e[k][i] * rs : __fdiv_rn(e[k][i], sum);
+                            if (kLabels) {
+                                if (!have) { best = q[i]; bi = 4 * ch + i; have = true; }
+                                else argmax_merge(q[i], 4 * ch + i, best, bi);
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(Q + (size_t)gp * Cp + 4 * ch) = make_float4(q[0], q[1], q[2], q[3]);
+                }
             }
             if (kLabels) {
-                float best = q[0];
-                int bi = 4 * ch;
-#pragma unroll
-                for (int i = 1; i < 4; ++i)
-                    if (4 * ch + i < C) argmax_first(q[i], 4 * ch + i, best, bi);
+                // lanes without a real channel carry (-inf, INT_MAX) and can never win
+                if (!have) { best = -INFINITY; bi = 0x7fffffff; }
                 float rb = __shfl_sync(0xffffffffu, best, base_lane);
                 int ri = __shfl_sync(0xffffffffu, bi, base_lane);
-                for (int k = 1; k < nch; ++k) {
-                    float ob = __shfl_sync(0xffffffffu, best, base_lane + k);
+                for (int k = 1; k < LPP; ++k) {
+                    float ob2 = __shfl_sync(0xffffffffu, best, base_lane + k);
                     int oi = __shfl_sync(0xffffffffu, bi, base_lane + k);
-                    argmax_first(ob, oi, rb, ri);
+                    argmax_merge(ob2, oi, rb, ri);
                 }
-                if (active && ch == 0) labels[gp] = ri;
+                if (active && li == 0) labels[gp] = ri;
             }
         }
     }
@@ -591,21 +633,37 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
     const long long n_tiles = ((long long)B * N + TP - 1) / TP;
     const int grid = (int)std::max<long long>(1, std::min<long long>(n_tiles, (long long)kNumSMs * 8));
     const int Wimg = lattices[0]->width, Himg = Wimg > 0 ? N / Wimg : 0;
-    const bool warp_path = Cp <= 128 && Wimg > 0 && (long long)Himg * Wimg == N && (long long)B * N < (1ll << 31) / Cp;
+    // lanes per pixel / chunks per lane: the split of the nch chunks over a warp that idles the fewest lanes
+    const int nch_all = Cp / 4;
+    int LPP = 0, CPL = 0;
+    {
+        double best_eff = 0.0;
+        for (int cpl = 1; cpl <= 4; ++cpl) {
+            int lpp = (nch_all + cpl - 1) / cpl;
+            if (lpp > 32) continue;
+            double eff = (double)(32 / lpp) * nch_all / (32.0 * cpl);
+            if (eff > best_eff + 1e-9) { best_eff = eff; LPP = lpp; CPL = cpl; }
+        }
+    }
+    const bool warp_path = CPL > 0 && Wimg > 0 && (long long)Himg * Wimg == N && (long long)B * N < (1ll << 31) / Cp;
     const int grid_w = (int)std::max<long long>(
         1, std::min<long long>((long long)B * ((Himg + kTile - 1) / kTile) * ((Wimg + kTile - 1) / kTile), (long long)kNumSMs * mult_update()));
+    auto launch_warp = [&](auto labels_tag, auto fast_tag) {
+        constexpr bool kL = decltype(labels_tag)::value, kF = decltype(fast_tag)::value;
+        switch (CPL) {
+            case 1: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 1><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
+            case 2: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 2><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
+            case 3: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 3><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
+            default: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 4><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
+        }
+    };
     auto update = [&](bool with_labels) {
         const bool fast = warp_path && P.n_kernels == 2 && P.lat[0].Dp1 == 3 && P.lat[0].shared && P.lat[1].Dp1 == 6 && !P.lat[1].shared;
-        if (fast) {
-            if (with_labels)
-                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<true, true><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
-            else
-                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<false, true><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
-        } else if (warp_path) {
-            if (with_labels)
-                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<true, false><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
-            else
-                PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<false, false><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp));
+        if (warp_path) {
+            if (with_labels && fast) launch_warp(std::true_type{}, std::true_type{});
+            else if (with_labels) launch_warp(std::true_type{}, std::false_type{});
+            else if (fast) launch_warp(std::false_type{}, std::true_type{});
+            else launch_warp(std::false_type{}, std::false_type{});
         } else {
             if (with_labels)
                 PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_kernel<true><<<grid, 256, 0, st>>>(P, unary, Q, labels, B, N, C, Cp));
