@@ -166,8 +166,9 @@ int pnp_lattice_finish(pnp_lattice *lat, pnp_stream_t stream);
  * U = -log(clip(p,1e-5,1)) (pydensecrf.utils.unary_from_softmax).  maps [B,C,N] channel-major;
  * minmax [B*C,2] or NULL (maps used as they are); unary [B,N,Cp] pixel-major, Cp = 4*ceil(C/4), padding
  * channels 0. */
-int pnp_crf_unary_from_maps(const float *maps, const float *minmax, float *unary, int B, int C, int N,
-                            pnp_stream_t stream);
+size_t pnp_crf_unary_workspace_bytes(int B, int C, int N); /* 0 for C <= 32 */
+int pnp_crf_unary_from_maps(const float *maps, const float *minmax, float *unary, void *workspace,
+                            size_t workspace_bytes, int B, int C, int N, pnp_stream_t stream);
 /* Layout helpers for the pydensecrf-shaped API: [B,C,N] <-> [B,N,Cp] (padding channels written as 0). */
 int pnp_crf_pack_cn_to_nc(const float *src_cn, float *dst_nc, int B, int C, int N, pnp_stream_t stream);
 int pnp_crf_unpack_nc_to_cn(const float *src_nc, float *dst_cn, int B, int C, int N, pnp_stream_t stream);

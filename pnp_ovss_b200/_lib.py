@@ -48,7 +48,8 @@ SIGNATURES = {
     "pnp_lattice_build": (c_int, [_LP, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_void_p,
                                   c_size_t, c_void_p]),
     "pnp_lattice_finish": (c_int, [_LP, c_void_p]),
-    "pnp_crf_unary_from_maps": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "pnp_crf_unary_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pnp_crf_unary_from_maps": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "pnp_crf_pack_cn_to_nc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pnp_crf_unpack_nc_to_cn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "pnp_crf_scratch_bytes": (c_size_t, [ctypes.POINTER(_LP), c_int, c_int, c_int]),

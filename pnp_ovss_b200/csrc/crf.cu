@@ -473,6 +473,70 @@ __global__ void __launch_bounds__(kUnaryPix) unary_from_maps_kernel(const float 
     }
 }
 
+// Many-channel variant (C > 32): the one-thread-per-pixel kernel above needs a [128][C+1] shared tile, which at 150-171
+// channels leaves 2 CTAs per SM.  Here pass A reduces max and sum per pixel (same arithmetic, same order), pass B
+// revisits the maps in 32-channel slabs and transposes each slab through a [128][33] tile.
+__global__ void __launch_bounds__(kUnaryPix) unary_stats_kernel(const float *__restrict__ maps, const float *__restrict__ minmax,
+                                                                float2 *__restrict__ stats, int C, int N) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * kUnaryPix + threadIdx.x;
+    if (p >= N) return;
+    const float *mb = maps + (long long)b * C * N + p;
+    const float *mm = minmax ? minmax + (long long)b * C * 2 : nullptr;
+    float mx = -INFINITY;
+    bool has_nan = false;
+    for (int c = 0; c < C; ++c) {
+        float v = mb[(long long)c * N];
+        if (mm) v = __fdiv_rn(__fsub_rn(v, mm[2 * c]), __fsub_rn(mm[2 * c + 1], mm[2 * c]));
+        has_nan = has_nan || (v != v);
+        mx = fmaxf(mx, v);
+    }
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) {
+        float v = mb[(long long)c * N];
+        if (mm) v = __fdiv_rn(__fsub_rn(v, mm[2 * c]), __fsub_rn(mm[2 * c + 1], mm[2 * c]));
+        sum += expf(v - mx);
+    }
+    stats[(long long)b * N + p] = make_float2(has_nan ? __int_as_float(0x7fc00000) : mx, sum);
+}
+
+constexpr int kUnarySlab = 32;
+
+__global__ void __launch_bounds__(kUnaryPix) unary_write_kernel(const float *__restrict__ maps, const float *__restrict__ minmax,
+                                                                const float2 *__restrict__ stats, float *__restrict__ unary, int C,
+                                                                int Cp, int N) {
+    __shared__ float s_tile[kUnaryPix][kUnarySlab + 1];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * kUnaryPix, c0 = blockIdx.y * kUnarySlab;
+    const int p = p0 + threadIdx.x;
+    const int n_c = min(kUnarySlab, Cp - c0);
+    if (p < N) {
+        const float2 st = stats[(long long)b * N + p];
+        const bool has_nan = st.x != st.x;
+        for (int j = 0; j < n_c; ++j) {
+            const int c = c0 + j;
+            float u = 0.f;  // padding channels
+            if (c < C) {
+                float v = maps[((long long)b * C + c) * N + p];
+                if (minmax) {
+                    float mn = minmax[((long long)b * C + c) * 2], hi = minmax[((long long)b * C + c) * 2 + 1];
+                    v = __fdiv_rn(__fsub_rn(v, mn), __fsub_rn(hi, mn));
+                }
+                float pr = __fdiv_rn(expf(v - st.x), st.y);
+                pr = fminf(fmaxf(pr, 1e-5f), 1.0f);
+                u = has_nan ? __int_as_float(0x7fc00000) : -logf(pr);
+            }
+            s_tile[threadIdx.x][j] = u;
+        }
+    }
+    __syncthreads();
+    const int n_here = min(kUnaryPix, N - p0);
+    for (int i = threadIdx.x; i < n_here * n_c; i += blockDim.x) {
+        const int pp = i / n_c, j = i - pp * n_c;
+        unary[((long long)b * N + p0 + pp) * Cp + c0 + j] = s_tile[pp][j];
+    }
+}
+
 __global__ void __launch_bounds__(kUnaryPix) pack_cn_to_nc_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int Cp, int N) {
     extern __shared__ float s_tile[];
     const int b = blockIdx.y, pitch = Cp + 1, p0 = blockIdx.x * kUnaryPix, p = p0 + threadIdx.x;
@@ -683,15 +747,30 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
     return launch_status();
 }
 
-extern "C" int pnp_crf_unary_from_maps(const float *maps, const float *minmax, float *unary, int B, int C, int N,
-                                       pnp_stream_t stream) {
+extern "C" size_t pnp_crf_unary_workspace_bytes(int B, int C, int N) {
+    if (B < 1 || C < 1 || N < 1) return 0;
+    return C > kUnarySlab ? align_up((size_t)B * N * sizeof(float2), 256) : 0;
+}
+
+extern "C" int pnp_crf_unary_from_maps(const float *maps, const float *minmax, float *unary, void *workspace, size_t workspace_bytes,
+                                       int B, int C, int N, pnp_stream_t stream) {
     if (!maps || !unary || B < 1 || C < 1 || N < 1 || B > 65535) return PNP_ERR_INVALID_ARGUMENT;
     const int Cp = (C + 3) / 4 * 4;
+    cudaStream_t st = as_stream(stream);
+    if (C > kUnarySlab) {  // many channels: two passes, 32-channel slabs
+        if (!workspace || workspace_bytes < pnp_crf_unary_workspace_bytes(B, C, N)) return PNP_ERR_WORKSPACE;
+        float2 *stats = reinterpret_cast<float2 *>(workspace);
+        const bool timed = prof::on(kCrfUnary, st);
+        if (timed) prof::begin(kCrfUnary, st);
+        unary_stats_kernel<<<dim3(ceil_div(N, kUnaryPix), B), kUnaryPix, 0, st>>>(maps, minmax, stats, C, N);
+        unary_write_kernel<<<dim3(ceil_div(N, kUnaryPix), ceil_div(Cp, kUnarySlab), B), kUnaryPix, 0, st>>>(maps, minmax, stats, unary, C,
+                                                                                                           Cp, N);
+        if (timed) prof::end(kCrfUnary, st);
+        return launch_status();
+    }
     size_t smem = unary_smem(Cp);
-    if (smem > 200 * 1024) return PNP_ERR_INVALID_ARGUMENT;
     cudaError_t e = cudaFuncSetAttribute(unary_from_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_err(e);
-    cudaStream_t st = as_stream(stream);
     PNP_LAUNCH(kCrfUnary, st, unary_from_maps_kernel<<<dim3(ceil_div(N, kUnaryPix), B), kUnaryPix, smem, st>>>(maps, minmax, unary, C, Cp, N));
     return launch_status();
 }

@@ -231,7 +231,10 @@ def crf_unary_from_maps(maps, minmax=None):
     if minmax is not None:
         _req(minmax, torch.float32, "minmax")
     U = torch.empty((B, N, crf_pad_channels(C)), dtype=torch.float32, device=maps.device)
-    check(_lib.load().pnp_crf_unary_from_maps(_p(maps), _p(minmax), _p(U), B, C, N, _stream()), "pnp_crf_unary_from_maps")
+    lib = _lib.load()
+    ws_bytes = lib.pnp_crf_unary_workspace_bytes(B, C, N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=maps.device) if ws_bytes else None
+    check(lib.pnp_crf_unary_from_maps(_p(maps), _p(minmax), _p(U), _p(ws), ws_bytes, B, C, N, _stream()), "pnp_crf_unary_from_maps")
     return U
 
 
