@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm", default="fp32", choices=["fp32", "tf32", "bf16"],
+    ap.add_argument("--gemm", default="fp32", choices=["fp32", "3xtf32", "tf32", "bf16"],
                     help="precision of the model's torch GEMMs (the reference runs fp32; anything else is reported in dtype)")
     ap.add_argument("--guide", default="natural", choices=["natural", "noise"], help="CRF guide image flavour (SURVEY 8d)")
     ap.add_argument("--ref-images", type=int, default=0, help="images per step of the CPU arm (0 = sized to the time budget)")
@@ -312,7 +312,7 @@ def run_ours(args):
                   for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.gemm == "fp32" else args.gemm, "data": "synthetic",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "3xtf32": "f32 (ViT GEMMs as 3 error-compensated TF32 products)"}.get(args.gemm, args.gemm), "data": "synthetic",
             "config": {"workload": w["name"], "images_per_step_per_gpu": B, "img_size": w["S"], "patch_grid": w["P"],
                        "classes": w["C"] if args.classes == "all20" else "live (mean %.2f per image)" % (sum(len(c) for c in w["class_lists"]) / B),
                        "channels": w["C"] + 1 if args.classes == "all20" else "classes + background", "drop_iter": w["drop_iter"], "block": w["layer"] + 1,

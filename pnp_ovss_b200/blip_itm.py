@@ -61,6 +61,33 @@ class FusedXattnSoftmax(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------- ViT-L/16
+def _tf32_split(t):
+    """t = hi + lo with hi exactly representable in TF32 (10 explicit mantissa bits, round to nearest)."""
+    hi = ((t.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+    return hi, t - hi
+
+
+def _linear_3xtf32(x, lin, cache):
+    """y = x W^T + b with fp32-grade accuracy on the TF32 tensor cores: three TF32 GEMMs on an exact hi/lo split of both
+    operands (x_hi W_hi + x_hi W_lo + x_lo W_hi; the dropped x_lo W_lo term is ~2^-22 relative).  Still plain torch
+    dense contractions; `cache` holds the split of the frozen weight."""
+    if "w" not in cache:
+        w_hi, w_lo = _tf32_split(lin.weight.detach())
+        cache["w"] = (w_hi.t().contiguous(), w_lo.t().contiguous())
+    w_hi, w_lo = cache["w"]
+    shape = x.shape
+    x2 = x.reshape(-1, shape[-1])
+    x_hi, x_lo = _tf32_split(x2.contiguous())
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        y = torch.addmm(lin.bias, x_hi, w_hi) if lin.bias is not None else x_hi @ w_hi
+        y = y + (x_hi @ w_lo + x_lo @ w_hi)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return y.view(*shape[:-1], -1)
+
+
 class _VitBlock(nn.Module):
     def __init__(self, dim, heads, mlp_ratio=4.0):
         super().__init__()
@@ -71,13 +98,20 @@ class _VitBlock(nn.Module):
         self.fc1 = nn.Linear(dim, int(dim * mlp_ratio))
         self.fc2 = nn.Linear(int(dim * mlp_ratio), dim)
         self.heads = heads
+        self.split3 = False          # "3xtf32": error-compensated TF32 GEMMs (inference only, frozen weights)
+        self._w3 = [{}, {}, {}, {}]
+
+    def _lin(self, i, lin, x):
+        if self.split3 and not torch.is_grad_enabled():
+            return _linear_3xtf32(x, lin, self._w3[i])
+        return lin(x)
 
     def forward(self, x):
         B, L, D = x.shape
-        qkv = self.qkv(self.norm1(x)).view(B, L, 3, self.heads, D // self.heads).permute(2, 0, 3, 1, 4)
+        qkv = self._lin(0, self.qkv, self.norm1(x)).view(B, L, 3, self.heads, D // self.heads).permute(2, 0, 3, 1, 4)
         a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
-        x = x + self.proj(a.transpose(1, 2).reshape(B, L, D))
-        return x + self.fc2(F.gelu(self.fc1(self.norm2(x))))
+        x = x + self._lin(1, self.proj, a.transpose(1, 2).reshape(B, L, D))
+        return x + self._lin(3, self.fc2, F.gelu(self._lin(2, self.fc1, self.norm2(x))))
 
 
 class VisionTransformer(nn.Module):
@@ -206,6 +240,9 @@ class BlipITM(nn.Module):
         return self.emb_ln(self.word_emb(ids) + self.pos_emb(pos)[None])
 
     def _vit(self, imgs):
+        split3 = self.gemm_precision == "3xtf32"
+        for blk in self.visual_encoder.blocks:
+            blk.split3 = split3
         if self.gemm_precision == "bf16":
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return self.visual_encoder(imgs).float()

@@ -13,7 +13,7 @@ imgs = w["imgs"][:8].to(dev)
 caps = w["captions"][:8]
 tok8 = w["tok"](caps, padding="max_length", max_length=500).to(dev)
 ref, _ = model.gradcam(imgs, caps, tok8, layer=7, head=9)
-for mode in ("tf32", "bf16"):
+for mode in ("3xtf32", "tf32", "bf16"):
     torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
     model.gemm_precision = mode
     got, _ = model.gradcam(imgs, caps, tok8, layer=7, head=9)

@@ -170,3 +170,27 @@ def test_config0_full_size_model_single_image(dev):
                                            threshold=0.15, data_type="voc", mode="blur", n_class=21)
     import smoke_case
     assert smoke_case.disagreement(h_e2e.cpu().numpy(), h_ref) <= 0.02
+
+
+def test_3xtf32_gemm_mode_keeps_fp32_grade_gradcam(dev):
+    """--gemm 3xtf32: the ViT linears run as three TF32 tensor-core GEMMs on an exact hi/lo split of both operands.
+    The GradCAM must stay far inside the 1e-3 tolerance (plain TF32 does not: profiles/tf32_gradcam_error.py)."""
+    from pnp_ovss_b200.blip_itm import BlipITM, _tf32_split
+    t = torch.randn(4096, device=dev) * 3
+    hi, lo = _tf32_split(t)
+    assert torch.equal(hi + lo, t) and int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    tok = synth.SyntheticWordPieceTokenizer()
+    caps = ["A picture of cat aeroplane", "A picture of dog"]
+    tokens = tok(caps, padding="max_length", max_length=500).to(dev)
+    torch.manual_seed(3)
+    m = BlipITM(img_size=96, tokenizer=tok, hidden=128, layers=3, heads=2, inter=256, vit_dim=256, vit_depth=4, vit_heads=4,
+                max_pos=64).eval()
+    with torch.no_grad():
+        for p_ in m.parameters():
+            p_.mul_(2.0)
+    m = m.to(dev).requires_grad_(False)
+    imgs = torch.randn(2, 3, 96, 96, generator=torch.Generator().manual_seed(1)).to(dev)
+    ref, _ = m.gradcam(imgs, caps, tokens, layer=1, head=1)
+    m.gemm_precision = "3xtf32"
+    got, _ = m.gradcam(imgs, caps, tokens, layer=1, head=1)
+    assert (got - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
