@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--ref-images", type=int, default=0, help="images per step of the CPU arm (0 = sized to the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra 3xtf32 measurement reported under `alt_gemm`")
     ap.add_argument("--no-overlap", action="store_true", help="run the round-0 pass on the main stream instead of a side stream")
     ap.add_argument("--classes", default="all20", choices=["all20", "live"],
                     help="all20: every image is captioned with the 20 VOC classes (BASELINE configs[1]); live: classes per image drawn "
@@ -278,6 +279,22 @@ def run_ours(args):
                "h2d_bytes_per_step": int(imgs_h.numel() * 4 + guides_h.numel() + gts_h.numel() * 4),
                "d2h_bytes_per_step": int(hist_host.numel() * 8), "ms_per_step": e2e_ms / args.steps}
 
+    # ---- the same steps with the ViT linears as error-compensated TF32 products (reported beside the fp32 headline)
+    alt = None
+    if args.gemm == "fp32" and not args.no_alt:
+        model.gemm_precision = "3xtf32"
+        step(False)
+        alt_ms = timed(False, args.steps)
+        probe = imgs_src[:4].contiguous()
+        tok4 = w["tok"](w["captions"][:4], padding="max_length", max_length=500).to(dev)
+        cam_3x = model.gradcam(probe, w["captions"][:4], tok4, layer=w["layer"], head=w["head"])[0]
+        model.gemm_precision = "fp32"
+        cam_32 = model.gradcam(probe, w["captions"][:4], tok4, layer=w["layer"], head=w["head"])[0]
+        dev_rel = float(((cam_3x - cam_32).abs().max() / cam_32.abs().max()).item())
+        alt = {"gemm": "3xtf32 (x_hi W_hi + x_hi W_lo + x_lo W_hi on TF32 tensor cores, fp32 accumulate, ViT linears only)",
+               "value": world * B * args.steps / (alt_ms / 1e3), "unit": "images/s", "ms_per_step": alt_ms / args.steps,
+               "gradcam_max_dev_vs_fp32_rel_to_max": dev_rel}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -323,7 +340,7 @@ def run_ours(args):
                        "M_s": stats.get("M_s"), "M_b_per_batch": stats.get("M_b"),
                        "l2": "per-step working set (>3 GB) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "alt_gemm": alt,
             "custom_kernels": {"ms_per_step": round(sum(v[0] for v in per_kernel.values()), 3),
                                "images_per_s": round(B / (sum(v[0] for v in per_kernel.values()) * 1e-3), 1),
                                "note": "sum of the in-situ event times of every pnp:: kernel in one (warm-up) step; the rest of "
