@@ -101,18 +101,34 @@ __global__ void __launch_bounds__(256) blur_axis_kernel(LatticeView L, const flo
     float *nb = new_v + img_off;
     const int2 *nbr = reinterpret_cast<const int2 *>(L.nbr) + (size_t)axis * L.vertex_stride;
     const long long total = (long long)(L.M + 1) * nch;
-    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int v = (int)(idx / nch), ch = (int)(idx - (long long)v * nch);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    // software pipeline over the grid-stride loop: the neighbour indices of the NEXT item are fetched while the rows
+    // of the current one are in flight (ncu: the kernel otherwise stalls on the index -> address -> row chain)
+    int v = (int)(idx / nch), ch = (int)(idx - (long long)v * nch);
+    int2 n = (v < L.M) ? nbr[v] : make_int2(0, 0);
+    while (true) {
+        const long long idx_next = idx + stride;
+        const bool more = idx_next < total;
+        int v_next = 0, ch_next = 0;
+        int2 n_next = make_int2(0, 0);
+        if (more) {
+            v_next = (int)(idx_next / nch);
+            ch_next = (int)(idx_next - (long long)v_next * nch);
+            if (v_next < L.M) n_next = nbr[v_next];
+        }
         if (v == L.M) {
             *reinterpret_cast<float4 *>(nb + 4 * ch) = make_float4(0.f, 0.f, 0.f, 0.f);
-            continue;
+        } else {
+            const float4 c = *reinterpret_cast<const float4 *>(ob + (long long)(v + 1) * L.vp + 4 * ch);
+            const float4 a1 = *reinterpret_cast<const float4 *>(ob + (long long)n.x * L.vp + 4 * ch);
+            const float4 a2 = *reinterpret_cast<const float4 *>(ob + (long long)n.y * L.vp + 4 * ch);
+            // new = old + 0.5f * (n1 + n2)   (plain cached accesses: streaming hints measured 4 % slower, profiles/README.md)
+            *reinterpret_cast<float4 *>(nb + (long long)(v + 1) * L.vp + 4 * ch) = f4_add(c, f4_mul(f4_add(a1, a2), 0.5f));
         }
-        const int2 n = nbr[v];
-        const float4 c = *reinterpret_cast<const float4 *>(ob + (long long)(v + 1) * L.vp + 4 * ch);
-        const float4 a1 = *reinterpret_cast<const float4 *>(ob + (long long)n.x * L.vp + 4 * ch);
-        const float4 a2 = *reinterpret_cast<const float4 *>(ob + (long long)n.y * L.vp + 4 * ch);
-        // new = old + 0.5f * (n1 + n2)   (plain cached accesses: streaming hints measured 4 % slower, profiles/README.md)
-        *reinterpret_cast<float4 *>(nb + (long long)(v + 1) * L.vp + 4 * ch) = f4_add(c, f4_mul(f4_add(a1, a2), 0.5f));
+        if (!more) break;
+        idx = idx_next; v = v_next; ch = ch_next; n = n_next;
     }
 }
 
