@@ -144,9 +144,10 @@ def algorithmic_bytes(kernel, w, stats, T):
         "blur_horizontal": 8 * B * Cc * N,
         "crf_unary": 8 * B * Cc * N,
         "crf_splat_bilateral": 4 * Cc * (B * N + Mb) + 8 * 6 * B * N,
-        "crf_blur_axis_bilateral": (8 * Cc + 8) * Mb,
+        # one launch fuses two axis passes (blur_axis2_kernel): two units of SURVEY 8(d)'s "read + write per blur pass"
+        "crf_blur_axis_bilateral": 2 * (8 * Cc + 8) * Mb,
         "crf_splat_spatial": 4 * Cc * B * (N + Ms) + 8 * 3 * N,
-        "crf_blur_axis_spatial": (8 * Cc + 8) * Ms * B,
+        "crf_blur_axis_spatial": 1.5 * (8 * Cc + 8) * Ms * B,  # 3 axes in 2 launches (one fused pair + one single)
         "crf_meanfield_update": 4 * Cc * B * (2 * N) + 4 * Cc * (B * Ms + Mb) + 8 * 9 * B * N,
         "confusion": 12 * B * N,
         "argmax_channels": 4 * Cc * B * N + 4 * B * N,

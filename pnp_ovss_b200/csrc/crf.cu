@@ -132,6 +132,46 @@ __global__ void __launch_bounds__(256) blur_axis_kernel(LatticeView L, const flo
     }
 }
 
+// Two consecutive axis passes in one launch (temporal fusion through the 126 MB L2): new = B_b(B_a(old)).  The first
+// pass is recomputed on the fly at the vertex and at its two axis-b neighbours (9 row gathers instead of 3 + 3), so the
+// intermediate lattice is never written to or read back from HBM: DRAM traffic per pair of axes drops from
+// 2 x (read + write) to one read + one write.  Every B_a value is computed with the same operations in the same order as
+// the single-axis kernel, so the result is bit-identical to two separate passes.
+__device__ __forceinline__ float4 blur_row(const float *__restrict__ ob, int row, int2 n, int vp, int ch) {
+    const float4 c = *reinterpret_cast<const float4 *>(ob + (size_t)row * vp + 4 * ch);
+    const float4 a1 = *reinterpret_cast<const float4 *>(ob + (size_t)n.x * vp + 4 * ch);
+    const float4 a2 = *reinterpret_cast<const float4 *>(ob + (size_t)n.y * vp + 4 * ch);
+    return f4_add(c, f4_mul(f4_add(a1, a2), 0.5f));
+}
+
+__global__ void __launch_bounds__(256) blur_axis2_kernel(LatticeView L, const float *__restrict__ old_v, float *__restrict__ new_v,
+                                                         int axis_a, int axis_b, int Cp) {
+    const int nch = Cp >> 2;
+    const int b = blockIdx.y;
+    const long long img_off = L.shared ? (long long)b * (L.M + 1) * L.vp : 0;
+    const float *ob = old_v + img_off;
+    float *nb = new_v + img_off;
+    const int2 *nbr_a = reinterpret_cast<const int2 *>(L.nbr) + (size_t)axis_a * L.vertex_stride;
+    const int2 *nbr_b = reinterpret_cast<const int2 *>(L.nbr) + (size_t)axis_b * L.vertex_stride;
+    const long long total = (long long)(L.M + 1) * nch;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(idx / nch), ch = (int)(idx - (long long)v * nch);
+        if (v == L.M) {
+            *reinterpret_cast<float4 *>(nb + 4 * ch) = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        const int2 nb2 = nbr_b[v];  // axis-b neighbours of v (+1 shifted, 0 = none)
+        const int2 na_v = nbr_a[v];
+        const int2 na_1 = nb2.x ? nbr_a[nb2.x - 1] : make_int2(0, 0);
+        const int2 na_2 = nb2.y ? nbr_a[nb2.y - 1] : make_int2(0, 0);
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 t_v = blur_row(ob, v + 1, na_v, L.vp, ch);
+        const float4 t_1 = nb2.x ? blur_row(ob, nb2.x, na_1, L.vp, ch) : zero;  // the sentinel row stays zero after pass a
+        const float4 t_2 = nb2.y ? blur_row(ob, nb2.y, na_2, L.vp, ch) : zero;
+        *reinterpret_cast<float4 *>(nb + (size_t)(v + 1) * L.vp + 4 * ch) = f4_add(t_v, f4_mul(f4_add(t_1, t_2), 0.5f));
+    }
+}
+
 // slice one lattice at (pixel gp of image b, chunk ch): sum_j (w_j * values[o_j]) * alpha, optionally * norm.
 // DP1 = d+1 is a template parameter so the d+1 gathers are all in flight before the (ordered) accumulation.
 template <int DP1>
@@ -638,7 +678,17 @@ static const float *run_splat_blur(const LatticeView &L, const float *x, float *
     const int id_blur = L.shared ? kBlurAxisSpatial : kBlurAxisBilateral;
     PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx_splat, gy), 256, 0, st>>>(L, x, va, Cp, normalized));
     float *src = va, *dst = vb;
-    for (int j = 0; j < L.Dp1; ++j) {
+    static const bool fuse_pairs = env_mult("PNP_BLUR_FUSE", 1) != 2;  // PNP_BLUR_FUSE=2: one launch per axis (tuning)
+    static const int mult2 = env_mult("PNP_GRID_MULT_BLUR2", 8);
+    const int gx2 = std::max(1, grid_for((long long)(L.M + 1) * nch, 256, mult2) / div);
+    int j = 0;
+    if (fuse_pairs) {
+        for (; j + 1 < L.Dp1; j += 2) {  // axes (0,1), (2,3), (4,5): two passes per launch
+            PNP_LAUNCH(id_blur, st, blur_axis2_kernel<<<dim3(gx2, gy), 256, 0, st>>>(L, src, dst, j, j + 1, Cp));
+            std::swap(src, dst);
+        }
+    }
+    for (; j < L.Dp1; ++j) {
         PNP_LAUNCH(id_blur, st, blur_axis_kernel<<<dim3(gx, gy), 256, 0, st>>>(L, src, dst, j, Cp));
         std::swap(src, dst);
     }
