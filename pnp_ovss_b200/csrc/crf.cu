@@ -768,7 +768,10 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
     int LPP = 0, CPL = 0;
     {
         double best_eff = 0.0;
-        for (int cpl = 1; cpl <= 4; ++cpl) {
+        static const int forced_cpl = env_mult("PNP_UPDATE_CPL", 9);  // tuning: force chunks per lane (1..4)
+        for (int cpl = 1; cpl <= 6; ++cpl) {
+            if (cpl == 5) continue;
+            if (forced_cpl <= 6 && cpl != forced_cpl) continue;
             int lpp = (nch_all + cpl - 1) / cpl;
             if (lpp > 32) continue;
             double eff = (double)(32 / lpp) * nch_all / (32.0 * cpl);
@@ -784,7 +787,8 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
             case 1: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 1><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
             case 2: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 2><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
             case 3: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 3><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
-            default: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 4><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
+            case 4: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 4><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
+            default: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 6><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
         }
     };
     auto update = [&](bool with_labels) {
