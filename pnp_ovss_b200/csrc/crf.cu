@@ -596,34 +596,34 @@ __global__ void __launch_bounds__(kUnaryPix) unary_write_kernel(const float *__r
     }
 }
 
+// [B,C,N] <-> [B,N,Cp] in 32-channel slabs through a [128][33] shared tile (any channel count)
 __global__ void __launch_bounds__(kUnaryPix) pack_cn_to_nc_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int Cp, int N) {
-    extern __shared__ float s_tile[];
-    const int b = blockIdx.y, pitch = Cp + 1, p0 = blockIdx.x * kUnaryPix, p = p0 + threadIdx.x;
-    if (p < N) {
-        for (int c = 0; c < C; ++c) s_tile[threadIdx.x * pitch + c] = src[((long long)b * C + c) * N + p];
-        for (int c = C; c < Cp; ++c) s_tile[threadIdx.x * pitch + c] = 0.f;
-    }
+    __shared__ float s_tile[kUnaryPix][kUnarySlab + 1];
+    const int b = blockIdx.z, p0 = blockIdx.x * kUnaryPix, c0 = blockIdx.y * kUnarySlab, p = p0 + threadIdx.x;
+    const int n_c = min(kUnarySlab, Cp - c0);
+    if (p < N)
+        for (int j = 0; j < n_c; ++j) s_tile[threadIdx.x][j] = (c0 + j < C) ? src[((long long)b * C + c0 + j) * N + p] : 0.f;
     __syncthreads();
     const int n_here = min(kUnaryPix, N - p0);
-    float *db = dst + ((long long)b * N + p0) * Cp;
-    for (int i = threadIdx.x; i < n_here * Cp; i += blockDim.x) {
-        int pp = i / Cp, c = i - pp * Cp;
-        db[i] = s_tile[pp * pitch + c];
+    for (int i = threadIdx.x; i < n_here * n_c; i += blockDim.x) {
+        const int pp = i / n_c, j = i - pp * n_c;
+        dst[((long long)b * N + p0 + pp) * Cp + c0 + j] = s_tile[pp][j];
     }
 }
 
 __global__ void __launch_bounds__(kUnaryPix) unpack_nc_to_cn_kernel(const float *__restrict__ src, float *__restrict__ dst, int C, int Cp, int N) {
-    extern __shared__ float s_tile[];
-    const int b = blockIdx.y, pitch = Cp + 1, p0 = blockIdx.x * kUnaryPix, p = p0 + threadIdx.x;
+    __shared__ float s_tile[kUnaryPix][kUnarySlab + 1];
+    const int b = blockIdx.z, p0 = blockIdx.x * kUnaryPix, c0 = blockIdx.y * kUnarySlab, p = p0 + threadIdx.x;
+    const int n_c = min(kUnarySlab, Cp - c0);
     const int n_here = min(kUnaryPix, N - p0);
-    const float *sb = src + ((long long)b * N + p0) * Cp;
-    for (int i = threadIdx.x; i < n_here * Cp; i += blockDim.x) {
-        int pp = i / Cp, c = i - pp * Cp;
-        s_tile[pp * pitch + c] = sb[i];
+    for (int i = threadIdx.x; i < n_here * n_c; i += blockDim.x) {
+        const int pp = i / n_c, j = i - pp * n_c;
+        s_tile[pp][j] = src[((long long)b * N + p0 + pp) * Cp + c0 + j];
     }
     __syncthreads();
     if (p < N)
-        for (int c = 0; c < C; ++c) dst[((long long)b * C + c) * N + p] = s_tile[threadIdx.x * pitch + c];
+        for (int j = 0; j < n_c; ++j)
+            if (c0 + j < C) dst[((long long)b * C + c0 + j) * N + p] = s_tile[threadIdx.x][j];
 }
 
 // ------------------------------------------------------------------------------------------ host helpers
@@ -851,21 +851,13 @@ extern "C" int pnp_crf_unary_from_maps(const float *maps, const float *minmax, f
 extern "C" int pnp_crf_pack_cn_to_nc(const float *src_cn, float *dst_nc, int B, int C, int N, pnp_stream_t stream) {
     if (!src_cn || !dst_nc || B < 1 || C < 1 || N < 1 || B > 65535) return PNP_ERR_INVALID_ARGUMENT;
     const int Cp = (C + 3) / 4 * 4;
-    size_t smem = unary_smem(Cp);
-    if (smem > 200 * 1024) return PNP_ERR_INVALID_ARGUMENT;
-    cudaError_t e = cudaFuncSetAttribute(pack_cn_to_nc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_err(e);
-    pack_cn_to_nc_kernel<<<dim3(ceil_div(N, kUnaryPix), B), kUnaryPix, smem, as_stream(stream)>>>(src_cn, dst_nc, C, Cp, N);
+    pack_cn_to_nc_kernel<<<dim3(ceil_div(N, kUnaryPix), ceil_div(Cp, kUnarySlab), B), kUnaryPix, 0, as_stream(stream)>>>(src_cn, dst_nc, C, Cp, N);
     return launch_status();
 }
 
 extern "C" int pnp_crf_unpack_nc_to_cn(const float *src_nc, float *dst_cn, int B, int C, int N, pnp_stream_t stream) {
     if (!src_nc || !dst_cn || B < 1 || C < 1 || N < 1 || B > 65535) return PNP_ERR_INVALID_ARGUMENT;
     const int Cp = (C + 3) / 4 * 4;
-    size_t smem = unary_smem(Cp);
-    if (smem > 200 * 1024) return PNP_ERR_INVALID_ARGUMENT;
-    cudaError_t e = cudaFuncSetAttribute(unpack_nc_to_cn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_err(e);
-    unpack_nc_to_cn_kernel<<<dim3(ceil_div(N, kUnaryPix), B), kUnaryPix, smem, as_stream(stream)>>>(src_nc, dst_cn, C, Cp, N);
+    unpack_nc_to_cn_kernel<<<dim3(ceil_div(N, kUnaryPix), ceil_div(Cp, kUnarySlab), B), kUnaryPix, 0, as_stream(stream)>>>(src_nc, dst_cn, C, Cp, N);
     return launch_status();
 }
