@@ -89,3 +89,15 @@ def test_header_cites_reference_lines():
     text = open(HEADER).read()
     for cite in ("MED:267-283", "BITM:415-433", "DRV:810-853", "DRV:638-647", "DRV:1149-1153", "DRV:1030-1074", "DRV:1106-1112"):
         assert cite in text
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: the header must compile as C99 (no C++ types, no torch types)."""
+    import subprocess
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write('#include "pnp_ovss_b200.h"\nint main(void) { return pnp_abi_version() == PNP_ABI_VERSION ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), f.name],
+                       capture_output=True, text=True)
+    os.unlink(f.name)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
