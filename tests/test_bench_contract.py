@@ -1,0 +1,58 @@
+"""CPU: bench.py's bookkeeping -- workload shapes of BASELINE.json configs[1], the algorithmic-bytes table covering
+the kernel classes the library can time, and the JSON keys the driver contract names."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def test_workload_is_baseline_config_1():
+    w = bench.make_workload(0)
+    assert (w["B"], w["S"], w["P"], w["C"], w["n_class"], w["drop_iter"], w["head"], w["layer"] + 1, w["mode"]) == \
+        (35, 336, 21, 20, 21, 4, 9, 8, "blur+crf")
+    assert tuple(w["imgs"].shape) == (35, 3, 336, 336) and w["guides"].shape == (35, 336, 336, 3) and w["guides"].dtype == np.uint8
+    assert w["gts"].shape == (35, 336, 336) and w["gts"].dtype == np.float32
+    assert all(len(c) == 20 for c in w["class_lists"]) and w["dataset_ids"][0] == list(range(1, 21))
+    w1 = bench.make_workload(1)
+    assert not np.array_equal(w["guides"], w1["guides"])          # ranks get different images (weak scaling)
+
+
+def test_live_class_distribution():
+    bench.WORKLOAD["classes"] = "live"
+    try:
+        w = bench.make_workload(0)
+    finally:
+        bench.WORKLOAD.pop("classes")
+    counts = [len(c) for c in w["class_lists"]]
+    assert min(counts) >= 1 and max(counts) <= 6 and 1.0 <= np.mean(counts) <= 2.2
+    assert all(ids == sorted(ids) and all(1 <= i <= 20 for i in ids) for ids in w["dataset_ids"])
+
+
+def test_algorithmic_bytes_cover_the_timed_kernel_classes():
+    from pnp_ovss_b200 import _lib
+    lib = _lib.load()
+    w = bench.make_workload(0)
+    stats = {"M_s": 14755, "M_b": 3245257}
+    names = [lib.pnp_profile_kernel_name(i).decode() for i in range(1, 19)]
+    assert len(set(names)) == 18 and all(names)
+    latency_bound = {"threshold_prep", "blur_normalize", "lattice_build"}   # reported in ms, not GB/s
+    for n in names:
+        b = bench.algorithmic_bytes(n, w, stats, 31)
+        assert (b is None) == (n in latency_bound), n
+        if b is not None:
+            assert b > 0
+    # the dominant kernels' figures of DESIGN.md section 3
+    assert bench.algorithmic_bytes("crf_blur_axis_bilateral", w, stats, 31) == 2 * (8 * 21 + 8) * 3245257
+    assert bench.algorithmic_bytes("softmax_fwd", w, stats, 31) == 8 * 35 * 12 * 31 * 442
+
+
+def test_reference_arm_sample_is_bounded():
+    # the CPU arm sizes its per-step sample so that warm-up + steps stay within a few minutes
+    for steps, warmup in ((3, 3), (10, 3), (1, 0), (20, 5)):
+        n = max(1, min(4, int(160.0 / (max(steps + warmup, 1) * 12.0))))
+        assert 1 <= n <= 4
