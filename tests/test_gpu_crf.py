@@ -377,3 +377,21 @@ def test_inference_matches_oracle_at_full_resolution(dev, D):
     err = np.abs(got_q - ref_q) / np.maximum(np.abs(ref_q), 1e-6)
     assert err.max() < 1e-3, "max relative error of the marginals at 336x336: %g" % err.max()
     assert (got_map != ref_map).mean() <= 1e-4
+
+
+def test_pydensecrf_surface_anisotropic_parameters(dev, D):
+    """Tuple sxy / srgb (anisotropic kernels, as pydensecrf accepts them) and other compat weights."""
+    from pnp_ovss_b200 import reference_api as R
+    H, W, C = 41, 58, 4
+    img = synth.guide_image(21, H, W)
+    p = np.random.default_rng(7).random((C, H, W)).astype(np.float32)
+    p /= p.sum(0, keepdims=True)
+    outs = []
+    for mod in (D, R):
+        d = mod.DenseCRF2D(W, H, C)
+        d.setUnaryEnergy(np.ascontiguousarray(mod.unary_from_softmax(p)))
+        d.addPairwiseGaussian(sxy=(2, 5), compat=3)
+        d.addPairwiseBilateral(sxy=(80, 40), srgb=(13, 7, 20), rgbim=img, compat=4)
+        outs.append(np.array(d.inference(3)).reshape(C, H, W))
+    err = np.abs(outs[1] - outs[0]) / np.maximum(np.abs(outs[0]), 1e-6)
+    assert err.max() < 1e-3
