@@ -65,15 +65,23 @@ def merge_tokens_batch(gradcam, token_ids, decode, class_lists, segs=None):
 
 # ---------------------------------------------------------------------------------------------- (d)(e)(f)
 class SpatialLatticeCache:
-    """The Gaussian-kernel lattice depends on (H, W, sxy) only; build once per shape (SURVEY 7 hard part 1)."""
+    """The Gaussian-kernel lattice depends on (H, W, sxy) only; build once per shape (SURVEY 7 hard part 1).  Real datasets
+    have many ground-truth sizes, so the cache is a small LRU (a 336x336 spatial lattice is about 11 MB)."""
 
-    def __init__(self):
-        self._cache = {}
+    def __init__(self, max_entries=32):
+        from collections import OrderedDict
+        self._cache = OrderedDict()
+        self._max = max_entries
 
     def get(self, H, W, sxy, device):
-        key = (H, W, float(sxy), str(device))
-        if key not in self._cache:
-            self._cache[key] = ops.build_lattice(H, W, sxy, device=device)
+        sx, sy = (sxy, sxy) if not isinstance(sxy, (tuple, list)) else sxy
+        key = (int(H), int(W), float(sx), float(sy), str(device))
+        if key in self._cache:
+            self._cache.move_to_end(key)
+        else:
+            self._cache[key] = ops.build_lattice(H, W, (sx, sy), device=device)
+            while len(self._cache) > self._max:
+                self._cache.popitem(last=False)
         return self._cache[key]
 
 

@@ -68,16 +68,10 @@ def unary_from_softmax(sm, scale=None, clip=1e-5):
     return (-x.log()).reshape(num_cls, -1).to(torch.float32).cpu().numpy()
 
 
-_SPATIAL_CACHE = {}
-
-
 def _spatial_lattice(H, W, sxy, device):
-    """The Gaussian-kernel lattice depends on (H, W, sxy) only: built once per shape and process."""
-    sx, sy = (sxy, sxy) if np.isscalar(sxy) else sxy
-    key = (int(H), int(W), float(sx), float(sy), str(device))
-    if key not in _SPATIAL_CACHE:
-        _SPATIAL_CACHE[key] = ops.build_lattice(H, W, (sx, sy), device=device)
-    return _SPATIAL_CACHE[key]
+    """The Gaussian-kernel lattice depends on (H, W, sxy) only: built once per shape (shared LRU of pipeline.py)."""
+    from .pipeline import _SPATIAL
+    return _SPATIAL.get(H, W, sxy, device)
 
 
 class DenseCRF2D:
