@@ -16,7 +16,7 @@ from pnp_ovss_b200 import host
 
 def _emulate_merge(g, segs):
     """What pnp_token_merge computes, in numpy fp32 (sequential adds, one division)."""
-    rows = g[3:-1] if False else g[3:]
+    rows = g[3:]  # pnp_token_merge addresses rows from row_offset = 3; segments never reach the trailing SEP row
     out = np.zeros((len(segs),) + g.shape[1:], np.float32)
     for c, (s, l, d) in enumerate(segs):
         if l == 0:
