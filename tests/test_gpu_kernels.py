@@ -290,3 +290,35 @@ def test_argmax_channels(dev, ops):
         x[1, 2, 15:20] = np.nan               # ... and the first NaN wins
         out = ops.argmax_channels(torch.from_numpy(x).to(dev)).cpu().numpy()
         assert np.array_equal(out, np.argmax(x, axis=1).astype(np.int32))
+
+
+# ------------------------------------------------------------------------------------------------ error behaviour
+def test_ops_fail_loudly_on_bad_arguments(dev, ops):
+    """No silent fallbacks: wrong dtypes / layouts / shapes / undersized workspaces raise PnpError (negative ABI code)."""
+    import ctypes
+    from pnp_ovss_b200 import PnpError, _lib
+    with pytest.raises(PnpError):
+        ops.softmax_fwd(torch.zeros(1, 12, 4, 442, dtype=torch.float16, device=dev))
+    with pytest.raises(PnpError):
+        ops.softmax_fwd(torch.zeros(1, 12, 4, 2000, device=dev))                    # K beyond the register-row limit
+    with pytest.raises(PnpError):
+        ops.argmax_channels(torch.zeros(2, 3, 16, device=dev).transpose(1, 2))      # not contiguous
+    with pytest.raises(PnpError):
+        ops.gaussian_blur(torch.zeros(1, 8, 8, device=dev), 0.0)                    # sigma must be positive
+    with pytest.raises(PnpError):
+        ops.threshold_upsample(torch.zeros(1, 2, 40, 40, device=dev), 64, 64, 0.15, False, True)   # P*P > 1024
+    lat = ops.build_lattice(16, 16, 3.0, rgb=torch.zeros(2, 16, 16, 3, dtype=torch.uint8, device=dev), srgb=5.0)
+    with pytest.raises(PnpError):
+        ops.crf_filter(lat, torch.zeros(3, 256, 4, device=dev))                     # lattice built for 2 images, 3 given
+    lib = _lib.load()
+    x = torch.zeros(1, 8, 8, device=dev)
+    y = torch.empty_like(x)
+    mm = torch.empty(1, 2, device=dev)
+    ws = torch.empty(16, dtype=torch.uint8, device=dev)
+    rc = lib.pnp_gaussian_blur(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(mm.data_ptr()),
+                               ctypes.c_void_p(ws.data_ptr()), 16, 1, 8, 8, 1.0, 1, ctypes.c_void_p(0))
+    assert rc == -2 and b"workspace" in lib.pnp_error_string(rc)                    # PNP_ERR_WORKSPACE
+    hist = torch.zeros(3, 3, dtype=torch.int64, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.confusion_accumulate(torch.full((1, 4), 7, dtype=torch.int32, device=dev), torch.zeros(1, 4, device=dev), 3, hist, bad_count=bad)
+    assert int(bad.item()) == 4 and int(hist.sum()) == 0                            # out-of-range ids are counted, never binned
