@@ -201,6 +201,18 @@ class _BertLayer(nn.Module):
         return self.out_ln(self.out(F.gelu(self.inter(x))) + x)
 
 
+class _TextEncoderView:
+    """The slice of the LAVIS XBertEncoder surface the reference touches: `.base_model` (itself) and `.encoder.layer`."""
+
+    def __init__(self, model):
+        self.encoder = self
+        self.layer = model.layer
+
+    @property
+    def base_model(self):
+        return self
+
+
 class BlipITM(nn.Module):
     def __init__(self, img_size=336, tokenizer=None, vocab=30524, hidden=768, layers=12, heads=12, inter=3072,
                  vit_dim=1024, vit_depth=24, vit_heads=16, max_pos=512):
@@ -228,6 +240,21 @@ class BlipITM(nn.Module):
             nn.init.ones_(m.weight)
             nn.init.zeros_(m.bias)
 
+    # ---- the reference's attribute path / checkpoint ---------------------------------------------------
+    @property
+    def text_encoder(self):
+        """model.text_encoder.base_model.base_model.encoder.layer[i].crossattention.self (BITM:388-392) resolves to
+        this model's cross-attention modules."""
+        return _TextEncoderView(self)
+
+    def load_lavis_checkpoint(self, path_or_state_dict):
+        """Weights of the reference's LAVIS BlipITM (YAML:10) -> this model; see lavis_compat.load_lavis_state_dict."""
+        from .lavis_compat import load_lavis_state_dict
+        sd = path_or_state_dict
+        if not isinstance(sd, dict):
+            sd = torch.load(sd, map_location="cpu")
+        return load_lavis_state_dict(self, sd)
+
     # ---- pieces -----------------------------------------------------------------------------------
     def _tokenize(self, text_input, device):
         text = self.tokenizer(text_input, padding="longest", truncation=True, max_length=500, return_tensors="pt")  # BITM:230-236
@@ -248,8 +275,13 @@ class BlipITM(nn.Module):
                 return self.visual_encoder(imgs).float()
         return self.visual_encoder(imgs)
 
-    def forward(self, visual_input, text_input):
-        """ITM logits [B,2] (BITM:217-249, match_head='itm')."""
+    def forward(self, visual_input, text_input=None, match_head="itm"):
+        """ITM logits [B,2] (BITM:217-249, match_head='itm').  Also takes the LAVIS call form
+        model({"image": ..., "text_input": ...}, match_head="itm") of BITM:395."""
+        if isinstance(visual_input, dict):
+            visual_input, text_input = visual_input["image"], visual_input["text_input"]
+        if match_head != "itm":
+            raise NotImplementedError("only the ITM head is on the mask-extraction path")
         ids, att = self._tokenize(text_input, visual_input.device)
         enc = self._vit(visual_input)
         add_mask = ((1.0 - att.float()) * -10000.0)[:, None, None, :]

@@ -212,15 +212,29 @@ def compute_gradcam_ensemble(args, model, visual_input, text_input, tokenized_te
     The reference builds all 12x12 maps and the drivers read exactly one, blocklist[max_att_block_num-1][prune_att_head]
     (DRV:572-574, 619-621).  Here that entry is computed eagerly by the fused softmax-backward/GradCAM kernel of the
     model's cross-attention (pnp_ovss_b200.blip_itm.BlipITM.gradcam); any other [layer][head] is computed on first
-    access by one more trimmed model pass, so the full 12x12 surface stays readable without paying for it."""
+    access by one more model pass, so the full 12x12 surface stays readable without paying for it.  `model` may also
+    be the reference's own LAVIS BlipITM object (see lavis_compat.gradcam_from_lavis_model)."""
     layer = int(args.max_att_block_num) - 1
     head = int(args.prune_att_head)
-    gradcam, output = model.gradcam(visual_input, text_input, tokenized_text, layer=layer, head=head)
+    if hasattr(model, "gradcam"):            # pnp_ovss_b200.blip_itm.BlipITM: trimmed pass, fused kernels (a)+(b)
+        def compute(l, h):
+            return model.gradcam(visual_input, text_input, tokenized_text, layer=l, head=h)
+    else:                                    # a live LAVIS BlipITM (BITM:388-425 attribute protocol), kernel (a) patched in
+        from . import lavis_compat
+        P = int(int(args.img_size) / 16)
 
-    def compute(l, h):
-        return model.gradcam(visual_input, text_input, tokenized_text, layer=l, head=h)[0]
+        def compute(l, h):
+            return lavis_compat.gradcam_from_lavis_model(model, visual_input, text_input, tokenized_text, l, h, P,
+                                                         fused=getattr(args, "fused_xattn", True))
+    gradcam, output = compute(layer, head)
+    xattn = _cross_attention_modules(model)
+    return _LazyBlocklist(lambda l, h: compute(l, h)[0], {(layer, head): gradcam}, len(xattn),
+                          getattr(xattn[0], "heads", None) or xattn[0].num_attention_heads), [], output
 
-    return _LazyBlocklist(compute, {(layer, head): gradcam}, len(model.layer), model.layer[0].crossattention.self.heads), [], output
+
+def _cross_attention_modules(model):
+    from .lavis_compat import cross_attention_modules
+    return cross_attention_modules(model)
 
 
 class _LazyBlocklist:

@@ -101,6 +101,55 @@ def test_inference_blip_filteredcaption_matches_oracle_loop(dev):
     assert torch.equal(cm.cpu(), want)
 
 
+def test_live_lavis_protocol_model_is_a_drop_in(dev):
+    """compute_gradcam_ensemble / Inference_BLIP_filteredcaption handed a LAVIS-shaped model object (the reference's
+    module tree, call form and capture protocol; tests/lavis_shaped_model.py) instead of the native BlipITM: the fused
+    softmax is patched into the requested block for the call (fused_xattn=True) or the model's own hooks are read on
+    the device (False).  Oracle: the CPU reference procedure on the same weights."""
+    from lavis_shaped_model import LavisShapedBlipITM
+    from oracle import hotpath as O
+    from oracle import reference_arm as RA
+    from pnp_ovss_b200 import reference_api as R
+    from pnp_ovss_b200.blip_itm import BlipITM
+    from pnp_ovss_b200.lavis_compat import cross_attention_modules
+    tok = synth.SyntheticWordPieceTokenizer()
+    caps = ["A picture of cat aeroplane", "A picture of dog"]
+    tokens = tok(caps, padding="max_length", max_length=500)
+    imgs = torch.randn(2, 3, 96, 96, generator=torch.Generator().manual_seed(3))
+    dims = dict(hidden=128, layers=3, heads=2, inter=256, vit_dim=64, vit_depth=2, vit_heads=2, max_pos=64)
+    torch.manual_seed(21)
+    lavis = LavisShapedBlipITM(tok, img_size=96, **dims).eval()
+    native = BlipITM(img_size=96, tokenizer=tok, vocab=30524, **dims).eval()
+    native.load_lavis_checkpoint(lavis.state_dict())
+    ref_model = RA.install_reference_capture(copy.deepcopy(native))
+    blocks, _, out_ref = RA.compute_gradcam_ensemble_reference(ref_model, imgs, caps, tokens)
+    want, scale = blocks[1][1], float(blocks[1][1].abs().max())
+    assert scale > 0
+    lavis = lavis.to(dev)
+
+    class A(_Args):
+        fused_xattn = True
+
+    for fused in (True, False):
+        A.fused_xattn = fused
+        lst, empty, out = R.compute_gradcam_ensemble(A, lavis, imgs.to(dev), caps, tokens.to(dev))
+        assert empty == [] and len(lst) == 3 and len(lst[0]) == 2
+        assert lst[1][1].shape == want.shape
+        assert (lst[1][1].cpu() - want).abs().max().item() <= 1e-3 * scale, fused
+        assert torch.allclose(out.cpu(), out_ref, rtol=1e-3, atol=1e-5)
+        other = lst[2][0]
+        assert (other.cpu() - blocks[2][0]).abs().max().item() <= 1e-3 * float(blocks[2][0].abs().max())
+        for xa in cross_attention_modules(lavis):            # the model is handed back untouched
+            assert "forward" not in xa.__dict__ and xa.save_attention is False and xa.attention_map is None
+    # the whole DropOut loop of DRV:564-722 around it
+    g0_o, agg_o, _, _ = O.salience_dropout(
+        lambda x: RA.compute_gradcam_ensemble_reference(ref_model, x, caps, tokens)[0][1][1], imgs, 3, 6, argsort_kind="stable")
+    A.fused_xattn = True
+    g0, agg = R.Inference_BLIP_filteredcaption(A, lavis, tokens.to(dev), imgs, None, ["a", "b"], caps, [["cat", "aeroplane"], ["dog"]], 0)
+    assert (g0.cpu() - g0_o).abs().max().item() <= 1e-3 * float(g0_o.abs().max())
+    assert (agg.cpu() - agg_o).abs().max().item() <= 1e-3 * float(agg_o.abs().max())
+
+
 def test_postprocess_entry_points_match_oracle(dev):
     from oracle import hotpath as O
     from pnp_ovss_b200 import reference_api as R
