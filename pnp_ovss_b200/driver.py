@@ -65,6 +65,8 @@ def get_args_parser():
     parser.add_argument("--synthetic_images", default=8, type=int, help="size of the synthetic dataset")
     parser.add_argument("--synthetic_classes", default=3, type=int, help="classes per image (captioned 'A picture of c1 c2 ...')")
     parser.add_argument("--synthetic_seed", default=1234, type=int)
+    parser.add_argument("--synthetic_gt_size", default=0, type=int,
+                        help="side of the ground-truth / guide images (0 = img_size); the maps are upsampled to it (DRV:435-437)")
     return parser
 
 
@@ -78,6 +80,7 @@ def ddp_setup(args, rank, world_size):
 def synthetic_shard(args, names, n_class, start, end):
     """Images [start, end) of the synthetic dataset (generated per image id, so shards do not depend on world_size)."""
     S = int(args.img_size)
+    G = int(args.synthetic_gt_size) or S
     rng = np.random.default_rng(args.synthetic_seed)
     class_ids_all = [sorted(rng.choice(len(names), size=min(args.synthetic_classes, len(names)), replace=False).tolist())
                      for _ in range(args.synthetic_images)]
@@ -86,8 +89,8 @@ def synthetic_shard(args, names, n_class, start, end):
         g = torch.Generator().manual_seed(args.synthetic_seed + i)
         ids = class_ids_all[i]
         items.append(dict(img_id="syn_%06d" % i, img=torch.randn(3, S, S, generator=g), class_idx=ids,
-                          classes=[names[c] for c in ids], gt=synthetic.gt_labels(args.synthetic_seed + i, S, S, n_class),
-                          guide=synthetic.guide_image(args.synthetic_seed + i, S, S)))
+                          classes=[names[c] for c in ids], gt=synthetic.gt_labels(args.synthetic_seed + i, G, G, n_class),
+                          guide=synthetic.guide_image(args.synthetic_seed + i, G, G)))
     return items
 
 
@@ -110,6 +113,7 @@ def main(rank, world_size, args):
     coco = args.data_type.startswith("coco")
     for b0 in range(0, len(items), args.batch_size):
         batch = items[b0:b0 + args.batch_size]
+        tic_batch = time.perf_counter()
         caps = ["A picture of " + " ".join(it["classes"]) for it in batch]                        # DRV:783
         tokens = tok(caps, padding="max_length", max_length=500).to(dev)                          # DRV:317-319
         imgs = torch.stack([it["img"] for it in batch]).to(dev)
@@ -126,6 +130,9 @@ def main(rank, world_size, args):
             hist0 += h0
         if hall is not None:
             hist_all += hall
+        if rank == 0:   # batch_confusion ends with a host read of its error flag, so the batch is complete here
+            dt = time.perf_counter() - tic_batch
+            print("Time: batch of %d images %.4f seconds (%.2f images/s on this rank)" % (len(batch), dt, len(batch) / dt))
     pipeline.allreduce_hist(hist0)
     pipeline.allreduce_hist(hist_all)
     result = None
