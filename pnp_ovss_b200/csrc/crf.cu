@@ -681,7 +681,12 @@ static const float *run_splat_blur(const LatticeView &L, const float *x, float *
     const int id_blur = L.shared ? kBlurAxisSpatial : kBlurAxisBilateral;
     PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx_splat, gy), 256, 0, st>>>(L, x, va, Cp, normalized));
     float *src = va, *dst = vb;
-    static const bool fuse_pairs = env_mult("PNP_BLUR_FUSE", 1) != 2;  // PNP_BLUR_FUSE=2: one launch per axis (tuning)
+    // Two axes per launch halve the HBM traffic of the blur but re-gather the first axis at both neighbours; measured on
+    // B200 that pays up to ~340-byte rows (21 ch: 0.187 vs 0.232 ms, 81 ch @448: 23.6 vs 27.5 ms per pass) and loses with
+    // 600-byte rows (150 ch: 44.4 vs 38.6 ms), where one launch per axis already runs at the HBM roofline.
+    static const int fuse_mode = env_mult("PNP_BLUR_FUSE", 1);        // 2: never fuse (tuning)
+    static const int fuse_max_cp = env_mult("PNP_BLUR_FUSE_MAX_CP", 112);
+    const bool fuse_pairs = fuse_mode != 2 && Cp <= fuse_max_cp;
     static const int mult2 = env_mult("PNP_GRID_MULT_BLUR2", 8);
     const int gx2 = std::max(1, grid_for((long long)(L.M + 1) * nch, 256, mult2) / div);
     int j = 0;
