@@ -283,3 +283,69 @@ def Inference_BLIP_filteredcaption(args, model_textloc, txt_tokens_filtered, img
 
     g0, agg, _ = salience_dropout_loop(gradcam_fn, imgs, norm, int(args.drop_iter), int(int(args.img_size) / 16))
     return g0, agg
+
+
+# ---------------------------------------------------------------------------------------------- inputs of the path (host side)
+def _gt_png(path):
+    from PIL import Image
+    return np.float32(Image.open(path))
+
+
+def Load_GroundTruth(args, img_ids, coco_thing=None):
+    """DRV:901-928 / DRVC:1095-1125: ground-truth label maps as float32 [H,W] arrays, one per image id.
+
+    voc: VOCdevkit/VOC2012/SegmentationClass/<id>.png with the 255 border folded into background 0; psc: the
+    59-class Context PNGs as they are; ade20k: ADE_val_<id padded to 8>.png; coco_stuff: stuff-164k PNGs with
+    255 -> 0 and every other value + 1 (the reference's per-pixel Python loop, vectorised).  coco_object needs the
+    pycocotools handle the reference passes (`coco_thing`) and paints instances in annotation order, first one wins."""
+    import os
+    dt = args.data_type
+    out = []
+    for img_id in img_ids:
+        if dt == "voc":
+            m = _gt_png(os.path.join("%s/VOCdevkit/VOC2012/SegmentationClass" % args.home_dir, img_id + ".png"))
+            m[m == 255] = 0
+        elif dt == "psc":
+            m = _gt_png(os.path.join("%s/mmsegmentation/data/VOCdevkit/VOC2010/SegmentationClassContext/" % args.home_dir,
+                                     img_id + ".png"))
+        elif dt == "ade20k":
+            m = _gt_png(os.path.join("%s/ADEChallengeData2016/annotations/validation/" % args.home_dir,
+                                     "ADE_val_" + str(img_id).rjust(8, "0") + ".png"))
+        elif dt == "coco_stuff":
+            m = _gt_png(os.path.join("%s/coco_stuff164k/annotations/val2017/" % args.home_dir, "{:012d}".format(int(img_id)) + ".png"))
+            m = np.where(m == 255, np.float32(0), m + np.float32(1)).astype(np.float32)
+        elif dt == "coco_object":
+            if coco_thing is None:
+                raise ValueError("coco_object ground truth needs the pycocotools COCO handle (coco_thing)")
+            info = coco_thing.loadImgs(coco_thing.getImgIds(imgIds=[int(img_id)]))[0]
+            m = np.zeros((info["height"], info["width"]))
+            for ann in coco_thing.loadAnns(coco_thing.getAnnIds(imgIds=info["id"], iscrowd=None)):
+                m[np.logical_and(coco_thing.annToMask(ann), m == 0)] = ann["category_id"]
+        else:
+            raise ValueError("unknown data_type %r" % (dt,))
+        out.append(m)
+    return out
+
+
+def load_OrgImage(args, img_ids, coco_thing=None):
+    """DRV:930-955 / DRVC:1127-1138: the RGB uint8 [H,W,3] images that guide the dense CRF."""
+    import os
+    from PIL import Image
+    dt = args.data_type
+    out = []
+    for img_id in img_ids:
+        if dt in ("voc", "psc"):
+            path = os.path.join("%s/VOCdevkit/VOC2012/JPEGImages/" % args.home_dir, img_id + ".jpg")
+        elif dt == "ade20k":
+            path = os.path.join("%s/ADEChallengeData2016/images/validation/" % args.home_dir,
+                                "ADE_val_" + str(img_id).rjust(8, "0") + ".jpg")
+        elif dt in ("coco_object", "coco_stuff"):
+            if coco_thing is not None:
+                name = coco_thing.loadImgs(coco_thing.getImgIds(imgIds=[int(img_id)]))[0]["file_name"]
+            else:
+                name = "{:012d}.jpg".format(int(img_id))      # val2017 file names are the zero-padded image id
+            path = os.path.join("%s/coco/images/val2017/" % args.home_dir, name)
+        else:
+            raise ValueError("unknown data_type %r" % (dt,))
+        out.append(np.asarray(Image.open(path).convert("RGB")))
+    return out

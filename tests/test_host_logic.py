@@ -164,3 +164,63 @@ def test_calculate_miou_reads_the_reference_layout(tmp_path):
     assert set(want) == set(table)
     iu = np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
     assert table["Mean IoU"] == np.nanmean(iu[hist.sum(1) > 0])
+
+
+def test_ground_truth_and_guide_image_loaders(tmp_path):
+    """Load_GroundTruth / load_OrgImage (DRV:901-955, DRVC:1111-1138) on a miniature copy of the directory layouts."""
+    from PIL import Image
+    from pnp_ovss_b200 import reference_api as R
+    rng = np.random.default_rng(0)
+    home = tmp_path
+
+    def put(rel, arr, mode=None):
+        p = home / rel
+        p.parent.mkdir(parents=True, exist_ok=True)
+        Image.fromarray(arr, mode=mode).save(p)
+
+    gt = rng.integers(0, 21, size=(7, 9)).astype(np.uint8)
+    gt[0, :3] = 255
+    rgb = rng.integers(0, 256, size=(7, 9, 3)).astype(np.uint8)
+    put("VOCdevkit/VOC2012/SegmentationClass/2007_000033.png", gt)
+    put("VOCdevkit/VOC2012/JPEGImages/2007_000033.png", rgb)          # lossless stand-in, renamed below
+    (home / "VOCdevkit/VOC2012/JPEGImages/2007_000033.png").rename(home / "VOCdevkit/VOC2012/JPEGImages/2007_000033.jpg")
+    put("mmsegmentation/data/VOCdevkit/VOC2010/SegmentationClassContext/2007_000033.png", gt)
+    put("ADEChallengeData2016/annotations/validation/ADE_val_00000012.png", gt)
+    put("ADEChallengeData2016/images/validation/ADE_val_00000012.png", rgb)
+    (home / "ADEChallengeData2016/images/validation/ADE_val_00000012.png").rename(
+        home / "ADEChallengeData2016/images/validation/ADE_val_00000012.jpg")
+    put("coco_stuff164k/annotations/val2017/000000000139.png", gt)
+    put("coco/images/val2017/000000000139.png", rgb)
+    (home / "coco/images/val2017/000000000139.png").rename(home / "coco/images/val2017/000000000139.jpg")
+
+    class A:
+        home_dir = str(home)
+        data_type = "voc"
+
+    voc = R.Load_GroundTruth(A, ["2007_000033"])[0]
+    assert voc.dtype == np.float32 and voc.shape == (7, 9)
+    want = gt.astype(np.float32)
+    want[want == 255] = 0
+    assert np.array_equal(voc, want)
+    img = R.load_OrgImage(A, ["2007_000033"])[0]
+    assert img.dtype == np.uint8 and np.array_equal(img, rgb)
+    A.data_type = "psc"
+    assert np.array_equal(R.Load_GroundTruth(A, ["2007_000033"])[0], gt.astype(np.float32))      # 255 kept
+    assert np.array_equal(R.load_OrgImage(A, ["2007_000033"])[0], rgb)
+    A.data_type = "ade20k"
+    assert np.array_equal(R.Load_GroundTruth(A, ["12"])[0], gt.astype(np.float32))
+    assert np.array_equal(R.load_OrgImage(A, ["12"])[0], rgb)
+    A.data_type = "coco_stuff"
+    stuff = R.Load_GroundTruth(A, ["139"])[0]
+    ref = gt.astype(np.float32)
+    for i in range(ref.shape[0]):               # the reference's loop, DRVC:1117-1122
+        for j in range(ref.shape[1]):
+            ref[i][j] = 0 if ref[i][j] == 255 else ref[i][j] + 1
+    assert stuff.dtype == np.float32 and np.array_equal(stuff, ref)
+    assert np.array_equal(R.load_OrgImage(A, ["139"])[0], rgb)
+    A.data_type = "coco_object"
+    with pytest.raises(ValueError):
+        R.Load_GroundTruth(A, ["139"])
+    A.data_type = "nope"
+    with pytest.raises(ValueError):
+        R.load_OrgImage(A, ["1"])
