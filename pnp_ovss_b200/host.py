@@ -104,3 +104,39 @@ def parse_gpt4o_classes(answer, names, keep_above=70):
     if not best:
         best, cls = [0], [names[0]]
     return best, cls, "A picture of " + " ".join(cls)
+
+
+def parse_gpt4o_classes_coco(answer, cat_ids, names, data_type):
+    """The COCO driver's variant (DRVC:855-963): GPT-4o lists COCO *category ids*, which are mapped to positions in
+    `cat_ids` (ids missing from it are dropped); an answer without a probability list keeps every listed class; no
+    answer at all means category 1 ('person').  coco_object walks the whole probability list (and fails like the
+    reference if it is longer than the class list); coco_stuff truncates it to the class list and skips entries whose
+    id does not parse.  Returns (best_class_idx, class names, caption)."""
+    parts = (answer.replace(']\n\n[', '], [').replace('],\n\n[', '], [').replace('], \n[', '], [ ').replace('],\n[', '], [ ')
+             .replace(']\n[', '], [ ').strip("][").split("], ["))
+    cls_list = parts[0].split(",")
+    if len(parts) == 1 and parts[0] == '':
+        cls_list = ["1: 'person'" for _ in range(len(cls_list))]
+        prob_list = [100 for _ in range(len(cls_list))]
+    elif len(parts) == 1:
+        prob_list = [100 for _ in range(len(cls_list))]
+    else:
+        prob_list = [int(p.split(":")[-1].split("%")[0]) for p in parts[1].split(",")]
+    ids = []
+    if data_type == "coco_object":
+        for i, p in enumerate(prob_list):
+            if p > 70:
+                ids.append(int(cls_list[i].split(":")[0]))
+    else:
+        for i, p in enumerate(prob_list[:len(cls_list)]):
+            if p > 70:
+                try:
+                    ids.append(int(cls_list[i].split(":")[0]))
+                except ValueError:
+                    pass
+    pos = {cid: j for j, cid in reversed(list(enumerate(cat_ids)))}   # first position of each id
+    best = [pos[v] for v in ids if v in pos]
+    cls = [names[j] for j in best]
+    if not best:
+        best, cls = [0], [names[0]]
+    return best, cls, "A picture of " + " ".join(cls)

@@ -140,7 +140,7 @@ def _as_device_batch(items, members, dtype, dev):
         if len(members) == items.shape[0]:
             return items
         return items[torch.as_tensor(members, device=dev)].contiguous()
-    return torch.stack([torch.as_tensor(np.ascontiguousarray(items[b])).to(dtype) for b in members]).to(dev)
+    return torch.stack([torch.as_tensor(np.require(items[b], requirements=["C", "W"])).to(dtype) for b in members]).to(dev)
 
 
 _SIDE_STREAMS = {}

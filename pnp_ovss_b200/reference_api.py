@@ -349,3 +349,106 @@ def load_OrgImage(args, img_ids, coco_thing=None):
             raise ValueError("unknown data_type %r" % (dt,))
         out.append(np.asarray(Image.open(path).convert("RGB")))
     return out
+
+
+_GPT4O_CACHE = {}
+
+
+def Load_predicted_classes(args, nms, *rest):
+    """DRV:726-787 and its COCO twin DRVC:855-963 (which takes `cats` after `nms`): appends image `img`'s GPT-4o
+    classes (probability > 70) to the three running lists and returns them.
+
+    VOC/Context/ADE driver:  (args, nms, best_class_idx_list, class_filtered_list, caption_filtered_list,
+                              gt_class_name_list, img_ids, img, pred_path)
+    COCO driver:             (args, nms, cats, best_class_idx_list, class_filtered_list, caption_filtered_list,
+                              gt_class_name_list, img_ids, img, pred_path)
+    The answers are read from {home_dir}/GPT4o_classification/<data_type>_classification_noboundary.json (parsed once
+    per file, not once per image like the reference)."""
+    import json
+    coco = args.data_type in ("coco_object", "coco_stuff")
+    if coco:
+        cats, best_list, class_list, caption_list, _gt_names, img_ids, img = rest[:7]
+    else:
+        best_list, class_list, caption_list, _gt_names, img_ids, img = rest[:6]
+    if args.data_type not in ("voc", "psc", "ade20k", "coco_object", "coco_stuff"):
+        raise ValueError("unknown data_type %r" % (args.data_type,))
+    path = "%s/GPT4o_classification/%s_classification_noboundary.json" % (args.home_dir, args.data_type)
+    if path not in _GPT4O_CACHE:
+        with open(path, "r") as f:
+            _GPT4O_CACHE[path] = json.load(f)
+    answers = _GPT4O_CACHE[path]
+    if coco:
+        answer = answers[str(int(img_ids[img])).rjust(12, "0")]
+        best, cls, caption = host.parse_gpt4o_classes_coco(answer, [c["id"] for c in cats], nms, args.data_type)
+    else:
+        key = "ADE_val_" + img_ids[img].rjust(8, "0") if args.data_type == "ade20k" else img_ids[img]
+        best, cls, caption = host.parse_gpt4o_classes(answers[key], nms)
+    best_list.append(best)
+    class_list.append(cls)
+    caption_list.append(caption)
+    return best_list, class_list, caption_list
+
+
+def save_img_union_attention(*a, max_block_num=None, cam_type="gradcam"):
+    """One batch of the reference's evaluation loop, DRV:290-521, and its COCO twin DRVC:338-640 (same positional
+    arguments after a leading pycocotools handle `coco_thing`):
+
+        (model_textloc, imgs_in, org_img_sizes, args, gt_class_name_list, img_ids, drop_iter, norm_imgs, img_shape, cats,
+         nms, txt_tokens, rank, att_head, max_block_num=None, cam_type="gradcam")
+
+    Reads the guide images, ground truth and GPT-4o class lists the way the reference does (load_OrgImage,
+    Load_GroundTruth, Load_predicted_classes), tokenises the filtered captions, then runs the whole batch on the GPU
+    (pipeline.batch_confusion: DropOut rounds through compute_gradcam_ensemble, token merge, threshold/upsample, blur,
+    CRF, argmax + relabel, confusion matrix) and writes the matrices where the reference writes them
+    (`hist_withfiltered_caption/`, `all_drop_hist_with_filtered_caption/`, float64 .npy named after the first image id).
+    Visualisation side outputs (getAttMap JPEGs, Draw_Segmentation_map) are not produced.  Returns None like the
+    reference; the two matrices are also kept on `save_img_union_attention.last` as int64 CUDA tensors."""
+    from . import pipeline
+    a = list(a)
+    coco_thing = None
+    if not (hasattr(a[0], "module") or hasattr(a[0], "parameters")):      # the COCO driver passes coco_thing first
+        coco_thing = a.pop(0)
+    if len(a) > 14 and max_block_num is None:
+        max_block_num = a[14]
+    (model_textloc, imgs_in, _org_img_sizes, args, gt_class_name_list, img_ids, _drop_iter, norm_imgs, _img_shape, cats, nms,
+     _txt_tokens, _rank, att_head) = a[:14]
+    model = model_textloc.module if hasattr(model_textloc, "module") else model_textloc
+    coco = args.data_type in ("coco_object", "coco_stuff")
+    org_img_list = load_OrgImage(args, img_ids, coco_thing)
+    label_trues = Load_GroundTruth(args, img_ids, coco_thing)
+    best_class_idx_list, class_filtered_list, caption_filtered_list = [], [], []
+    for img in range(len(img_ids)):
+        if coco:
+            Load_predicted_classes(args, nms, cats, best_class_idx_list, class_filtered_list, caption_filtered_list,
+                                   gt_class_name_list, img_ids, img, None)
+        else:
+            Load_predicted_classes(args, nms, best_class_idx_list, class_filtered_list, caption_filtered_list,
+                                   gt_class_name_list, img_ids, img, None)
+    dev = _device()
+    tokens = model.tokenizer(caption_filtered_list, padding="max_length", max_length=500, return_tensors="pt").to(dev)  # DRV:317-319
+    layer, head = int(args.max_att_block_num) - 1, int(args.prune_att_head)
+
+    def gradcam_fn(x):
+        return compute_gradcam_ensemble(args, model, x, caption_filtered_list, tokens)[0][layer][head]
+
+    if coco:
+        dataset_ids = [[int(cats[i]["id"]) for i in best] for best in best_class_idx_list]       # DRVC:549-556
+        n_class = 91 if args.data_type == "coco_object" else 183                                   # DRVC:597-600
+    else:
+        dataset_ids = [[i + 1 for i in best] for best in best_class_idx_list]                      # DRV:468-480
+        n_class = len(cats) + 1                                                                    # DRV:496
+    imgs = _to_dev(imgs_in).clone()
+    norm = _to_dev(norm_imgs).clone() if isinstance(norm_imgs, torch.Tensor) else None
+    hist0, hist_all, _ = pipeline.batch_confusion(
+        gradcam_fn, imgs, tokens.input_ids.tolist(), model.tokenizer.decode, class_filtered_list, dataset_ids, label_trues,
+        org_img_list, drop_iter=int(args.drop_iter), patch_num=int(int(args.img_size) / 16), threshold=float(args.threshold),
+        data_type=args.data_type, mode=args.postprocess, n_class=n_class, coco=coco, norm_imgs=norm)
+    if hist0 is not None:
+        print(img_ids, "miou filtered_caption", metrics_from_hist(hist0.cpu().numpy().astype(np.float64))[0]["Mean IoU"])
+        pipeline.save_hist_npy(hist0, args.save_path, "hist_withfiltered_caption", img_ids[0], max_block_num, att_head)
+    if hist_all is not None:
+        print(img_ids, "miou all_drop_with_filtered caption",
+              metrics_from_hist(hist_all.cpu().numpy().astype(np.float64))[0]["Mean IoU"])
+        pipeline.save_hist_npy(hist_all, args.save_path, "all_drop_hist_with_filtered_caption", img_ids[0], max_block_num, att_head)
+    save_img_union_attention.last = (hist0, hist_all)
+    return None

@@ -150,6 +150,75 @@ def test_live_lavis_protocol_model_is_a_drop_in(dev):
     assert (agg.cpu() - agg_o).abs().max().item() <= 1e-3 * float(agg_o.abs().max())
 
 
+def test_save_img_union_attention_reads_the_reference_layouts(dev, tmp_path):
+    """reference_api.save_img_union_attention (DRV:290-521) on a miniature VOC tree: JPEG/PNG inputs and the GPT-4o
+    answers are read from disk, the batch (three different ground-truth sizes) runs on the GPU, and the .npy matrices
+    land where Calculate_mIoU.py looks for them.  Oracle: oracle.hotpath.batch_confusion on the same inputs."""
+    import json
+    import types
+    from PIL import Image
+    from oracle import hotpath as O
+    from pnp_ovss_b200 import reference_api as R
+    from pnp_ovss_b200.driver import DATASETS
+    nms = DATASETS["voc"][0]
+    cats = [{"id": i + 1, "name": n} for i, n in enumerate(nms)]
+    img_ids = ["2007_000033", "2007_000042", "2007_000061"]
+    sizes = [(40, 56), (64, 48), (50, 50)]
+    answers = ["[15: 'person', 12: 'dog'], [95%, 80%]", "[1: 'aeroplane', 8: 'cat', 3: 'bird'],\n[90%, 60%, 99%]", "[19: 'train'], [75%]"]
+    home = tmp_path / "home"
+    for sub in ("VOCdevkit/VOC2012/SegmentationClass", "VOCdevkit/VOC2012/JPEGImages", "GPT4o_classification"):
+        (home / sub).mkdir(parents=True)
+    gts, guides = [], []
+    for k, (img_id, (H, W)) in enumerate(zip(img_ids, sizes)):
+        gt = synth.gt_labels(300 + k, H, W, 21).astype(np.uint8)
+        gd = synth.guide_image(400 + k, H, W)
+        Image.fromarray(gt).save(home / "VOCdevkit/VOC2012/SegmentationClass" / (img_id + ".png"))
+        Image.fromarray(gd).save(home / "VOCdevkit/VOC2012/JPEGImages" / (img_id + ".png"))
+        (home / "VOCdevkit/VOC2012/JPEGImages" / (img_id + ".png")).rename(home / "VOCdevkit/VOC2012/JPEGImages" / (img_id + ".jpg"))
+        g = gt.astype(np.float32)
+        g[g == 255] = 0
+        gts.append(g)
+        guides.append(gd)
+    json.dump(dict(zip(img_ids, answers)), open(home / "GPT4o_classification/voc_classification_noboundary.json", "w"))
+    tok = synth.SyntheticWordPieceTokenizer()
+    class_lists = [["person", "dog"], ["aeroplane", "bird"], ["train"]]
+    ids = [[15, 12], [1, 3], [19]]
+    caps = ["A picture of " + " ".join(c) for c in class_lists]
+    tokens = tok(caps, padding="max_length", max_length=500)
+    T = max(len(tok.encode(c)) for c in caps)
+    rows = tokens.attention_mask[:, 1:T].float()
+    S, P = 96, 6
+    imgs = torch.randn(3, 3, S, S, generator=torch.Generator().manual_seed(9)).abs()
+
+    class FakeModel:   # stands where BlipITM stands: .tokenizer and .gradcam(...) (the SynthGradcamFn saliency)
+        tokenizer = tok
+        layer = [types.SimpleNamespace(crossattention=types.SimpleNamespace(self=types.SimpleNamespace(heads=12)))] * 12
+
+        def __init__(self):
+            self.fn = synth.SynthGradcamFn(31, 3, T, P)
+
+        def gradcam(self, x, text_input, tokenized_text, layer, head):
+            assert list(text_input) == caps and (layer, head) == (7, 9)
+            return self.fn(x.cpu(), rows).to(x.device), None
+
+    wrap = types.SimpleNamespace(module=FakeModel())
+    args = types.SimpleNamespace(home_dir=str(home), data_type="voc", save_path=str(tmp_path / "out"), drop_iter=3, img_size=S,
+                                 max_att_block_num=8, prune_att_head=9, threshold=0.15, postprocess="blur")
+    out = R.save_img_union_attention(wrap, imgs, None, args, [None] * 3, img_ids, 3, None, None, cats, nms, None, 0, 9, max_block_num=8)
+    assert out is None
+    fn = synth.SynthGradcamFn(31, 3, T, P)
+    with np.errstate(all="ignore"):
+        h0, hagg, _ = O.batch_confusion(lambda x: fn(x, rows), imgs.clone(), tokens.input_ids, tok.decode, class_lists, ids, gts, guides,
+                                        drop_iter=3, patch_num=P, threshold=0.15, data_type="voc", mode="blur", n_class=21,
+                                        coco=False, argsort_kind="stable")
+    got0 = np.load(tmp_path / "out/hist_withfiltered_caption/img_2007_000033_max_blocknum_8_atthead_9.npy")
+    gotagg = np.load(tmp_path / "out/all_drop_hist_with_filtered_caption/img_2007_000033_max_blocknum_8_atthead_9.npy")
+    assert got0.dtype == np.float64 and got0.shape == (21, 21)
+    assert np.array_equal(got0, h0) and np.array_equal(gotagg, hagg)
+    assert got0.sum() == sum(h * w for h, w in sizes)
+    assert torch.equal(R.save_img_union_attention.last[1].cpu(), torch.from_numpy(hagg.astype(np.int64)))
+
+
 def test_postprocess_entry_points_match_oracle(dev):
     from oracle import hotpath as O
     from pnp_ovss_b200 import reference_api as R

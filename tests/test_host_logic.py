@@ -138,7 +138,8 @@ def test_gpt4o_class_list_parser_matches_reference():
     import json
     cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpt4o_golden.json")))
     n = 0
-    for data_type, blob in cases.items():
+    for data_type in ("voc", "psc", "ade20k"):
+        blob = cases[data_type]
         names = ["name%03d" % i for i in range(blob["n_names"])]
         for c in blob["cases"]:
             if "error" in c:
@@ -224,3 +225,33 @@ def test_ground_truth_and_guide_image_loaders(tmp_path):
     A.data_type = "nope"
     with pytest.raises(ValueError):
         R.load_OrgImage(A, ["1"])
+
+
+def test_gpt4o_class_list_parser_coco_variant_matches_reference(tmp_path):
+    """host.parse_gpt4o_classes_coco and reference_api.Load_predicted_classes vs the COCO driver's own function
+    (DRVC:855-963) run on the answers the reference ships (tests/golden/gpt4o_golden.json)."""
+    import json
+    import types
+    from pnp_ovss_b200 import reference_api as R
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpt4o_golden.json")))
+    for data_type in ("coco_object", "coco_stuff"):
+        block = cases[data_type]
+        ids, names = block["cat_ids"], ["name%03d" % i for i in range(block["n_names"])]
+        assert len(block["cases"]) > 100
+        for c in block["cases"]:
+            best, cls, cap = host.parse_gpt4o_classes_coco(c["raw"], ids, names, data_type)
+            assert best == c["best_class_idx"] and cap == c["caption"], c["raw"]
+    # the file-reading entry points, both signatures, on a miniature GPT4o_classification directory
+    d = tmp_path / "GPT4o_classification"
+    d.mkdir()
+    voc_case, coco_case = cases["voc"]["cases"][0], cases["coco_object"]["cases"][0]
+    json.dump({"2007_000033": voc_case["raw"]}, open(d / "voc_classification_noboundary.json", "w"))
+    json.dump({"000000000139": coco_case["raw"]}, open(d / "coco_object_classification_noboundary.json", "w"))
+    args = types.SimpleNamespace(home_dir=str(tmp_path), data_type="voc")
+    b, c, caps = R.Load_predicted_classes(args, ["name%03d" % i for i in range(20)], [], [], [], None, ["2007_000033"], 0, None)
+    assert b == [voc_case["best_class_idx"]] and caps == [voc_case["caption"]] and len(c[0]) == len(b[0])
+    args.data_type = "coco_object"
+    ids = cases["coco_object"]["cat_ids"]
+    b, c, caps = R.Load_predicted_classes(args, ["name%03d" % i for i in range(len(ids))], [{"id": i} for i in ids], [], [], [],
+                                          [None], [139], 0, None)
+    assert b == [coco_case["best_class_idx"]] and caps == [coco_case["caption"]]
