@@ -98,6 +98,12 @@ def main(rank, world_size, args):
     from .blip_itm import BlipITM
     tic = time.perf_counter()
     if world_size > 1:
+        # One process per GPU shares the host's cores: with torch's default of one OpenMP worker per core in EVERY rank the
+        # spinning workers of one rank starve the kernel-launching thread of the others (measured on 2 GPUs at 150 classes:
+        # 2.33 s per batch against 1.58 s with one thread per rank; profiles/diag_two_process_slowdown.sh).  torchrun sets
+        # OMP_NUM_THREADS=1 for the same reason; mp.spawn (DRV:1439) does not.
+        if "OMP_NUM_THREADS" not in os.environ:
+            torch.set_num_threads(1)
         ddp_setup(args, rank, world_size)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
