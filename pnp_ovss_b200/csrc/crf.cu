@@ -324,9 +324,9 @@ __device__ __forceinline__ void argmax_merge(float v, int c, float &best, int &b
 // shuffle rounds, more pixels per warp): 21 channels (nch 6) -> 1 lane x 6 chunks, 32 pixels per warp; 81 channels (nch 21)
 // -> 4 lanes x 6 chunks, 8 pixels (32.3 ms per pass against 36.9 for 7 x 3); 150 channels (nch 38) -> 10 lanes x 4 chunks.
 template <bool kLabels, bool kFast, int CPL>
-__global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldParams P, const float *__restrict__ unary,
-                                                                    float *__restrict__ Q, int32_t *__restrict__ labels, int B, int H,
-                                                                    int W, int C, int Cp, int LPP) {
+__device__ __forceinline__ void meanfield_update_warp_body(const MeanFieldParams &P, const float *__restrict__ unary,
+                                                           float *__restrict__ Q, int32_t *__restrict__ labels, int B, int H, int W,
+                                                           int C, int Cp, int LPP) {
     const int nch = Cp >> 2;
     const int PW = 32 / LPP;                       // pixels per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -482,6 +482,23 @@ __global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldPar
             }
         }
     }
+}
+
+// Two entry points around the same body.  The plain one lets ptxas take the ~105 registers the six-chunk variants want
+// (2 CTAs per SM): fastest for narrow rows (21 channels: 5.35 against 5.52 ms per pass).  The occ3 one caps registers at 80
+// (3 CTAs per SM, ~30 bytes of spills): with rows of 300+ bytes the kernel is latency-bound at 25 % occupancy (ncu: 0.49
+// eligible warps per scheduler) and the third CTA buys 9-18 % (150 ch: 38.2 -> 31.2, 81 ch @448: 31.6 -> 28.9 ms per pass).
+template <bool kLabels, bool kFast, int CPL>
+__global__ void __launch_bounds__(256) meanfield_update_warp_kernel(MeanFieldParams P, const float *__restrict__ unary,
+                                                                    float *__restrict__ Q, int32_t *__restrict__ labels, int B, int H,
+                                                                    int W, int C, int Cp, int LPP) {
+    meanfield_update_warp_body<kLabels, kFast, CPL>(P, unary, Q, labels, B, H, W, C, Cp, LPP);
+}
+template <bool kLabels, bool kFast, int CPL>
+__global__ void __launch_bounds__(256, 3) meanfield_update_warp_occ3_kernel(MeanFieldParams P, const float *__restrict__ unary,
+                                                                            float *__restrict__ Q, int32_t *__restrict__ labels, int B,
+                                                                            int H, int W, int C, int Cp, int LPP) {
+    meanfield_update_warp_body<kLabels, kFast, CPL>(P, unary, Q, labels, B, H, W, C, Cp, LPP);
 }
 
 // ------------------------------------------------------------------------------------------ unary + layout helpers
@@ -787,11 +804,18 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
             if (eff >= best_eff - 1e-9) { best_eff = eff; LPP = lpp; CPL = cpl; }  // ties: more chunks per lane wins (measured)
         }
     }
+    static const int occ3_min_nch = env_mult("PNP_UPDATE_OCC3_MIN_NCH", 12);   // rows of >= 192 bytes
+    const bool occ3 = (CPL == 4 || CPL == 6) && nch_all >= occ3_min_nch;
     const bool warp_path = CPL > 0 && Wimg > 0 && (long long)Himg * Wimg == N && (long long)B * N < (1ll << 31) / Cp;
     const int grid_w = (int)std::max<long long>(
         1, std::min<long long>((long long)B * ((Himg + kTile - 1) / kTile) * ((Wimg + kTile - 1) / kTile), (long long)kNumSMs * mult_update()));
     auto launch_warp = [&](auto labels_tag, auto fast_tag) {
         constexpr bool kL = decltype(labels_tag)::value, kF = decltype(fast_tag)::value;
+        if (occ3) {
+            if (CPL == 4) PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_occ3_kernel<kL, kF, 4><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP));
+            else PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_occ3_kernel<kL, kF, 6><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP));
+            return;
+        }
         switch (CPL) {
             case 1: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 1><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;
             case 2: PNP_LAUNCH(kMeanfieldUpdate, st, meanfield_update_warp_kernel<kL, kF, 2><<<grid_w, 256, 0, st>>>(P, unary, Q, labels, B, Himg, Wimg, C, Cp, LPP)); break;

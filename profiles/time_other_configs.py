@@ -5,7 +5,8 @@ import numpy as np, torch
 from pnp_ovss_b200 import _lib, ops, pipeline, synthetic as synth
 dev = torch.device("cuda:0")
 lib = _lib.load()
-for name, B, C, P, S, with_bg, n in (("voc21@336", 35, 20, 21, 336, True, 21), ("ade150@336", 35, 150, 21, 336, False, 151),
+for name, B, C, P, S, with_bg, n in (("voc21@336", 35, 20, 21, 336, True, 21), ("context59@336", 35, 59, 21, 336, False, 60),
+                                     ("ade150@336", 35, 150, 21, 336, False, 151),
                                      ("coco_obj81@448", 35, 80, 28, 448, True, 91), ("coco_stuff171@512", 8, 171, 21, 512, False, 183)):
     if len(sys.argv) > 1 and name not in sys.argv[1:]:
         continue
