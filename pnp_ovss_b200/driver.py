@@ -12,7 +12,13 @@ Differences from the reference, all forced by what exists offline:
   * ranks take disjoint contiguous shards (host.shard_range) instead of DistributedSampler's padded shuffle, and the
     per-rank confusion matrices are summed with ONE int64 all-reduce over NCCL instead of through .npy files; rank 0
     still writes the matrix where Calculate_mIoU.py looks for it (DRV:513-520) and prints the same statistics.
-`--sort_threshold` is accepted and unused, like in the reference (DRV:85-86 is never read)."""
+`--sort_threshold` is accepted and unused, like in the reference (DRV:85-86 is never read).
+
+With the real inputs on disk the same driver runs them (`main_real`):
+    python -m pnp_ovss_b200.driver --real_data --home_dir /data --data_type voc --bert_vocab vocab.txt \\
+        --checkpoint model_large_retrieval_flickr.pth --img_size 336 --batch_size 35 --max_att_block_num 8 ...
+reads {home_dir}/VOCdevkit/VOC2012/{val.txt,JPEGImages,SegmentationClass} and {home_dir}/GPT4o_classification/*.json in the
+reference's layouts (pnp_ovss_b200/data.py, reference_api.save_img_union_attention)."""
 import argparse
 import os
 import time
@@ -65,6 +71,13 @@ def get_args_parser():
     parser.add_argument("--synthetic_images", default=8, type=int, help="size of the synthetic dataset")
     parser.add_argument("--synthetic_classes", default=3, type=int, help="classes per image (captioned 'A picture of c1 c2 ...')")
     parser.add_argument("--synthetic_seed", default=1234, type=int)
+    parser.add_argument("--real_data", action="store_true",
+                        help="read images / ground truth / GPT-4o class lists from --home_dir in the reference's layouts "
+                             "(needs --bert_vocab; --checkpoint for the real weights) instead of the synthetic stand-ins")
+    parser.add_argument("--bert_vocab", default=None, type=str, help="local bert-base-uncased vocab.txt (the hub is offline)")
+    parser.add_argument("--checkpoint", default=None, type=str, help="LAVIS BlipITM checkpoint (model_large_retrieval_flickr.pth)")
+    parser.add_argument("--coco_annotation_file", default=None, type=str, help="instances_val2017.json (COCO category table)")
+    parser.add_argument("--max_images", default=0, type=int, help="real data: evaluate only the first N images (0 = all)")
     parser.add_argument("--synthetic_gt_size", default=0, type=int,
                         help="side of the ground-truth / guide images (0 = img_size); the maps are upsampled to it (DRV:435-437)")
     return parser
@@ -94,8 +107,73 @@ def synthetic_shard(args, names, n_class, start, end):
     return items
 
 
+def main_real(rank, world_size, args, model=None):
+    """captions_text_loc (DRV:1090-1188) on the real directory layouts: images from disk through the reference's
+    transform, then reference_api.save_img_union_attention per batch (which reads guide images, ground truth and GPT-4o
+    class lists itself and writes the per-batch .npy matrices), the matrices summed on the device and all-reduced."""
+    from . import data
+    from . import reference_api as R
+    from .blip_itm import BlipITM
+    if world_size > 1:
+        if "OMP_NUM_THREADS" not in os.environ:
+            torch.set_num_threads(1)
+        ddp_setup(args, rank, world_size)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    if not args.bert_vocab:
+        raise SystemExit("--real_data needs --bert_vocab (a local bert-base-uncased vocab.txt)")
+    tok = data.init_tokenizer(args.bert_vocab)
+    cats, nms = data.categories(args, args.coco_annotation_file)
+    coco = args.data_type.startswith("coco")
+    coco_thing = None
+    if args.data_type == "coco_object":      # instance masks need pycocotools, like the reference
+        from pycocotools.coco import COCO
+        coco_thing = COCO(args.coco_annotation_file)
+    if model is None:            # BLIP ITM-large; random init unless --checkpoint names the reference's weights
+        torch.manual_seed(4321)
+        model = BlipITM(img_size=int(args.img_size), tokenizer=tok).eval()
+        if args.checkpoint:
+            model.load_lavis_checkpoint(args.checkpoint)
+    model.tokenizer = tok
+    model = model.to(dev).requires_grad_(False)
+    ids = data.image_ids(args)
+    if args.max_images:
+        ids = ids[:int(args.max_images)]
+    n_class = (91 if args.data_type == "coco_object" else 183) if coco else len(cats) + 1
+    hist0 = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
+    hist_all = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
+    wrapped = type("Wrapped", (), {"module": model})()        # the drivers hand a DDP-wrapped model around
+    for img_ids in data.batches(ids, args.batch_size, rank, world_size):
+        loaded = [data.load_model_image(data.image_path(args, i), args.img_size) for i in img_ids]
+        imgs_in = torch.stack([t for t, _, _ in loaded])
+        norm_imgs = torch.from_numpy(np.stack([n for _, n, _ in loaded]))
+        sizes = [s for _, _, s in loaded]
+        head = ([coco_thing] if coco else []) + [wrapped, imgs_in, sizes, args, [None] * len(img_ids), img_ids, args.drop_iter,
+                                                 norm_imgs, None, cats, nms, None, rank, args.prune_att_head]
+        R.save_img_union_attention(*head, max_block_num=args.max_att_block_num)
+        h0, hall = R.save_img_union_attention.last
+        if h0 is not None:
+            hist0 += h0
+        if hall is not None:
+            hist_all += hall
+    pipeline.allreduce_hist(hist0)
+    pipeline.allreduce_hist(hist_all)
+    result = None
+    if rank == 0:
+        scored = hist_all if int(args.drop_iter) > 1 else hist0
+        table, _ = metrics_from_hist(scored.cpu().numpy().astype(np.float64))
+        print("images %d  pixAcc %.4f  mAcc %.4f  mIoU %.4f  fwIoU %.4f" % (
+            len(ids), table["Pixel Accuracy"], table["Mean Accuracy"], table["Mean IoU"], table["Frequency Weighted IoU"]))
+        result = scored.cpu().numpy()
+    if world_size > 1:
+        torch.distributed.destroy_process_group()
+    return result
+
+
 def main(rank, world_size, args):
     from .blip_itm import BlipITM
+    if getattr(args, "real_data", False):
+        return main_real(rank, world_size, args)
     tic = time.perf_counter()
     if world_size > 1:
         # One process per GPU shares the host's cores: with torch's default of one OpenMP worker per core in EVERY rank the
