@@ -26,15 +26,14 @@ import time
 import numpy as np
 import torch
 
-from . import host, pipeline, synthetic
+from . import data, host, pipeline, synthetic
 from .reference_api import metrics_from_hist
 
-DATASETS = {  # data_type -> (class names, n_class for the confusion matrix)   DRV:496, DRVC:597-600
-    "voc": (["aeroplane", "bicycle", "bird", "boat", "bottle", "bus", "car", "cat", "chair", "cow", "table", "dog", "horse",
-             "motorbike", "person", "plant", "sheep", "sofa", "train", "television"], 21),
-    "psc": (["class%02d" % i for i in range(59)], 60),
-    "ade20k": (["class%03d" % i for i in range(150)], 151),
-    "coco_object": (["class%02d" % i for i in range(80)], 91),
+DATASETS = {  # data_type -> (caption class names, n_class for the confusion matrix)   LD:8-92, DRV:496, DRVC:597-600
+    "voc": (list(data.VOC_NAMES), 21),
+    "psc": (list(data.CONTEXT_NAMES), 60),
+    "ade20k": (["".join(n.split(" ")) for n in data.ADE_NAMES], 151),
+    "coco_object": (["class%02d" % i for i in range(80)], 91),       # the COCO names live in the annotation file
     "coco_stuff": (["class%03d" % i for i in range(171)], 183),
 }
 
@@ -111,7 +110,6 @@ def main_real(rank, world_size, args, model=None):
     """captions_text_loc (DRV:1090-1188) on the real directory layouts: images from disk through the reference's
     transform, then reference_api.save_img_union_attention per batch (which reads guide images, ground truth and GPT-4o
     class lists itself and writes the per-batch .npy matrices), the matrices summed on the device and all-reduced."""
-    from . import data
     from . import reference_api as R
     from .blip_itm import BlipITM
     if world_size > 1:
