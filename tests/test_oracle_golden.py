@@ -111,7 +111,8 @@ def _run_driver_case(golden, tag, argsort_kind=None):
 def test_driver_end_to_end_hists(golden):
     """The reference's save_img_union_attention (real code, --postprocess blur) vs the oracle composition."""
     for tag in DRIVER_CASES:
-        h0, hagg, _ = _run_driver_case(golden, tag)
+        with np.errstate(all="ignore"):   # 0/0 channels are reference behaviour (DRV:1151-1152)
+            h0, hagg, _ = _run_driver_case(golden, tag)
         k0, kagg = "drv_%s_hist_withfiltered_caption" % tag, "drv_%s_all_drop_hist_with_filtered_caption" % tag
         if h0 is not None:
             assert np.array_equal(h0, golden[k0]), tag
