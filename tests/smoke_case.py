@@ -65,9 +65,29 @@ def disagreement(h_gpu, h_ref):
     return float(np.abs(h_gpu.astype(np.float64) - h_ref).sum() / 2.0 / max(h_ref.sum(), 1.0))
 
 
+def run_xattn(dev):
+    """Rows a1/a2: the fused cross-attention softmax and softmax-backward/GradCAM kernels on the capture the reference's
+    own code produced (golden gc_* vectors) and against the oracle's restatement."""
+    from oracle import hotpath as O
+    from pnp_ovss_b200 import ops
+    g = np.load(os.path.join(HERE, "golden", "reference_golden.npz"), allow_pickle=False)
+    probs = ops.softmax_fwd(torch.from_numpy(g["gc_scores_scaled"]).to(dev).contiguous(), None, 1.0)
+    err = float(np.abs(probs.cpu().numpy() - g["gc_probs"]).max())
+    assert err <= 1e-6, "softmax differs from the reference capture by %g" % err
+    p, dp = torch.from_numpy(g["gc_probs"]), torch.from_numpy(g["gc_dprobs"])
+    mask = torch.from_numpy(g["gc_mask500"])
+    ds, cam = ops.softmax_bwd_gradcam(p.to(dev), dp.to(dev), mask.to(dev), 9, 0.125, True, True)
+    want = g["gc_head9"]
+    assert np.array_equal(cam.cpu().numpy().reshape(want.shape), want), "GradCAM differs from the reference's"
+    ref_ds = O.softmax_backward(p, dp)
+    assert np.allclose(ds.cpu().numpy(), ref_ds.numpy(), rtol=1e-4, atol=1e-9), "softmax backward differs from the oracle"
+    return err
+
+
 def run(dev):
-    """smoke(): one DropOut + blur + CRF batch on the GPU against the oracle."""
-    report = {}
+    """smoke(): the fused softmax/GradCAM kernels on the reference's capture, then one DropOut + blur + CRF batch on the GPU
+    against the oracle."""
+    report = {"xattn_softmax_max_abs_err": run_xattn(dev)}
     for mode in ("blur", "blur+crf"):
         g0, gagg = run_gpu("voc_r4", mode, dev)
         o0, oagg = run_oracle("voc_r4", mode)
