@@ -5,7 +5,9 @@
   host                      string/table logic of the path (token segments, relabel LUT, sharding)
   reference_api             drop-in replacements with the reference's function names and signatures
   pipeline                  batched on-device composition + the int64 confusion-matrix all-reduce
-  blip_itm                  random-init BLIP ITM-large stand-in whose block-8 cross-attention uses kernel (a)
+  blip_itm                  BLIP ITM-large whose block-8 cross-attention uses kernel (a) (random init offline)
+  lavis_compat              LAVIS checkpoint -> that model; GradCAM from a live LAVIS BlipITM with kernel (a) patched in
+  data, driver              the reference's dataset layouts / transform / tokenizer; driver with the reference's CLI
 
 There is no CPU fallback anywhere in this package (oracle/ is test infrastructure and is never imported here)."""
 from ._lib import PnpError, LIB_PATH  # noqa: F401
