@@ -47,6 +47,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra 3xtf32 measurement reported under `alt_gemm`")
+    ap.add_argument("--cublas-emulation", action="store_true",
+                    help="run torch's own fp32 GEMMs through cuBLAS 12.9's BF16x9 FP32 emulation: re-executes this script with the "
+                         "system libcublas/libcublasLt 12.9 preloaded over the 12.8 that torch bundles (which has no emulation) and "
+                         "CUBLAS_EMULATE_SINGLE_PRECISION=1; reported in `dtype`")
     ap.add_argument("--no-overlap", action="store_true", help="run the round-0 pass on the main stream instead of a side stream")
     ap.add_argument("--classes", default="all20", choices=["all20", "live"],
                     help="all20: every image is captioned with the 20 VOC classes (BASELINE configs[1]); live: classes per image drawn "
@@ -155,6 +159,38 @@ def algorithmic_bytes(kernel, w, stats, T):
 
 
 # --------------------------------------------------------------------------------------------------- our arm
+SYSTEM_CUBLAS = ("/usr/local/cuda/lib64/libcublasLt.so.12", "/usr/local/cuda/lib64/libcublas.so.12")
+
+
+def emulation_env():
+    """Environment in which torch's sgemm calls run as cuBLAS BF16x9 FP32 emulation, or None if the system cuBLAS is absent."""
+    if not all(os.path.exists(p) for p in SYSTEM_CUBLAS):
+        return None
+    env = dict(os.environ)
+    env["LD_PRELOAD"] = ":".join(list(SYSTEM_CUBLAS) + ([env["LD_PRELOAD"]] if env.get("LD_PRELOAD") else []))
+    env["CUBLAS_EMULATE_SINGLE_PRECISION"] = "1"
+    env["PNP_BENCH_CUBLAS_EMULATION"] = "1"
+    return env
+
+
+def run_emulated_child(args):
+    """The same steps in a child process under emulation_env(); returns the `alt_gemm_emulated` object."""
+    env = emulation_env()
+    if env is None:
+        return {"unavailable": "no system cuBLAS >= 12.9 under /usr/local/cuda/lib64"}
+    cmd = [sys.executable, os.path.abspath(__file__), "--cublas-emulation", "--steps", str(args.steps), "--warmup", str(args.warmup),
+           "--no-cpu-baseline", "--no-alt", "--guide", args.guide, "--classes", args.classes]
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    except (subprocess.SubprocessError, IndexError, ValueError) as e:
+        return {"unavailable": "child run failed: %s" % str(e)[:160]}
+    return {"gemm": "torch's own fp32 GEMM calls, executed by cuBLAS 12.9 as BF16x9 FP32 emulation (system libcublas preloaded over "
+                    "torch's bundled 12.8, CUBLAS_EMULATE_SINGLE_PRECISION=1); `python bench.py --cublas-emulation` runs it as the main mode",
+            "value": line["value"], "unit": "images/s", "ms_per_step": line["ms_per_step"],
+            "e2e": (line.get("e2e") or {}).get("value"), "gradcam_max_err_vs_fp64_rel_to_max": line.get("gradcam_err_vs_fp64")}
+
+
 def gradcam_fp64(model, imgs, captions, tokens, layer, head, P):
     """GradCAM of (layer, head) from an fp64 copy of the model with plain torch autograd (MED:228-300, BITM:399-433
     restated in torch; no custom kernel) -- the ground truth the GEMM-precision modes are judged against."""
@@ -337,10 +373,24 @@ def run_ours(args):
                "value": world * B * args.steps / (alt_ms / 1e3), "unit": "images/s", "ms_per_step": alt_ms / args.steps,
                "gradcam_max_dev_vs_fp32_rel_to_max": dev_rel, "gradcam_max_err_vs_fp64_rel_to_max": vs_fp64}
 
+    emulated = bool(os.environ.get("PNP_BENCH_CUBLAS_EMULATION"))
+    err_fp64 = None
+    if emulated and rank == 0:  # this process IS the emulated run: how far is its GradCAM from the fp64 pass?
+        probe = imgs_src[:4].contiguous()
+        tok4 = w["tok"](w["captions"][:4], padding="max_length", max_length=500).to(dev)
+        cam = model.gradcam(probe, w["captions"][:4], tok4, layer=w["layer"], head=w["head"])[0]
+        truth = gradcam_fp64(model, probe, w["captions"][:4], tok4, w["layer"], w["head"], w["P"])
+        err_fp64 = float(((cam.double() - truth).abs().max() / truth.abs().max()).item())
+        del truth
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    alt_emulated = None
+    if args.gemm == "fp32" and not args.no_alt and not emulated and world == 1:
+        alt_emulated = run_emulated_child(args)
 
     peaks = {}
     try:
@@ -371,7 +421,8 @@ def run_ours(args):
                   for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])}
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "3xtf32": "f32 (ViT GEMMs as 3 error-compensated TF32 products)"}.get(args.gemm, args.gemm), "data": "synthetic",
+            "vs_baseline": None, "dtype": ("f32 (cuBLAS 12.9 BF16x9 FP32 emulation of torch's sgemm calls)" if emulated else
+                                     {"fp32": "f32", "3xtf32": "f32 (ViT GEMMs as 3 error-compensated TF32 products)"}.get(args.gemm, args.gemm)), "data": "synthetic",
             "config": {"workload": w["name"], "images_per_step_per_gpu": B, "img_size": w["S"], "patch_grid": w["P"],
                        "classes": w["C"] if args.classes == "all20" else "live (mean %.2f per image)" % (sum(len(c) for c in w["class_lists"]) / B),
                        "channels": w["C"] + 1 if args.classes == "all20" else "classes + background", "drop_iter": w["drop_iter"], "block": w["layer"] + 1,
@@ -382,7 +433,8 @@ def run_ours(args):
                        "M_s": stats.get("M_s"), "M_b_per_batch": stats.get("M_b"),
                        "l2": "per-step working set (>3 GB) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "alt_gemm": alt,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "alt_gemm": alt, "alt_gemm_emulated": alt_emulated,
+            "gradcam_err_vs_fp64": err_fp64,
             "custom_kernels": {"ms_per_step": round(sum(v[0] for v in per_kernel.values()), 3),
                                "images_per_s": round(B / (sum(v[0] for v in per_kernel.values()) * 1e-3), 1),
                                "note": "sum of the in-situ event times of every pnp:: kernel in one (warm-up) step; the rest of "
@@ -455,6 +507,11 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    if a.cublas_emulation and a.impl == "ours" and not os.environ.get("PNP_BENCH_CUBLAS_EMULATION"):
+        env = emulation_env()
+        if env is None:
+            raise SystemExit("bench.py --cublas-emulation: no system cuBLAS >= 12.9 under /usr/local/cuda/lib64")
+        os.execve(sys.executable, [sys.executable] + sys.argv, env)
     if a.impl == "reference":
         run_reference(a)
     else:
