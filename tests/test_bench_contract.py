@@ -56,3 +56,20 @@ def test_reference_arm_sample_is_bounded():
     for steps, warmup in ((3, 3), (10, 3), (1, 0), (20, 5)):
         n = max(1, min(4, int(160.0 / (max(steps + warmup, 1) * 12.0))))
         assert 1 <= n <= 4
+
+
+def test_cublas_emulation_environment(monkeypatch):
+    """bench.py --cublas-emulation: the system cuBLAS 12.9 pair is preloaded ahead of anything already there and the
+    emulation switch is set; without the libraries the mode reports itself unavailable instead of failing."""
+    import bench
+    monkeypatch.setenv("LD_PRELOAD", "/opt/other.so")
+    env = bench.emulation_env()
+    if all(os.path.exists(p) for p in bench.SYSTEM_CUBLAS):
+        assert env["LD_PRELOAD"].split(":") == list(bench.SYSTEM_CUBLAS) + ["/opt/other.so"]
+        assert env["CUBLAS_EMULATE_SINGLE_PRECISION"] == "1" and env["PNP_BENCH_CUBLAS_EMULATION"] == "1"
+    else:
+        assert env is None
+    monkeypatch.setattr(bench, "SYSTEM_CUBLAS", ("/nonexistent/libcublasLt.so.12", "/nonexistent/libcublas.so.12"))
+    assert bench.emulation_env() is None
+    args = bench.parse_args.__globals__["argparse"].Namespace(steps=1, warmup=3, guide="natural", classes="all20")
+    assert "unavailable" in bench.run_emulated_child(args)
