@@ -158,7 +158,7 @@ def _fused_forward(xa, capture):
         probs = FusedXattnSoftmax.apply(scores.float(), key_mask, 1.0 / math.sqrt(q.shape[-1]), capture)  # MED:267-274
         xa.save_attention_map(probs)                                                            # MED:281
         probs.register_hook(xa.save_attn_gradients)                                             # MED:283
-        dropped = xa.dropout(probs)
+        dropped = xa.dropout(probs if probs.dtype == v.dtype else probs.to(v.dtype))   # fp16/bf16 models: kernel (a) is fp32
         if head_mask is not None:
             dropped = dropped * head_mask
         ctx = torch.matmul(dropped, v).permute(0, 2, 1, 3).contiguous()                         # MED:300-304
