@@ -341,18 +341,20 @@ __global__ void __launch_bounds__(kTCols *kTGroups) blur_vertical_tma_kernel(con
 
 constexpr int kHRows = 32;    // rows per CTA in pass H (one per lane)
 constexpr int kHCols = 16;    // output columns per thread per sweep
-constexpr int kHGroups = 16;  // column groups per CTA (32 * 16 = 512 threads)
+constexpr int kHGroupsMax = 32;  // column groups (warps) per CTA: as many as one sweep over the tile needs, up to 1024 threads
 
 // pass H: out[y][x] = sum_j w[j] * in[y][reflect(x + j - lw)], + min/max of the result
-__global__ void __launch_bounds__(kHRows *kHGroups) blur_horizontal_kernel(const float *__restrict__ in, float *__restrict__ out,
+template <int kMaxWarps, int kMinCtas>
+__global__ void __launch_bounds__(kHRows *kMaxWarps, kMinCtas) blur_horizontal_kernel(const float *__restrict__ in, float *__restrict__ out,
                                                                            const float *__restrict__ weights,
                                                                            unsigned *__restrict__ mm_keys, int H, int W, int lw,
                                                                            int tile_cols, int pitch, int n_w_padded) {
     extern __shared__ float smem[];
     float *s_w = smem;                                   // [n_w_padded]
     float *s_in = smem + n_w_padded;                     // [kHRows][pitch]
-    float *s_out = s_in + kHRows * pitch;                // [kHRows][kHGroups*kHCols + 1]
-    constexpr int kOutPitch = kHGroups * kHCols + 1;
+    const int n_groups = blockDim.x >> 5;                // warps of this CTA, one column group of kHCols outputs each
+    float *s_out = s_in + kHRows * pitch;                // [kHRows][n_groups*kHCols + 1]
+    const int kOutPitch = n_groups * kHCols + 1;
     __shared__ unsigned s_mm[2];
     const int map = blockIdx.z;
     const int y_base = blockIdx.y * kHRows;
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(kHRows *kHGroups) blur_horizontal_kernel(const
     const int gy = y_base + lane;
     float mn = INFINITY, mx = -INFINITY;
     bool has_nan = false;
-    for (int sweep = 0; sweep < cols_here; sweep += kHGroups * kHCols) {
+    for (int sweep = 0; sweep < cols_here; sweep += n_groups * kHCols) {
         const int xl = sweep + grp * kHCols;
         if (xl < cols_here) {
             float acc[kHCols];
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(kHRows *kHGroups) blur_horizontal_kernel(const
         }
         __syncthreads();
         // coalesced write-back of this sweep's [kHRows][<=256] block, tracking min/max
-        const int sweep_cols = min(kHGroups * kHCols, cols_here - sweep);
+        const int sweep_cols = min(n_groups * kHCols, cols_here - sweep);
         for (int i = threadIdx.x; i < kHRows * sweep_cols; i += blockDim.x) {
             int r = i / sweep_cols, c = i - r * sweep_cols;
             if (y_base + r < H) {
@@ -486,7 +488,7 @@ extern "C" int pnp_threshold_upsample(const float *class_maps, float *out, void 
 
 namespace {
 struct BlurPlan {
-    int lw, n_w_padded, tile_rows, tile_cols, pitch, tile_rows_tma;
+    int lw, n_w_padded, tile_rows, tile_cols, pitch, tile_rows_tma, h_groups;
     size_t smem_v, smem_h, smem_v_tma;
     size_t off_keys, off_tmp, total;
 };
@@ -511,12 +513,21 @@ bool make_blur_plan(int n_maps, int H, int W, double sigma, BlurPlan &p) {
         p.smem_v_tma = (p.n_w_padded + (p.tile_rows_tma + fixed_rows) * kTCols) * sizeof(float);
     }
     // pass H: full rows if they fit, else column tiles
-    size_t out_floats = (size_t)kHRows * (kHGroups * kHCols + 1);
+    // one warp per 16-column group so that a tile is one sweep (336 columns: 21 warps instead of 16 + 5 in two sweeps);
+    // PNP_BLUR_H_GROUPS caps the warps per CTA (16 = the former fixed shape)
+    static const int groups_cap = std::min(kHGroupsMax, std::max(1, getenv("PNP_BLUR_H_GROUPS") ? atoi(getenv("PNP_BLUR_H_GROUPS")) : kHGroupsMax));
+    size_t out_floats = (size_t)kHRows * (groups_cap * kHCols + 1);  // worst case while the tile width is being chosen
     size_t max_pitch = (kSmemBudget - (p.n_w_padded + out_floats) * sizeof(float)) / (kHRows * sizeof(float));
     size_t fixed_cols = 2 * (size_t)p.lw + kTapPad + kHCols;
     if (max_pitch <= fixed_cols + kHCols + 1) return false;
     p.tile_cols = (int)std::min<size_t>((size_t)W, (max_pitch - 1 - fixed_cols) / kHCols * kHCols);
     p.pitch = (int)(p.tile_cols + fixed_cols) | 1;
+    {   // warps per CTA: spread the tile's column groups evenly over the fewest sweeps
+        const int n_col_groups = (p.tile_cols + kHCols - 1) / kHCols;
+        const int sweeps = (n_col_groups + groups_cap - 1) / groups_cap;
+        p.h_groups = (n_col_groups + sweeps - 1) / sweeps;
+    }
+    out_floats = (size_t)kHRows * (p.h_groups * kHCols + 1);
     p.smem_h = (p.n_w_padded + (size_t)kHRows * p.pitch + out_floats) * sizeof(float);
     p.off_keys = align_up(p.n_w_padded * sizeof(float), 256);
     p.off_tmp = p.off_keys + align_up((size_t)n_maps * 2 * sizeof(unsigned), 256);
@@ -544,7 +555,10 @@ extern "C" int pnp_gaussian_blur(const float *in, float *out, float *minmax, voi
     float *tmp = reinterpret_cast<float *>(ws + p.off_tmp);
     cudaError_t e = cudaFuncSetAttribute(blur_vertical_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_v);
     if (e != cudaSuccess) return cuda_err(e);
-    e = cudaFuncSetAttribute(blur_horizontal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_h);
+    // up to 21 warps (tiles of <= 336 columns) two CTAs share an SM: cap the registers for that; wider tiles own the SM
+    const bool h_pair = p.h_groups <= 21 && 2 * (p.smem_h + 1024) <= 227 * 1024;
+    e = h_pair ? cudaFuncSetAttribute(blur_horizontal_kernel<21, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_h)
+               : cudaFuncSetAttribute(blur_horizontal_kernel<kHGroupsMax, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_h);
     if (e != cudaSuccess) return cuda_err(e);
     blur_prologue_kernel<<<1, 256, 0, st>>>(weights, keys, n_maps, p.lw, p.n_w_padded, sigma);
     const bool tma_ok = p.tile_rows_tma > 0 && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
@@ -557,8 +571,13 @@ extern "C" int pnp_gaussian_blur(const float *in, float *out, float *minmax, voi
         PNP_LAUNCH(kBlurVertical, st, blur_vertical_kernel<<<dim3(ceil_div(W, kVCols), ceil_div(H, p.tile_rows), n_maps), kVCols * kVGroups, p.smem_v, st>>>(
             in, tmp, weights, H, W, p.lw, p.tile_rows, p.n_w_padded));
     }
-    PNP_LAUNCH(kBlurHorizontal, st, blur_horizontal_kernel<<<dim3(ceil_div(W, p.tile_cols), ceil_div(H, kHRows), n_maps), kHRows * kHGroups, p.smem_h, st>>>(
-        tmp, out, weights, keys, H, W, p.lw, p.tile_cols, p.pitch, p.n_w_padded));
+    const dim3 h_grid(ceil_div(W, p.tile_cols), ceil_div(H, kHRows), n_maps);
+    if (h_pair)
+        PNP_LAUNCH(kBlurHorizontal, st, (blur_horizontal_kernel<21, 2><<<h_grid, kHRows * p.h_groups, p.smem_h, st>>>(
+            tmp, out, weights, keys, H, W, p.lw, p.tile_cols, p.pitch, p.n_w_padded)));
+    else
+        PNP_LAUNCH(kBlurHorizontal, st, (blur_horizontal_kernel<kHGroupsMax, 1><<<h_grid, kHRows * p.h_groups, p.smem_h, st>>>(
+            tmp, out, weights, keys, H, W, p.lw, p.tile_cols, p.pitch, p.n_w_padded)));
     blur_minmax_decode_kernel<<<ceil_div(n_maps, 256), 256, 0, st>>>(keys, minmax, n_maps);
     if (normalize) {
         long long total = (long long)n_maps * H * W;
