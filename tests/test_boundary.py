@@ -101,3 +101,29 @@ def test_header_is_plain_c():
                        capture_output=True, text=True)
     os.unlink(f.name)
     assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+
+
+def test_ctypes_lattice_struct_matches_the_header_layout(tmp_path):
+    """struct pnp_lattice crosses the boundary by pointer: the ctypes mirror in _lib.py must have the field order, offsets
+    and size the C compiler gives the header's struct."""
+    import subprocess
+    from pnp_ovss_b200 import _lib
+    names = [n for n, _ in _lib.Lattice._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "pnp_ovss_b200.h"\nint main(void) {\n'
+                   '  printf("%zu\\n", sizeof(struct pnp_lattice));\n' +
+                   "".join('  printf("%s %%zu\\n", offsetof(struct pnp_lattice, %s));\n' % (n, n) for n in names) +
+                   "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr          # fails to compile if _lib.py names a field the header lacks
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout.split("\n")
+    assert int(out[0]) == ctypes.sizeof(_lib.Lattice)
+    for line, name in zip(out[1:], names):
+        field, off = line.split()
+        assert field == name and int(off) == getattr(_lib.Lattice, name).offset, line
+    # and the header has no field the mirror lacks
+    body = re.search(r"struct pnp_lattice\s*\{(.*?)\}\s*pnp_lattice\s*;", open(HEADER).read(), re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    declared = re.findall(r"(\w+)\s*;", body)
+    assert declared == names, (declared, names)
