@@ -127,3 +127,37 @@ def test_ctypes_lattice_struct_matches_the_header_layout(tmp_path):
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     declared = re.findall(r"(\w+)\s*;", body)
     assert declared == names, (declared, names)
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of the header, parsed as C: parameter count and the class of each parameter (pointer / integer /
+    float / double / size_t) must agree with the argtypes in _lib.SIGNATURES, and so must the return type."""
+    from pnp_ovss_b200 import _lib
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    protos = re.findall(r"^\s*(?:PNP_API\s+)?([A-Za-z_][\w\s\*]*?)\b(pnp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.M)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def c_class(decl):
+        decl = decl.strip()
+        if "*" in decl or "pnp_stream_t" in decl:
+            return "ptr"
+        base = re.sub(r"\b\w+$", "", decl).strip() if re.search(r"\w+\s+\w+$", decl) else decl   # drop the parameter name
+        base = base.replace("const", "").strip()
+        return {"int": "int", "int32_t": "int", "unsigned": "int", "unsigned int": "int", "long long": "i64", "int64_t": "i64",
+                "size_t": "size", "float": "float", "double": "double", "void": "void"}[base]
+
+    def py_class(t):
+        if t is None:
+            return "void"
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(t, "contents") or issubclass(t, ctypes._Pointer):
+            return "ptr"
+        return {ctypes.c_int: "int", ctypes.c_uint: "int", ctypes.c_longlong: "i64", ctypes.c_size_t: "size",
+                ctypes.c_float: "float", ctypes.c_double: "double"}[t]
+
+    for ret, name, params in protos:
+        restype, argtypes = _lib.SIGNATURES[name]
+        plist = [] if params.strip() in ("", "void") else [p for p in params.split(",")]
+        assert len(plist) == len(argtypes), "%s: header has %d parameters, ctypes %d" % (name, len(plist), len(argtypes))
+        for i, (p, t) in enumerate(zip(plist, argtypes)):
+            assert c_class(p) == py_class(t), "%s parameter %d: header '%s', ctypes %s" % (name, i, p.strip(), t)
+        assert c_class(ret + " x") == py_class(restype), "%s return type" % name
