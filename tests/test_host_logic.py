@@ -255,3 +255,27 @@ def test_gpt4o_class_list_parser_coco_variant_matches_reference(tmp_path):
     b, c, caps = R.Load_predicted_classes(args, ["name%03d" % i for i in range(len(ids))], [{"id": i} for i in ids], [], [], [],
                                           [None], [139], 0, None)
     assert b == [coco_case["best_class_idx"]] and caps == [coco_case["caption"]]
+
+
+def test_token_segments_property_random_wordpiece_shapes():
+    """For arbitrary captions (1..9 words of 1..4 pieces each) the host's segment table, applied the way pnp_token_merge
+    applies it, reproduces the oracle's restatement of the reference loop bit for bit -- including the cases where the
+    number of pieces happens to equal the number of classes (rows taken verbatim) and a split word comes last (summed)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=4), min_size=1, max_size=9), st.integers(min_value=0, max_value=2 ** 31 - 1))
+    def check(pieces_per_word, seed):
+        toks = []
+        for w, n in enumerate(pieces_per_word):
+            toks.append("w%d" % w)
+            toks.extend("##p%d" % k for k in range(n - 1))
+        n_classes = len(pieces_per_word)
+        rng = np.random.default_rng(seed)
+        g = rng.random((3 + len(toks) + 1, 3, 3)).astype(np.float32)      # rows: "a picture of", the pieces, [SEP]
+        want = O.mean_over_filtered_label_tokens(toks, torch.from_numpy(g), n_classes).numpy()
+        segs = host.build_token_segments(toks, n_classes)
+        assert len(segs) == n_classes
+        assert np.array_equal(_emulate_merge(g, segs), want)
+
+    check()
