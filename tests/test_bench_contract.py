@@ -73,3 +73,21 @@ def test_cublas_emulation_environment(monkeypatch):
     assert bench.emulation_env() is None
     args = bench.parse_args.__globals__["argparse"].Namespace(steps=1, warmup=3, guide="natural", classes="all20")
     assert "unavailable" in bench.run_emulated_child(args)
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` end to end on the host CPU (one image, one step): the JSON line the driver parses."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--ref-images", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"] == bench.WORKLOAD["name"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
