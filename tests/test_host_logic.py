@@ -279,3 +279,59 @@ def test_token_segments_property_random_wordpiece_shapes():
         assert np.array_equal(_emulate_merge(g, segs), want)
 
     check()
+
+
+def test_save_img_union_attention_coco_signature_host_glue(tmp_path, monkeypatch):
+    """The COCO form of save_img_union_attention (DRVC:338: leading coco_thing, `cats` as a list of dicts with sparse ids,
+    183-class matrix, round-0 pass skipped at drop_iter >= 3) with the GPU part stubbed out: what reaches
+    pipeline.batch_confusion and what lands on disk."""
+    import json
+    import types
+    from PIL import Image
+    from pnp_ovss_b200 import pipeline
+    from pnp_ovss_b200 import reference_api as R
+    rng = np.random.default_rng(1)
+    home = tmp_path / "home"
+    (home / "coco_stuff164k/annotations/val2017").mkdir(parents=True)
+    (home / "coco/images/val2017").mkdir(parents=True)
+    (home / "GPT4o_classification").mkdir()
+    gt = rng.integers(0, 171, size=(9, 11)).astype(np.uint8)
+    gt[0, 0] = 255
+    Image.fromarray(gt).save(home / "coco_stuff164k/annotations/val2017/000000000139.png")
+    rgb = rng.integers(0, 256, size=(9, 11, 3)).astype(np.uint8)
+    Image.fromarray(rgb).save(home / "coco/images/val2017/000000000139.png")
+    (home / "coco/images/val2017/000000000139.png").rename(home / "coco/images/val2017/000000000139.jpg")
+    json.dump({"000000000139": "[1: 'person', 18: 'dog', 93: 'branch'], [95%, 40%, 88%]"},
+              open(home / "GPT4o_classification/coco_stuff_classification_noboundary.json", "w"))
+    cat_ids = [1, 2, 18, 92, 93]
+    cats = [{"id": i, "name": "n%d" % i} for i in cat_ids]
+    nms = ["person", "bicycle", "dog", "banner", "branch"]
+    tok = synth.SyntheticWordPieceTokenizer()
+
+    class Model:
+        tokenizer = tok
+    seen = {}
+
+    def fake_batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_ids, gts, guides, **kw):
+        seen.update(kw, class_lists=class_lists, dataset_ids=dataset_ids, gts=gts, guides=guides, imgs=imgs, token_ids=token_ids)
+        return None, torch.full((kw["n_class"], kw["n_class"]), 2, dtype=torch.int64), None
+
+    monkeypatch.setattr(R, "_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(pipeline, "batch_confusion", fake_batch_confusion)
+    args = types.SimpleNamespace(home_dir=str(home), data_type="coco_stuff", save_path=str(tmp_path / "out"), drop_iter=4, img_size=32,
+                                 max_att_block_num=8, prune_att_head="9", threshold=0.15, postprocess="blur+crf")
+    imgs = torch.zeros(1, 3, 32, 32)
+    coco_thing = types.SimpleNamespace(loadImgs=lambda ids: [{"file_name": "000000000139.jpg"}], getImgIds=lambda imgIds: imgIds)
+    out = R.save_img_union_attention(coco_thing,
+                                     types.SimpleNamespace(module=Model()), imgs, None, args, [None], [139], 4, None, None, cats,
+                                     nms, None, 0, "9", 8)
+    assert out is None
+    assert seen["class_lists"] == [["person", "branch"]] and seen["dataset_ids"] == [[1, 93]]     # category ids, not positions
+    assert seen["n_class"] == 183 and seen["coco"] is True and seen["data_type"] == "coco_stuff"
+    assert seen["drop_iter"] == 4 and seen["patch_num"] == 2 and seen["mode"] == "blur+crf"
+    want_gt = np.where(gt == 255, 0, gt.astype(np.float32) + 1).astype(np.float32)              # DRVC:1117-1122
+    assert np.array_equal(seen["gts"][0], want_gt) and np.array_equal(seen["guides"][0], rgb)
+    assert len(seen["token_ids"]) == 1 and len(seen["token_ids"][0]) == 500
+    saved = np.load(tmp_path / "out/all_drop_hist_with_filtered_caption/img_139_max_blocknum_8_atthead_9.npy")
+    assert saved.shape == (183, 183) and saved.dtype == np.float64 and saved.sum() == 2 * 183 * 183
+    assert not (tmp_path / "out/hist_withfiltered_caption").exists() or not list((tmp_path / "out/hist_withfiltered_caption").iterdir())
