@@ -208,14 +208,37 @@ int pnp_confusion_accumulate(const int32_t *labels, const float *gt, const int32
                              pnp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * (f)1 model pass (BITM:386-404 drives VIT:93-119 / MED:201-228): operand preparation for
+ *      fp32-grade GEMMs on the TF32 tensor cores.  The dense contractions themselves stay torch's (cuBLAS);
+ *      y = x W^T runs as ONE TF32 GEMM of depth 3K on [x_hi | x_lo | x_hi] x [W_hi | W_hi | W_lo]^T, where
+ *      hi = the operand rounded to TF32 (10 explicit mantissa bits) and lo = operand - hi (exact in fp32).
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* out3[m, 0:K] = hi(x[m,:]), out3[m, K:2K] = x - hi, out3[m, 2K:3K] = hi.  x [M,K], out3 [M,3K]; K % 4 == 0,
+ * 16-byte aligned pointers. */
+int pnp_tf32_split3(const float *x, float *out3, long long M, int K, pnp_stream_t stream);
+/* Same split of GELU(x + bias) (exact erf form, VIT:35-40 Mlp / nn.GELU); bias [K] or NULL. */
+int pnp_gelu_tf32_split3(const float *x, const float *bias, float *out3, long long M, int K,
+                         pnp_stream_t stream);
+/* y = LayerNorm(x') * gamma + beta over the last dimension (biased variance, eps inside the sqrt: nn.LayerNorm
+ * of VIT:70-71), where x' = x, or x + residual (+ residual_bias [K]) when residual != NULL -- in which case
+ * x' is also written to x_out when x_out != NULL (x_out may alias x).  y goes to out3 as the [hi | lo | hi]
+ * split ([M,3K]) and/or to out1 unsplit ([M,K]); at least one of them.  K % 4 == 0, K <= 2048. */
+int pnp_layernorm_tf32_split3(const float *x, const float *residual, const float *residual_bias, float *x_out,
+                              const float *gamma, const float *beta, float eps, float *out3, float *out1,
+                              long long M, int K, pnp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------
  * In-situ kernel timing for bench.py's roofline (the one piece of process-global state in the library):
  * between start and stop, every launch of a kernel class whose bit is set in kernel_mask is bracketed by
  * CUDA events recorded on the launch's own stream.  Kernel ids: 1 softmax_fwd, 2 softmax_bwd_gradcam,
  * 3 token_merge, 4 salience_dropout_round, 5 threshold_prep, 6 upsample_write, 7 blur_vertical,
  * 8 blur_horizontal, 9 blur_normalize, 10 lattice_build (all of it), 11 crf_unary, 12 crf_splat_bilateral,
  * 13 crf_blur_axis_bilateral, 14 crf_meanfield_update, 15 argmax_channels, 16 confusion, 17 crf_splat_spatial,
- * 18 crf_blur_axis_spatial.
+ * 18 crf_blur_axis_spatial, 19 tf32_split3, 20 gelu_tf32_split3, 21 layernorm_tf32_split3, 22 lowrank_blur,
+ * 23 lowrank_unary, 24 background_blur (pnp_profile_kernel_name() is authoritative).
  * ---------------------------------------------------------------------------------------------------- */
+int pnp_profile_num_kernels(void); /* ids are 1 .. pnp_profile_num_kernels()-1 */
 int pnp_profile_start(unsigned kernel_mask);
 /* Waits for the recorded events; total_ms[id] / n_launches[id] for id < n_ids (host arrays). */
 int pnp_profile_stop(float *total_ms, int *n_launches, int n_ids);

@@ -41,7 +41,7 @@ class ReferenceCrossAttention(nn.Module):
         B, L, D = x.shape
         return x.view(B, L, self.heads, D // self.heads).permute(0, 2, 1, 3)
 
-    def forward(self, hidden, enc, enc_mask=None):
+    def forward(self, hidden, enc, enc_mask=None, kv=None):
         q, k, v = self._split(self.query(hidden)), self._split(self.key(enc)), self._split(self.value(enc))
         scores = torch.matmul(q, k.transpose(-1, -2))          # MED:228
         scores = scores / math.sqrt(q.shape[-1])               # MED:267
@@ -96,12 +96,17 @@ def _post_one(args):
 
 
 def reference_batch_confusion(model, imgs, captions, tokens, decode, class_lists, dataset_ids, gts, guides, *, drop_iter,
-                              layer, head, threshold, data_type, mode, n_class, coco=False, pool=None, timings=None):
-    """One batch of save_img_union_attention on the CPU (DRV:290-521).  Images' post-processing is fanned over
-    `pool` (a multiprocessing pool) when given -- the reference itself does it in one Python loop."""
+                              layer, head, threshold, data_type, mode, n_class, coco=False, pool=None, timings=None, device=None):
+    """One batch of save_img_union_attention on the CPU (DRV:290-521).  Images' post-processing -- every (image, pass) job of
+    the batch in ONE map call -- is fanned over `pool` (a multiprocessing pool) when given; the reference itself does it in
+    one Python loop.  device: run the model pass on that CUDA device the reference's way (imgs .to(rank) at DRV:608, the
+    12x12 GradCAM maps .cpu()-ed one by one at BITM:431-433); everything after it stays on the CPU like in the reference."""
     P = model.patch_num
 
     def gradcam_fn(x):
+        if device is not None:
+            tk = type(tokens)(tokens.input_ids.to(device), tokens.attention_mask.to(device))
+            return compute_gradcam_ensemble_reference(model, x.to(device), captions, tk)[0][layer][head]
         return compute_gradcam_ensemble_reference(model, x, captions, tokens)[0][layer][head]
 
     import time
@@ -114,16 +119,14 @@ def reference_batch_confusion(model, imgs, captions, tokens, decode, class_lists
         passes.append((g0, True))
     if agg is not None:
         passes.append((agg, coco))
-    hists = []
+    jobs = []
     for gmaps, rescale in passes:
-        jobs = []
         for b in range(B):
             toks = O.token_strings(tokens.input_ids[b], decode)
             cm = O.mean_over_filtered_label_tokens(toks, gmaps[b], len(class_lists[b]))
             jobs.append((cm.numpy().copy(), threshold, tuple(gts[b].shape), guides[b], data_type, dataset_ids[b], mode, rescale))
-        preds = pool.map(_post_one, jobs) if pool is not None else [_post_one(j) for j in jobs]
-        _, hist = O.scores(gts, preds, n_class)
-        hists.append(hist)
+    preds = pool.map(_post_one, jobs, chunksize=1) if pool is not None else [_post_one(j) for j in jobs]
+    hists = [O.scores(gts, preds[i * B:(i + 1) * B], n_class)[1] for i in range(len(passes))]
     if timings is not None:
         timings["model_s"] = timings.get("model_s", 0.0) + t_model
         timings["post_s"] = timings.get("post_s", 0.0) + (time.perf_counter() - t0 - t_model)

@@ -56,6 +56,11 @@ SIGNATURES = {
     "pnp_crf_filter": (c_int, [_LP, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     "pnp_crf_inference": (c_int, [ctypes.POINTER(_LP), ctypes.POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "pnp_tf32_split3": (c_int, [c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
+    "pnp_gelu_tf32_split3": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
+    "pnp_layernorm_tf32_split3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                          ctypes.c_longlong, c_int, c_void_p]),
+    "pnp_profile_num_kernels": (c_int, []),
     "pnp_profile_start": (c_int, [ctypes.c_uint]),
     "pnp_profile_stop": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int), c_int]),
     "pnp_profile_kernel_name": (ctypes.c_char_p, [c_int]),

@@ -67,25 +67,37 @@ def _tf32_split(t):
     return hi, t - hi
 
 
-def _linear_3xtf32(x, lin, cache):
-    """y = x W^T + b with fp32-grade accuracy on the TF32 tensor cores: three TF32 GEMMs on an exact hi/lo split of both
-    operands (x_hi W_hi + x_hi W_lo + x_lo W_hi; the dropped x_lo W_lo term is ~2^-22 relative).  Still plain torch
-    dense contractions; `cache` holds the split of the frozen weight."""
-    if "w" not in cache:
-        w_hi, w_lo = _tf32_split(lin.weight.detach())
-        cache["w"] = (w_hi.t().contiguous(), w_lo.t().contiguous())
-    w_hi, w_lo = cache["w"]
-    shape = x.shape
-    x2 = x.reshape(-1, shape[-1])
-    x_hi, x_lo = _tf32_split(x2.contiguous())
+def _w3(weight):
+    """[N,K] frozen weight -> [N,3K] = [W_hi | W_hi | W_lo]: the right-hand operand of the depth-3K TF32 GEMM whose left
+    operand is [x_hi | x_lo | x_hi] (ops.tf32_split3 and its fused producers)."""
+    w_hi, w_lo = _tf32_split(weight.detach().contiguous())
+    return torch.cat([w_hi, w_hi, w_lo], 1).contiguous()
+
+
+MM3_SEPARATE_CORRECTION = True
+
+
+def _mm3(x3, w3, bias=None):
+    """y = x W^T (+ bias) at fp32-grade accuracy on the TF32 tensor cores over the tripled operands (fp32 accumulate; the
+    dropped x_lo W_lo term is ~2^-22 relative).  Still plain torch dense contractions (cuBLAS).
+
+    Two launches by default: the main product x_hi W_hi^T (depth K), then the two correction products accumulated onto it
+    in place ([x_lo | x_hi] [W_hi | W_lo]^T, depth 2K, beta = 1).  The tensor core adds into its fp32 accumulator with
+    truncation, an error that grows with the depth of ONE accumulation chain: keeping the 2^-11-sized corrections out of
+    the main chain leaves rms 4.8e-7 of max|y| at K = 1024 (native SIMT fp32: 1.1e-7; all three products in one depth-3K
+    chain: 2.1e-6; plain TF32: 5.7e-5) for 9 % more GEMM time (profiles/experiments/r2_gemm_precision.py)."""
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
-        y = torch.addmm(lin.bias, x_hi, w_hi) if lin.bias is not None else x_hi @ w_hi
-        y = y + (x_hi @ w_lo + x_lo @ w_hi)
+        if not MM3_SEPARATE_CORRECTION:
+            return F.linear(x3, w3, bias)
+        K = w3.shape[1] // 3
+        x2 = x3.reshape(-1, 3 * K)
+        y = F.linear(x2[:, :K], w3[:, :K], bias)
+        y.addmm_(x2[:, K:], w3[:, K:].t())
+        return y.view(*x3.shape[:-1], w3.shape[0])
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    return y.view(*shape[:-1], -1)
 
 
 class _VitBlock(nn.Module):
@@ -98,20 +110,13 @@ class _VitBlock(nn.Module):
         self.fc1 = nn.Linear(dim, int(dim * mlp_ratio))
         self.fc2 = nn.Linear(int(dim * mlp_ratio), dim)
         self.heads = heads
-        self.split3 = False          # "3xtf32": error-compensated TF32 GEMMs (inference only, frozen weights)
-        self._w3 = [{}, {}, {}, {}]
-
-    def _lin(self, i, lin, x):
-        if self.split3 and not torch.is_grad_enabled():
-            return _linear_3xtf32(x, lin, self._w3[i])
-        return lin(x)
 
     def forward(self, x):
         B, L, D = x.shape
-        qkv = self._lin(0, self.qkv, self.norm1(x)).view(B, L, 3, self.heads, D // self.heads).permute(2, 0, 3, 1, 4)
+        qkv = self.qkv(self.norm1(x)).view(B, L, 3, self.heads, D // self.heads).permute(2, 0, 3, 1, 4)
         a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
-        x = x + self._lin(1, self.proj, a.transpose(1, 2).reshape(B, L, D))
-        return x + self._lin(3, self.fc2, F.gelu(self._lin(2, self.fc1, self.norm2(x))))
+        x = x + self.proj(a.transpose(1, 2).reshape(B, L, D))
+        return x + self.fc2(F.gelu(self.fc1(self.norm2(x))))
 
 
 class VisionTransformer(nn.Module):
@@ -156,8 +161,10 @@ class CrossAttentionSelf(nn.Module):
         B, L, D = x.shape
         return x.view(B, L, self.heads, D // self.heads).permute(0, 2, 1, 3)
 
-    def forward(self, hidden, enc, enc_mask=None):
-        q, k, v = self._split(self.query(hidden)), self._split(self.key(enc)), self._split(self.value(enc))
+    def forward(self, hidden, enc, enc_mask=None, kv=None):
+        """kv: (key(enc), value(enc)) [B,L,hidden] each, precomputed for all blocks in one GEMM (3xTF32 mode)."""
+        k, v = kv if kv is not None else (self.key(enc), self.value(enc))
+        q, k, v = self._split(self.query(hidden)), self._split(k), self._split(v)
         scores = torch.matmul(q, k.transpose(-1, -2))                       # MED:228
         scale = 1.0 / math.sqrt(q.shape[-1])                                 # MED:267
         if self.save_attention:
@@ -196,8 +203,8 @@ class _BertLayer(nn.Module):
         a = F.scaled_dot_product_attention(sp(self.q(x)), sp(self.k(x)), sp(self.v(x)), attn_mask=add_mask)
         return self.attn_ln(self.attn_out(a.permute(0, 2, 1, 3).reshape(B, T, D)) + x)
 
-    def cross_and_ffn(self, x, enc):
-        x = self.cross_ln(self.cross_out(self.crossattention.self(x, enc)) + x)
+    def cross_and_ffn(self, x, enc, kv=None):
+        x = self.cross_ln(self.cross_out(self.crossattention.self(x, enc, kv=kv)) + x)
         return self.out_ln(self.out(F.gelu(self.inter(x))) + x)
 
 
@@ -267,13 +274,72 @@ class BlipITM(nn.Module):
         return self.emb_ln(self.word_emb(ids) + self.pos_emb(pos)[None])
 
     def _vit(self, imgs):
-        split3 = self.gemm_precision == "3xtf32"
-        for blk in self.visual_encoder.blocks:
-            blk.split3 = split3
         if self.gemm_precision == "bf16":
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 return self.visual_encoder(imgs).float()
         return self.visual_encoder(imgs)
+
+    # ---- "3xtf32": the frozen-weight encoder pass with every large GEMM on the TF32 tensor cores at fp32-grade accuracy
+    def _weights3(self):
+        """Tripled TF32 splits of the frozen weights ([W_hi | W_hi | W_lo], see _w3), rebuilt when a parameter changes."""
+        ve = self.visual_encoder
+        params = [ve.patch_embed.weight] + [p for blk in ve.blocks for p in (blk.qkv.weight, blk.proj.weight, blk.fc1.weight, blk.fc2.weight)]
+        params += [p for lyr in self.layer for p in (lyr.crossattention.self.key.weight, lyr.crossattention.self.value.weight)]
+        stamp = tuple((p.data_ptr(), p._version) for p in params)
+        cache = self.__dict__.get("_w3_cache")
+        if cache is None or cache["stamp"] != stamp:
+            with torch.no_grad():
+                xs = [lyr.crossattention.self for lyr in self.layer]
+                cache = {
+                    "stamp": stamp,
+                    "patch": _w3(ve.patch_embed.weight.reshape(ve.patch_embed.weight.shape[0], -1)),
+                    "blocks": [tuple(_w3(l.weight) for l in (blk.qkv, blk.proj, blk.fc1, blk.fc2)) for blk in ve.blocks],
+                    # key/value projections of all cross-attention blocks as one [layers*2*hidden, 3*enc_width] operand
+                    "kv": _w3(torch.cat([w for x in xs for w in (x.key.weight, x.value.weight)], 0)),
+                    "kv_bias": torch.cat([b for x in xs for b in (x.key.bias, x.value.bias)], 0).contiguous(),
+                }
+            self.__dict__["_w3_cache"] = cache
+        return cache
+
+    def _vit3(self, imgs, want_plain=False):
+        """ViT-L forward (VIT:274-290) under no_grad with the GEMM operands prepared by the fused split kernels:
+        residual add + LayerNorm + split, GELU + split, plain split.  Returns (enc3 [B,L,3D] split, enc [B,L,D] or None)."""
+        ve = self.visual_encoder
+        w = self._weights3()
+        B, _, S, _ = imgs.shape
+        ps = ve.patch_embed.kernel_size[0]
+        G = S // ps
+        D = ve.pos_embed.shape[-1]
+        patches = imgs.view(B, 3, G, ps, G, ps).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, 3 * ps * ps)
+        pe = _mm3(ops.tf32_split3(patches.contiguous()), w["patch"], ve.patch_embed.bias).view(B, G * G, D)
+        x = (torch.cat([ve.cls_token.expand(B, -1, -1), pe], 1) + ve.pos_embed).contiguous()
+        L = x.shape[1]
+        r = rb = None
+        for blk, (w_qkv, w_proj, w_fc1, w_fc2) in zip(ve.blocks, w["blocks"]):
+            h3, _ = ops.layernorm_tf32_split3(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, residual=r, residual_bias=rb)
+            qkv = _mm3(h3, w_qkv, blk.qkv.bias).view(B, L, 3, blk.heads, D // blk.heads).permute(2, 0, 3, 1, 4)
+            a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
+            r = _mm3(ops.tf32_split3(a.transpose(1, 2).reshape(B, L, D).contiguous()), w_proj)
+            h3, _ = ops.layernorm_tf32_split3(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, residual=r, residual_bias=blk.proj.bias)
+            g3 = ops.gelu_tf32_split3(_mm3(h3, w_fc1), blk.fc1.bias)
+            r, rb = _mm3(g3, w_fc2), blk.fc2.bias
+        return ops.layernorm_tf32_split3(x, ve.norm.weight, ve.norm.bias, ve.norm.eps, residual=r, residual_bias=rb,
+                                         split=True, plain=want_plain)
+
+    def _cross_kv3(self, enc3):
+        """key(enc) / value(enc) of every cross-attention block (MED:201-221) in one GEMM -> list of (k, v) [B,L,hidden]."""
+        w = self._weights3()
+        n = len(self.layer)
+        kv = _mm3(enc3, w["kv"], w["kv_bias"]).view(enc3.shape[0], enc3.shape[1], n, 2, -1)
+        return [(kv[:, :, i, 0], kv[:, :, i, 1]) for i in range(n)]
+
+    def _encode(self, imgs):
+        """(enc or None, per-block cross-attention (k, v) or [None]*n) for the current gemm_precision."""
+        if self.gemm_precision == "3xtf32" and imgs.is_cuda and not any(p.requires_grad for p in self.visual_encoder.parameters()):
+            with torch.no_grad():
+                enc3, _ = self._vit3(imgs)
+                return None, self._cross_kv3(enc3)
+        return self._vit(imgs), [None] * len(self.layer)
 
     def forward(self, visual_input, text_input=None, match_head="itm"):
         """ITM logits [B,2] (BITM:217-249, match_head='itm').  Also takes the LAVIS call form
@@ -283,11 +349,11 @@ class BlipITM(nn.Module):
         if match_head != "itm":
             raise NotImplementedError("only the ITM head is on the mask-extraction path")
         ids, att = self._tokenize(text_input, visual_input.device)
-        enc = self._vit(visual_input)
+        enc, kvs = self._encode(visual_input)
         add_mask = ((1.0 - att.float()) * -10000.0)[:, None, None, :]
         x = self._embed(ids)
-        for lyr in self.layer:
-            x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc)
+        for lyr, kv in zip(self.layer, kvs):
+            x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc, kv)
         return self.itm_head(x[:, 0])
 
     # ---- GradCAM of one (block, head) ----------------------------------------------------------------
@@ -318,15 +384,15 @@ class BlipITM(nn.Module):
                 cam = cap.gradcam
             else:
                 with torch.no_grad():
-                    enc = self._vit(visual_input)
+                    enc, kvs = self._encode(visual_input)
                     x = self._embed(ids)
-                    for lyr in self.layer[:layer]:
-                        x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc)
+                    for lyr, kv in zip(self.layer[:layer], kvs):
+                        x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc, kv)
                     x = self.layer[layer].self_attention(x, add_mask)
                 with torch.enable_grad():
-                    x = self.layer[layer].cross_and_ffn(x, enc)   # probs become a leaf inside (detach_probs)
-                    for lyr in self.layer[layer + 1:]:
-                        x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc)
+                    x = self.layer[layer].cross_and_ffn(x, enc, kvs[layer])   # probs become a leaf inside (detach_probs)
+                    for lyr, kv in zip(self.layer[layer + 1:], kvs[layer + 1:]):
+                        x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc, kv)
                     out = self.itm_head(x[:, 0])
                     loss = out[:, 1].sum()
                     (dprobs,) = torch.autograd.grad(loss, cap.probs)

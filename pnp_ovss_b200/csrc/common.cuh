@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "../../include/pnp_ovss_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -70,7 +72,8 @@ enum KernelId {
     kSoftmaxFwd = 1, kSoftmaxBwdGradcam = 2, kTokenMerge = 3, kDropoutRound = 4, kThresholdPrep = 5, kUpsampleWrite = 6,
     kBlurVertical = 7, kBlurHorizontal = 8, kBlurNormalize = 9, kLatticeBuild = 10, kCrfUnary = 11, kSplatBilateral = 12,
     kBlurAxisBilateral = 13, kMeanfieldUpdate = 14, kArgmax = 15, kConfusion = 16, kSplatSpatial = 17, kBlurAxisSpatial = 18,
-    kNumKernelIds = 19
+    kTf32Split = 19, kGeluSplit = 20, kLayernormSplit = 21, kLowrankBlur = 22, kLowrankUnary = 23, kBackgroundBlur = 24,
+    kNumKernelIds = 25
 };
 namespace prof {
 extern unsigned g_mask;

@@ -1,0 +1,170 @@
+// tf32x3.cu -- operand preparation for fp32-grade GEMMs on the TF32 tensor cores (the model pass,
+// BITM:386-404, whose dense contractions stay torch's -- cuBLAS TF32 GEMMs -- while everything around them is here).
+//
+// y = x W^T is computed as ONE TF32 GEMM of depth 3K on an exact split of both operands:
+//     x = x_hi + x_lo,  W = W_hi + W_lo    (hi = x rounded to TF32's 10 explicit mantissa bits; lo = x - hi is exact)
+//     [x_hi | x_lo | x_hi] (M x 3K)  times  [W_hi | W_hi | W_lo]^T (3K x N)  =  x_hi W_hi + x_lo W_hi + x_hi W_lo
+// (the dropped x_lo W_lo term is 2^-22 relative; accumulation is fp32 inside the tensor core).  The kernels below write
+// the tripled activation operand straight from its producer, so the split costs no extra pass over HBM:
+//     split3            x                        -> [hi | lo | hi]
+//     layernorm_split3  LayerNorm(x) (VIT:70-71) -> [hi | lo | hi]   (one warp per row, row held in registers)
+//     gelu_split3       GELU(x + bias) (exact erf, VIT:35-40)  -> [hi | lo | hi]
+// All three are pure HBM streams (4 B read, 12 B written per element) with 128-bit accesses.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pnp {
+
+__device__ __forceinline__ float tf32_hi(float x) {
+    // round to nearest (ties away) at bit 13; non-finite inputs and overflow to inf keep x itself (lo = 0)
+    float hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    return (fabsf(hi) <= 3.402823466e38f) ? hi : x;
+}
+
+__device__ __forceinline__ void store_split3(float *__restrict__ row_out, int K, int k, float4 v) {
+    float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    // lo = v - hi exactly; where hi fell back to v itself (inf, NaN, overflow) the difference is defined as 0, not inf - inf
+    float4 lo = make_float4(hi.x == v.x ? 0.f : v.x - hi.x, hi.y == v.y ? 0.f : v.y - hi.y, hi.z == v.z ? 0.f : v.z - hi.z,
+                            hi.w == v.w ? 0.f : v.w - hi.w);
+    stg_stream4(row_out + k, hi);
+    stg_stream4(row_out + K + k, lo);
+    stg_stream4(row_out + 2 * K + k, hi);
+}
+
+__global__ void __launch_bounds__(256) split3_kernel(const float *__restrict__ x, float *__restrict__ out, long long M, int K) {
+    const int kq = K >> 2;
+    const long long total = M * kq;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / kq;
+        const int k = (int)(i - m * kq) * 4;
+        store_split3(out + m * 3 * K, K, k, ldg_stream4(x + m * K + k));
+    }
+}
+
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(256) gelu_split3_kernel(const float *__restrict__ x, const float *__restrict__ bias,
+                                                          float *__restrict__ out, long long M, int K) {
+    const int kq = K >> 2;
+    const long long total = M * kq;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / kq;
+        const int k = (int)(i - m * kq) * 4;
+        float4 v = ldg_stream4(x + m * K + k);
+        if (bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + k));
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        }
+        store_split3(out + m * 3 * K, K, k, make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w)));
+    }
+}
+
+// One warp per row; the row (K <= 128*kChunks floats) stays in registers between the mean, the variance and the write.
+// Optional residual: x = x + res (+ res_bias) is formed first and written back to x_out (the running hidden state), so the
+// residual add, the LayerNorm and the operand split are one pass.
+template <int kChunks>
+__global__ void __launch_bounds__(256) layernorm_split3_kernel(const float *__restrict__ x, const float *__restrict__ res,
+                                                               const float *__restrict__ res_bias, float *__restrict__ x_out,
+                                                               const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                               float eps, float *__restrict__ out3, float *__restrict__ out1,
+                                                               long long M, int K) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (long long m = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * wpb) {
+        float4 v[kChunks];
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            const int k = (lane + 32 * c) * 4;
+            if (k < K) {
+                float4 t = ldg_stream4(x + m * K + k);
+                if (res) {
+                    const float4 r = ldg_stream4(res + m * K + k);
+                    t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+                    if (res_bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(res_bias + k));
+                        t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+                    }
+                    if (x_out) *reinterpret_cast<float4 *>(x_out + m * K + k) = t;
+                }
+                v[c] = t;
+                sum += (t.x + t.y) + (t.z + t.w);
+            } else {
+                v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        const float mean = warp_sum(sum) / (float)K;
+        float sq = 0.f;
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            if ((lane + 32 * c) * 4 < K) {
+                const float a = v[c].x - mean, b = v[c].y - mean, cc = v[c].z - mean, d = v[c].w - mean;
+                sq += (a * a + b * b) + (cc * cc + d * d);
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / (float)K + eps);
+#pragma unroll
+        for (int c = 0; c < kChunks; ++c) {
+            const int k = (lane + 32 * c) * 4;
+            if (k < K) {
+                const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma + k));
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(beta + k));
+                const float4 y = make_float4((v[c].x - mean) * rstd * g.x + b.x, (v[c].y - mean) * rstd * g.y + b.y,
+                                             (v[c].z - mean) * rstd * g.z + b.z, (v[c].w - mean) * rstd * g.w + b.w);
+                if (out3) store_split3(out3 + m * 3 * K, K, k, y);
+                if (out1) stg_stream4(out1 + m * K + k, y);
+            }
+        }
+    }
+}
+
+}  // namespace pnp
+
+using namespace pnp;
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int pnp_tf32_split3(const float *x, float *out3, long long M, int K, pnp_stream_t stream) {
+    if (!x || !out3 || M < 0 || K < 4 || K % 4 || !aligned16(x) || !aligned16(out3)) return PNP_ERR_INVALID_ARGUMENT;
+    if (M == 0) return PNP_OK;
+    cudaStream_t st = as_stream(stream);
+    const long long total = M * (K / 4);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16));
+    PNP_LAUNCH(kTf32Split, st, split3_kernel<<<grid, 256, 0, st>>>(x, out3, M, K));
+    return launch_status();
+}
+
+extern "C" int pnp_gelu_tf32_split3(const float *x, const float *bias, float *out3, long long M, int K, pnp_stream_t stream) {
+    if (!x || !out3 || M < 0 || K < 4 || K % 4 || !aligned16(x) || !aligned16(out3) || (bias && !aligned16(bias)))
+        return PNP_ERR_INVALID_ARGUMENT;
+    if (M == 0) return PNP_OK;
+    cudaStream_t st = as_stream(stream);
+    const long long total = M * (K / 4);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16));
+    PNP_LAUNCH(kGeluSplit, st, gelu_split3_kernel<<<grid, 256, 0, st>>>(x, bias, out3, M, K));
+    return launch_status();
+}
+
+extern "C" int pnp_layernorm_tf32_split3(const float *x, const float *residual, const float *residual_bias, float *x_out,
+                                         const float *gamma, const float *beta, float eps, float *out3, float *out1, long long M,
+                                         int K, pnp_stream_t stream) {
+    if (!x || !gamma || !beta || (!out3 && !out1) || M < 0 || K < 4 || K % 4 || K > 128 * 16 || !aligned16(x) ||
+        (out3 && !aligned16(out3)) || (out1 && !aligned16(out1)) || !aligned16(gamma) || !aligned16(beta) ||
+        (residual && !aligned16(residual)) || (residual_bias && (!residual || !aligned16(residual_bias))) ||
+        (x_out && (!residual || !aligned16(x_out))))
+        return PNP_ERR_INVALID_ARGUMENT;
+    if (M == 0) return PNP_OK;
+    cudaStream_t st = as_stream(stream);
+    const int wpb = 8;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((M + wpb - 1) / wpb, (long long)kNumSMs * 8));
+    const int chunks = (K + 127) / 128;
+#define PNP_LN(C)                                                                                                      \
+    PNP_LAUNCH(kLayernormSplit, st, layernorm_split3_kernel<C><<<grid, 32 * wpb, 0, st>>>(x, residual, residual_bias, x_out, gamma, \
+                                                                                          beta, eps, out3, out1, M, K))
+    if (chunks <= 6) PNP_LN(6);
+    else if (chunks <= 8) PNP_LN(8);
+    else PNP_LN(16);
+#undef PNP_LN
+    return launch_status();
+}

@@ -26,7 +26,7 @@ from .blip_itm import FusedXattnSoftmax, GradcamCapture
 
 # keys of the reference checkpoint that the ITM path never reads (ITC projections, momentum copies, queues, buffers)
 _IGNORED_PREFIXES = ("vision_proj.", "text_proj.", "temp", "visual_encoder_m.", "text_encoder_m.", "vision_proj_m.",
-                     "text_proj_m.", "image_queue", "text_queue", "idx_queue", "queue_ptr")
+                     "text_proj_m.", "image_queue", "text_queue", "idx_queue", "queue_ptr", "ptr_queue")
 _IGNORED_SUFFIXES = ("position_ids",)
 
 
@@ -87,8 +87,10 @@ def resize_pos_embed(pos_embed, n_tokens):
 def load_lavis_state_dict(model, state_dict):
     """Copy a LAVIS BlipITM checkpoint (the dict itself or {"model": dict}, BASE:103-106) into `model`.
 
-    Every native parameter must be found with the right shape (position embedding aside, which is resized); LAVIS keys
-    that the ITM path does not use are ignored, anything else unknown raises.  Returns the list of ignored keys."""
+    Every native parameter must be found with the right shape (position embedding aside, which is resized).  Extra keys
+    never raise, like the reference's `load_state_dict(..., strict=False)` (BASE:112): keys the ITM path is known not to use
+    (ITC projections, momentum copies, queues) are ignored silently, any other extra key is ignored with a warning.
+    Returns the list of all ignored keys."""
     sd = state_dict["model"] if "model" in state_dict and isinstance(state_dict["model"], dict) else state_dict
     kmap = native_to_lavis_keys(model)
     own = model.state_dict()
@@ -102,7 +104,9 @@ def load_lavis_state_dict(model, state_dict):
             continue
         (ignored if k.startswith(_IGNORED_PREFIXES) or k.endswith(_IGNORED_SUFFIXES) else unknown).append(k)
     if unknown:
-        raise KeyError("checkpoint has %d keys this model does not know, first: %s" % (len(unknown), unknown[:4]))
+        import warnings
+        warnings.warn("checkpoint has %d keys this model does not use (ignored like strict=False), first: %s" % (len(unknown), unknown[:4]))
+        ignored += unknown
     new = {}
     for nk, lk in kmap.items():
         t = sd[lk]
@@ -112,9 +116,7 @@ def load_lavis_state_dict(model, state_dict):
             raise ValueError("%s: checkpoint shape %s, model shape %s" % (lk, tuple(t.shape), tuple(own[nk].shape)))
         new[nk] = t
     model.load_state_dict(new, strict=True)
-    for blk in model.visual_encoder.blocks:       # cached 3xTF32 weight splits belong to the old weights
-        for c in blk._w3:
-            c.clear()
+    model.__dict__.pop("_w3_cache", None)         # cached 3xTF32 weight splits belong to the old weights
     return ignored
 
 

@@ -68,8 +68,10 @@ def softmax_bwd_gradcam(probs, dprobs, token_mask, head, scale=0.125, need_dscor
 
 
 # ----------------------------------------------------------------------------------------------- (b)
-def token_merge(gradcam, seg_start, seg_len, seg_div, row_offset=3):
-    """gradcam [B,Tm,P,P] or [B,Tm,PP]; seg_* [B,C] -> class maps [B,C,*spatial] (DRV:810-853)."""
+def token_merge(gradcam, seg_start, seg_len, seg_div, row_offset=3, max_end=None):
+    """gradcam [B,Tm,P,P] or [B,Tm,PP]; seg_* [B,C] -> class maps [B,C,*spatial] (DRV:810-853).
+    max_end = max(seg_start + seg_len), known to the host code that built the tables (pipeline.segment_tensors); when it
+    is not given the bound is read back from the device (a blocking copy: tests and one-off calls only)."""
     _req(gradcam, torch.float32, "gradcam")
     B, Tm = gradcam.shape[:2]
     spatial = tuple(gradcam.shape[2:])
@@ -80,7 +82,9 @@ def token_merge(gradcam, seg_start, seg_len, seg_div, row_offset=3):
     _req(seg_len, torch.int32, "seg_len", 2)
     _req(seg_div, torch.float32, "seg_div", 2)
     C = seg_start.shape[1]
-    if int((seg_start + seg_len).max()) + row_offset > Tm:
+    if max_end is None:
+        max_end = int((seg_start + seg_len).max())
+    if int(max_end) + row_offset > Tm:
         raise PnpError("token segment runs past the GradCAM rows")
     out = torch.empty((B, C) + spatial, dtype=torch.float32, device=gradcam.device)
     check(_lib.load().pnp_token_merge(_p(gradcam), _p(seg_start), _p(seg_len), _p(seg_div), _p(out), B, Tm, PP, C, row_offset,
@@ -291,6 +295,59 @@ def crf_inference(lattices, weights, unary, C, n_iter, want_labels=True, scratch
     check(lib.pnp_crf_inference(arr, w, len(lattices), _p(unary), _p(Q), _p(scratch), scratch.numel(), _p(labels), B, int(C), Cp,
                                 int(n_iter), _stream()), "pnp_crf_inference")
     return Q, labels
+
+
+# ----------------------------------------------------------------------------------------------- (f)1 model-pass GEMM operands
+def tf32_split3(x):
+    """x [..., K] -> [..., 3K] = [hi | lo | hi] (exact TF32 split; see pnp_tf32_split3)."""
+    _req(x, torch.float32, "x")
+    K = x.shape[-1]
+    M = x.numel() // K
+    out = torch.empty(x.shape[:-1] + (3 * K,), dtype=torch.float32, device=x.device)
+    check(_lib.load().pnp_tf32_split3(_p(x), _p(out), M, K, _stream()), "pnp_tf32_split3")
+    return out
+
+
+def gelu_tf32_split3(x, bias=None):
+    """[hi | lo | hi] split of GELU(x + bias) (exact erf form)."""
+    _req(x, torch.float32, "x")
+    K = x.shape[-1]
+    M = x.numel() // K
+    if bias is not None:
+        _req(bias, torch.float32, "bias", 1)
+        if bias.shape[0] != K:
+            raise PnpError("bias must be [K]")
+    out = torch.empty(x.shape[:-1] + (3 * K,), dtype=torch.float32, device=x.device)
+    check(_lib.load().pnp_gelu_tf32_split3(_p(x), _p(bias), _p(out), M, K, _stream()), "pnp_gelu_tf32_split3")
+    return out
+
+
+def layernorm_tf32_split3(x, gamma, beta, eps, residual=None, residual_bias=None, split=True, plain=False):
+    """LayerNorm over the last dim of x (or of x + residual + residual_bias, which then REPLACES x in place).
+    Returns (split [..., 3K] or None, plain [..., K] or None)."""
+    _req(x, torch.float32, "x")
+    K = x.shape[-1]
+    M = x.numel() // K
+    _req(gamma, torch.float32, "gamma", 1)
+    _req(beta, torch.float32, "beta", 1)
+    if gamma.shape[0] != K or beta.shape[0] != K:
+        raise PnpError("gamma/beta must be [K]")
+    if residual is not None:
+        _req(residual, torch.float32, "residual")
+        if residual.shape != x.shape:
+            raise PnpError("residual shape mismatch")
+    if residual_bias is not None:
+        _req(residual_bias, torch.float32, "residual_bias", 1)
+        if residual is None or residual_bias.shape[0] != K:
+            raise PnpError("residual_bias needs a residual and must be [K]")
+    if not (split or plain):
+        raise PnpError("nothing to compute")
+    out3 = torch.empty(x.shape[:-1] + (3 * K,), dtype=torch.float32, device=x.device) if split else None
+    out1 = torch.empty_like(x) if plain else None
+    check(_lib.load().pnp_layernorm_tf32_split3(_p(x), _p(residual), _p(residual_bias), _p(x if residual is not None else None),
+                                                _p(gamma), _p(beta), float(eps), _p(out3), _p(out1), M, K, _stream()),
+          "pnp_layernorm_tf32_split3")
+    return out3, out1
 
 
 # ----------------------------------------------------------------------------------------------- (f)

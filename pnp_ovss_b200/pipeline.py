@@ -39,19 +39,43 @@ def salience_dropout_loop(gradcam_fn, imgs, norm_imgs, drop_iter, P, save_len=SA
 
 
 # ---------------------------------------------------------------------------------------------- (b) batched merge
+_SEG_ROWS = {}     # (token id row up to SEP, n_classes, decode) -> [(start, len, div)]: the walk depends on the caption only
+_SEG_TABLES = {}   # (rows of a whole batch, device) -> (start, len, div device tensors, max_end): repeated batches upload nothing
+
+
+def _segment_row(ids_row, n_classes, decode):
+    ids = tuple(int(t) for t in ids_row)
+    if host.SEP_ID in ids[1:]:
+        ids = ids[:ids.index(host.SEP_ID, 1) + 1]
+    key = (ids, n_classes, decode)
+    if key not in _SEG_ROWS:
+        if len(_SEG_ROWS) > 4096:
+            _SEG_ROWS.clear()
+        _SEG_ROWS[key] = tuple(host.build_token_segments(host.token_strings(list(ids), decode), n_classes))
+    return _SEG_ROWS[key]
+
+
 def segment_tensors(token_ids, decode, class_lists, dev):
     """Host walk of the WordPiece strings (host.build_token_segments) -> the three [B,Cmax] device tables of
-    pnp_token_merge.  Depends on the captions only, so both reference passes of a batch share it."""
+    pnp_token_merge plus max_end = the last GradCAM row any segment touches (so the merge need not ask the device).
+    Depends on the captions only: both reference passes of a batch share it and repeated captions are cached."""
     B = len(class_lists)
+    rows = tuple(_segment_row(token_ids[b], len(class_lists[b]), decode) for b in range(B))
+    key = (rows, str(dev))
+    if key in _SEG_TABLES:
+        return _SEG_TABLES[key]
     Cmax = max(len(c) for c in class_lists)
     start = np.zeros((B, Cmax), np.int32)
     length = np.zeros((B, Cmax), np.int32)
     div = np.ones((B, Cmax), np.float32)
     for b in range(B):
-        toks = host.token_strings(list(token_ids[b]), decode)
-        for c, (s, l, d) in enumerate(host.build_token_segments(toks, len(class_lists[b]))):
+        for c, (s, l, d) in enumerate(rows[b]):
             start[b, c], length[b, c], div[b, c] = s, l, d
-    return torch.from_numpy(start).to(dev), torch.from_numpy(length).to(dev), torch.from_numpy(div).to(dev)
+    max_end = int((start + length).max()) if start.size else 0
+    if len(_SEG_TABLES) > 64:
+        _SEG_TABLES.clear()
+    _SEG_TABLES[key] = (torch.from_numpy(start).to(dev), torch.from_numpy(length).to(dev), torch.from_numpy(div).to(dev), max_end)
+    return _SEG_TABLES[key]
 
 
 def merge_tokens_batch(gradcam, token_ids, decode, class_lists, segs=None):
@@ -59,7 +83,7 @@ def merge_tokens_batch(gradcam, token_ids, decode, class_lists, segs=None):
     (one pnp_token_merge launch over the batch, padded to the largest C)."""
     if segs is None:
         segs = segment_tensors(token_ids, decode, class_lists, gradcam.device)
-    maps = ops.token_merge(gradcam.contiguous(), segs[0], segs[1], segs[2], row_offset=3)
+    maps = ops.token_merge(gradcam.contiguous(), segs[0], segs[1], segs[2], row_offset=3, max_end=segs[3] if len(segs) > 3 else None)
     return [maps[b, :len(class_lists[b])] for b in range(gradcam.shape[0])]
 
 
@@ -154,7 +178,8 @@ def _side_stream(dev):
 
 
 def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_ids, gts, guides, *, drop_iter, patch_num,
-                    threshold, data_type, mode, n_class, coco=False, crf=None, norm_imgs=None, stats=None, overlap=True):
+                    threshold, data_type, mode, n_class, coco=False, crf=None, norm_imgs=None, stats=None, overlap=True,
+                    labels_out=None, bad_count=None):
     """One batch of save_img_union_attention: returns (hist_round0 or None, hist_all_drop or None, chosen) with the
     matrices as int64 CUDA tensors [n,n] -- what the reference saves to hist_withfiltered_caption/ and
     all_drop_hist_with_filtered_caption/ (DRV:495-520).  `coco` selects the COCO driver's deltas (DRVC:420, 527, 602).
@@ -164,14 +189,18 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
     local class i.
 
     overlap: the bilateral lattice build and the whole round-0 pass (which needs only the round-0 map) run on a second
-    CUDA stream while DropOut rounds 1..R-1 (model passes) occupy the main stream; results are identical either way."""
+    CUDA stream while DropOut rounds 1..R-1 (model passes) occupy the main stream; results are identical either way.
+
+    labels_out: a dict that receives {"round0" / "all_drop": float32 [B,H,W] relabelled maps} (uniform batches only).
+    bad_count: an int32 [1] CUDA tensor that accumulates the number of relabelled ids outside [0, n_class); when given,
+    the caller checks it once per run and this function never reads the device back (no host sync per batch)."""
     dev = imgs.device
     B = imgs.shape[0]
-    main = torch.cuda.current_stream(dev)
     round0_scored = not coco or drop_iter < 3
     timed_stages = stats is not None and "events" in stats
     use_side = bool(overlap) and drop_iter > 1 and round0_scored and not timed_stages
-    side = _side_stream(dev) if use_side else main
+    main = torch.cuda.current_stream(dev) if use_side else None
+    side = _side_stream(dev) if use_side else None
     use_crf = bool(mode) and "crf" in mode
     crf_p = dict(CRF_DEFAULTS)
     crf_p.update(crf or {})
@@ -194,7 +223,7 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
         hists["round0"] = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
     if drop_iter > 1:
         hists["all_drop"] = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
-    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    bad = bad_count if bad_count is not None else torch.zeros(1, dtype=torch.int32, device=dev)
     ev_inputs = main.record_event() if use_side else None
     lattices = {}
     ev_lattices = None
@@ -212,8 +241,13 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
         for key, members in buckets.items():
             gt, gd, lut = inputs[key]
             cm = torch.stack([merged[b] for b in members]).contiguous()
-            postprocess_batch(cm, gd, gt, lut, hists[name], threshold=threshold, rescale=rescale, with_background=key[1],
-                              mode=mode, n_class=n_class, crf=crf, bad_count=bad, stats=stats, bilateral=lattices.get(key))
+            pred = postprocess_batch(cm, gd, gt, lut, hists[name], threshold=threshold, rescale=rescale, with_background=key[1],
+                                     mode=mode, n_class=n_class, crf=crf, bad_count=bad, stats=stats, bilateral=lattices.get(key),
+                                     return_labels=labels_out is not None)
+            if labels_out is not None:
+                if len(buckets) != 1:
+                    raise PnpError("labels_out needs a uniform batch (one bucket)")
+                labels_out[name] = pred
 
     def after_round0(g0):
         nonlocal ev_lattices
@@ -225,7 +259,7 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
             build_lattices()                       # runs under round 0's model pass; host waits for the build only
             ev_lattices = side.record_event()
             side.wait_event(ev_r0)
-            for t in (g0, bad, hists["round0"]) + tuple(x for v in inputs.values() for x in v) + tuple(segs):
+            for t in (g0, bad, hists["round0"]) + tuple(x for v in inputs.values() for x in v) + tuple(segs[:3]):
                 t.record_stream(side)
             run_pass("round0", g0, True)           # 1-round path applies Scale_0_1 (DRV:362)
 
@@ -243,7 +277,7 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
         run_pass("all_drop", agg, coco)            # N-round path: only the COCO driver rescales (DRV:438 vs DRVC:527)
     if use_side:
         main.wait_stream(side)
-    if int(bad.item()):
+    if bad_count is None and int(bad.item()):
         raise PnpError("a relabelled id fell outside [0, n_class)")
     return hists.get("round0"), hists.get("all_drop"), chosen
 

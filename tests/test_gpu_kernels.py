@@ -322,3 +322,71 @@ def test_ops_fail_loudly_on_bad_arguments(dev, ops):
     bad = torch.zeros(1, dtype=torch.int32, device=dev)
     ops.confusion_accumulate(torch.full((1, 4), 7, dtype=torch.int32, device=dev), torch.zeros(1, 4, device=dev), 3, hist, bad_count=bad)
     assert int(bad.item()) == 4 and int(hist.sum()) == 0                            # out-of-range ids are counted, never binned
+
+
+# ------------------------------------------------------------------------------------------------ (f)1 GEMM operand kernels
+def _split_ref(t):
+    hi = ((t.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+    return torch.cat([hi, t - hi, hi], -1)
+
+
+@pytest.mark.parametrize("M,K", [(1, 4), (37, 768), (442 * 3, 1024), (50, 4096)])
+def test_tf32_split3_is_exact(dev, ops, M, K):
+    """[hi | lo | hi]: hi has no bits below TF32's mantissa, hi + lo == x bit for bit (integer work: exact)."""
+    x = (torch.randn(M, K, generator=torch.Generator().manual_seed(M + K)) * 3).to(dev)
+    got = ops.tf32_split3(x)
+    assert got.shape == (M, 3 * K)
+    assert torch.equal(got, _split_ref(x))
+    assert int((got[:, :K].view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert torch.equal(got[:, :K] + got[:, K:2 * K], x)
+    special = torch.tensor([[0.0, -0.0, float("inf"), -float("inf")], [3.4028234e38, -3.4028234e38, 1e-45, float("nan")]], device=dev)
+    s3 = ops.tf32_split3(special)
+    back = s3[:, :4] + s3[:, 4:8]
+    assert torch.equal(back[~special.isnan()], special[~special.isnan()]) and bool(back[1, 3].isnan())
+
+
+@pytest.mark.parametrize("K", [768, 1024, 2048])
+def test_layernorm_tf32_split3_matches_torch(dev, ops, K):
+    g = torch.Generator().manual_seed(K)
+    M = 333
+    x, res = torch.randn(M, K, generator=g).to(dev) * 2 + 0.3, torch.randn(M, K, generator=g).to(dev)
+    gamma, beta, rb = (torch.randn(K, generator=g).to(dev) for _ in range(3))
+    want = torch.nn.functional.layer_norm(x.double(), (K,), gamma.double(), beta.double(), 1e-6)
+    s3, plain = ops.layernorm_tf32_split3(x.clone(), gamma, beta, 1e-6, split=True, plain=True)
+    _close(plain.cpu(), want.cpu(), rtol=1e-5, atol=2e-6)
+    assert torch.equal(s3, _split_ref(plain))
+    # fused residual: x <- x + res + bias (written back in place), then the same LayerNorm
+    xin = x.clone()
+    s3, plain = ops.layernorm_tf32_split3(xin, gamma, beta, 1e-6, residual=res, residual_bias=rb, split=True, plain=True)
+    assert torch.equal(xin, (x + res) + rb)
+    want = torch.nn.functional.layer_norm(xin.double(), (K,), gamma.double(), beta.double(), 1e-6)
+    _close(plain.cpu(), want.cpu(), rtol=1e-5, atol=2e-6)
+    assert torch.equal(s3, _split_ref(plain))
+
+
+def test_gelu_tf32_split3_matches_torch(dev, ops):
+    g = torch.Generator().manual_seed(9)
+    x, b = torch.randn(257, 4096, generator=g).to(dev) * 3, torch.randn(4096, generator=g).to(dev)
+    got = ops.gelu_tf32_split3(x, b)
+    want = torch.nn.functional.gelu((x + b).double())
+    back = got[:, :4096] + got[:, 4096:8192]
+    _close(back.cpu(), want.cpu(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(got[:, :4096], got[:, 8192:])
+    assert int((got[:, :4096].view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+def test_tripled_tf32_gemm_is_fp32_grade(dev, ops):
+    """One TF32 GEMM over [x_hi|x_lo|x_hi] x [W_hi|W_hi|W_lo]^T against an fp64 product: the error must be of the order of
+    a native fp32 GEMM's, far below plain TF32's."""
+    from pnp_ovss_b200.blip_itm import _mm3, _w3
+    g = torch.Generator().manual_seed(2)
+    x, w, b = torch.randn(512, 1024, generator=g).to(dev), (torch.randn(768, 1024, generator=g) * 0.02).to(dev), torch.randn(768, generator=g).to(dev)
+    truth = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    err3 = (_mm3(ops.tf32_split3(x), _w3(w), b).double() - truth).abs().max().item()
+    err32 = (torch.nn.functional.linear(x, w, b).double() - truth).abs().max().item()
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    err_tf32 = (torch.nn.functional.linear(x, w, b).double() - truth).abs().max().item()
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    assert err3 <= 4 * err32 + 1e-6, (err3, err32)
+    assert err3 * 20 <= err_tf32, (err3, err_tf32)

@@ -62,7 +62,7 @@ def test_position_embedding_is_resized_like_the_reference_loader():
         L.resize_pos_embed(pe, 12)
 
 
-def test_loader_rejects_missing_unknown_and_misshapen_keys():
+def test_loader_rejects_missing_and_misshapen_keys_and_warns_on_unknown_ones():
     from pnp_ovss_b200 import lavis_compat as L
     tok, lavis, native = _pair()
     sd = dict(lavis.state_dict())
@@ -70,8 +70,8 @@ def test_loader_rejects_missing_unknown_and_misshapen_keys():
     del missing["itm_head.weight"]
     with pytest.raises(KeyError):
         L.load_lavis_state_dict(native, missing)
-    with pytest.raises(KeyError):
-        L.load_lavis_state_dict(native, dict(sd, **{"text_decoder.cls.bias": torch.zeros(1)}))
+    with pytest.warns(UserWarning, match="does not use"):      # strict=False like BASE:112
+        assert "text_decoder.cls.bias" in L.load_lavis_state_dict(native, dict(sd, **{"text_decoder.cls.bias": torch.zeros(1)}))
     with pytest.raises(ValueError):
         L.load_lavis_state_dict(native, dict(sd, **{"itm_head.weight": torch.zeros(3, 24)}))
 
@@ -84,3 +84,30 @@ def test_reference_attribute_path_on_the_native_model():
     from pnp_ovss_b200.lavis_compat import cross_attention_modules
     assert cross_attention_modules(native)[2] is native.layer[2].crossattention.self
     assert cross_attention_modules(lavis)[2] is lavis.text_encoder.encoder.layer[2].crossattention.self
+
+
+def test_original_blip_retrieval_checkpoint_extras_are_tolerated():
+    """model_large_retrieval_flickr.pth (YAML:10) is the original BLIP retrieval checkpoint: it carries momentum copies, the
+    queues and their pointer under the name `ptr_queue`; the reference loads it with strict=False (BASE:112).  A key nobody
+    has heard of is ignored with a warning; a missing ITM-path key or a wrong shape still raises."""
+    import warnings
+    tok, lavis, native = _pair()
+    sd = dict(lavis.state_dict())
+    sd.update({"ptr_queue": torch.zeros(1, dtype=torch.long), "idx_queue": torch.full((1, 8), -100), "image_queue": torch.randn(4, 8),
+               "text_queue": torch.randn(4, 8), "temp": torch.tensor(0.07),
+               "visual_encoder_m.cls_token": torch.zeros(1, 1, 32), "text_encoder_m.embeddings.word_embeddings.weight": torch.zeros(4, 24),
+               "vision_proj_m.weight": torch.zeros(4, 32), "text_proj_m.weight": torch.zeros(4, 24)})
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        ignored = native.load_lavis_checkpoint({"model": sd})
+    assert "ptr_queue" in ignored and "visual_encoder_m.cls_token" in ignored
+    sd["some.future.buffer"] = torch.zeros(3)
+    with pytest.warns(UserWarning, match="does not use"):
+        ignored = native.load_lavis_checkpoint(sd)
+    assert "some.future.buffer" in ignored
+    broken = {k: v for k, v in sd.items() if k != "itm_head.weight"}
+    with pytest.raises(KeyError):
+        native.load_lavis_checkpoint(broken)
+    sd["itm_head.weight"] = torch.zeros(3, 24)
+    with pytest.raises(ValueError):
+        native.load_lavis_checkpoint(sd)
