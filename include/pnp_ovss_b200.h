@@ -115,6 +115,22 @@ size_t pnp_gaussian_blur_workspace_bytes(int n_maps, int H, int W, double sigma)
 int pnp_gaussian_blur(const float *in, float *out, float *minmax, void *workspace, size_t workspace_bytes,
                       int n_maps, int H, int W, double sigma, int normalize, pnp_stream_t stream);
 
+/* Fused low-rank form of the whole (d) group for a batch whose maps are blurred (--postprocess blur / blur+crf):
+ * threshold (DRV:425-433) -> bilinear upsample (DRV:435-437) -> [Scale_0_1] -> background channel (DRV:446-455) ->
+ * Gaussian blur + min-max of every channel (DRV:1005-1011, 1149-1153) -> one of
+ *   unary  [B,N,Cp]   -log(clip(softmax_c(maps), 1e-5, 1)), pixel-major, Cp = 4*ceil(C'/4), padding 0 (DRV:1057-1063)
+ *   labels [B,N]      argmax_c(maps), first maximum, NaN counts as maximum (blur-only mode, DRV:1018-1025)
+ *   maps_out [B,C',H,W]  the normalised blurred maps themselves (what `blurring` returns per channel)
+ * (any subset; at least one).  minmax_out (optional) [B*C',2] receives (min, max) of every blurred channel.
+ * Upsample and blur are linear and separable, so a class channel is A_y m A_x^T with A = G_sigma U (H x P, W x P): no
+ * full-resolution input or intermediate exists; Scale_0_1 is affine per channel and cancels in the min-max that follows
+ * the blur, so `rescale` only enters the background test.  The background indicator is evaluated at full resolution with
+ * the arithmetic of pnp_threshold_upsample and blurred tap by tap like pnp_gaussian_blur.  class_maps [B,C,P,P], P <= 32. */
+size_t pnp_lowrank_blur_workspace_bytes(int B, int C, int P, int H, int W, double sigma, int with_background);
+int pnp_lowrank_blur_unary(const float *class_maps, float *unary, int32_t *labels, float *maps_out, float *minmax_out,
+                           void *workspace, size_t workspace_bytes, int B, int C, int P, int H, int W, float threshold,
+                           int rescale, int with_background, double sigma, pnp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * (e) dense-CRF mean-field inference on permutohedral lattices; replaces the pydensecrf calls of
  *     DRV:1030-1074 (DenseCRF2D / addPairwiseGaussian / addPairwiseBilateral / inference)

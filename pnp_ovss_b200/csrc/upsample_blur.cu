@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(256) threshold_prep_kernel(const float *__rest
 }
 
 // K2: write out[b, bg + c, y, x..x+VEC) for all c, plus the background channel.
-template <int VEC>
+// kBgOnly: evaluate every channel exactly as above but store ONLY the background indicator, to out [B,H,W] (the fused
+// low-rank path blurs the class channels from their PxP grids and needs the full-resolution values just for this test).
+template <int VEC, bool kBgOnly = false>
 __global__ void __launch_bounds__(256) upsample_write_kernel(const float *__restrict__ masked, const float *__restrict__ scale_params,
                                                              float *__restrict__ out, int C, int P, int H, int W, int rescale,
                                                              int with_background) {
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) upsample_write_kernel(const float *__rest
     const float rh = (H > 1) ? (float)(P - 1) / (float)(H - 1) : 0.f;
     const float rw = (W > 1) ? (float)(P - 1) / (float)(W - 1) : 0.f;
     const float *grid0 = masked + (long long)b * C * PP;
-    float *out_b = out + (long long)b * Cout * N;
+    float *out_b = out + (long long)b * (kBgOnly ? 1 : Cout) * N;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < H * Wq; q += gridDim.x * blockDim.x) {
         const int y = q / Wq, xb = (q - y * Wq) * VEC;
         const float sy = rh * y;
@@ -143,11 +145,13 @@ __global__ void __launch_bounds__(256) upsample_write_kernel(const float *__rest
                 vnan[v] = vnan[v] || (val != val);
                 vmax[v] = fmaxf(vmax[v], val);
             }
-            float *dst = out_b + (long long)(c + (with_background ? 1 : 0)) * N + (long long)y * W + xb;
-            if (VEC == 4)
-                stg_stream4(dst, make_float4(r[0], r[1], r[2], r[3]));
-            else
-                dst[0] = r[0];
+            if (!kBgOnly) {
+                float *dst = out_b + (long long)(c + (with_background ? 1 : 0)) * N + (long long)y * W + xb;
+                if (VEC == 4)
+                    stg_stream4(dst, make_float4(r[0], r[1], r[2], r[3]));
+                else
+                    dst[0] = r[0];
+            }
         }
         if (with_background) {  // DRV:446-450: background = (max over classes == 0); torch.max propagates NaN
             float r[VEC];
@@ -447,6 +451,215 @@ __global__ void __launch_bounds__(256) blur_normalize_kernel(float *__restrict__
     }
 }
 
+
+// ============================================================================================ fused low-rank (d) group
+// The maps that get blurred are bilinear upsamples of PxP grids (thresholded BEFORE upsampling, DRV:425-437), and both the
+// upsample and the separable Gaussian are linear and separable, so for a class channel
+//     blur(upsample(m)) = (G U_y) m (G U_x)^T = A_y m A_x^T          A_y: H x P,  A_x: W x P   (reflect boundary folded in)
+// -- about 2 P multiply-adds per output instead of 2 (2 lw + 1) (42 against 270 at 336 px), and no full-resolution input or
+// intermediate at all.  Scale_0_1 (DRV:1078-1094) is an affine map per channel and G's rows sum to one, so it commutes with
+// the blur and cancels in the min-max normalisation that follows it (DRV:1151-1152): the class channels never need it.
+// Only the background channel -- a non-linear indicator of the full-resolution values (DRV:446-450) -- keeps the direct
+// path: indicator at full resolution (same arithmetic as the direct kernels, bit-exact), then the tap-by-tap blur.
+//   pass A (one CTA per (image, class)):  T = A_y m (H x P, also stored for pass B), min/max of Y = T A_x^T, never stored
+//   pass B (one CTA per row segment):     Y recomputed for every channel of a pixel, normalised, then either
+//                                         unary = -log(clip(softmax_c)) written pixel-major for the CRF (DRV:1057-1063),
+//                                         or the argmax label (blur-only mode, DRV:1018-1025), or the maps themselves.
+constexpr int kLrMaxP = 32;
+
+__global__ void lowrank_operator_kernel(float *__restrict__ Ay, float *__restrict__ AxT, unsigned *__restrict__ bg_keys, int n_bg, int H,
+                                        int W, int P, int PPAD, int lw, double sigma) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_bg) {  // reset the background maps' min/max keys (they are reduced by pass H of the direct blur)
+        bg_keys[2 * t + 0] = 0xffffffffu;
+        bg_keys[2 * t + 1] = 0u;
+    }
+    if (t >= H + W) return;
+    const bool is_y = t < H;
+    const int n = is_y ? H : W, pos = is_y ? t : t - H;
+    const float r = (n > 1) ? (float)(P - 1) / (float)(n - 1) : 0.f;  // align_corners=True scale, as upsample_write_kernel
+    double acc[kLrMaxP];
+#pragma unroll
+    for (int i = 0; i < kLrMaxP; ++i) acc[i] = 0.0;
+    double wsum = 0.0;
+    for (int j = -lw; j <= lw; ++j) wsum += exp(-0.5 / (sigma * sigma) * (double)(j * j));
+    for (int j = -lw; j <= lw; ++j) {
+        const double w = exp(-0.5 / (sigma * sigma) * (double)(j * j)) / wsum;   // scipy _gaussian_kernel1d, float64
+        const int src = reflect_index(pos + j, n);
+        const float sp = r * src;
+        const int i0 = min((int)sp, P - 1), i1 = min(i0 + 1, P - 1);
+        const float l = fminf(fmaxf(sp - i0, 0.f), 1.f), h = 1.f - l;
+        acc[i0] += w * (double)h;
+        acc[i1] += w * (double)l;
+    }
+    for (int i = 0; i < PPAD; ++i) {
+        const float v = (i < P) ? (float)acc[i] : 0.f;
+        if (is_y) Ay[(size_t)pos * PPAD + i] = v;
+        else AxT[(size_t)i * W + pos] = v;
+    }
+}
+
+// Y = sum_j t[j] * ax[j], j ascending, one fmaf chain: pass A and pass B must produce bit-identical values
+template <int PPAD>
+__device__ __forceinline__ float lr_dot(const float *__restrict__ t_row, const float (&ax)[PPAD]) {
+    float y = 0.f;
+#pragma unroll
+    for (int q = 0; q < PPAD / 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4 *>(t_row + 4 * q);
+        y = fmaf(t.x, ax[4 * q + 0], y);
+        y = fmaf(t.y, ax[4 * q + 1], y);
+        y = fmaf(t.z, ax[4 * q + 2], y);
+        y = fmaf(t.w, ax[4 * q + 3], y);
+    }
+    return y;
+}
+
+template <int PPAD>
+__global__ void __launch_bounds__(512) lowrank_minmax_kernel(const float *__restrict__ masked, const float *__restrict__ Ay,
+                                                             const float *__restrict__ AxT, float *__restrict__ T,
+                                                             float *__restrict__ norm, float *__restrict__ minmax_out, int C, int P,
+                                                             int H, int W, int rows_chunk, int out_channel_offset, int out_channels) {
+    extern __shared__ __align__(16) float lr_smem[];
+    float *s_m = lr_smem;                   // [PPAD][PPAD] the thresholded grid, zero padded
+    float *s_T = lr_smem + PPAD * PPAD;     // [rows_chunk][PPAD]
+    __shared__ float s_red[2][16];
+    __shared__ int s_nan;
+    const int c = blockIdx.x, b = blockIdx.y;
+    const float *m = masked + ((size_t)b * C + c) * P * P;
+    for (int e = threadIdx.x; e < PPAD * PPAD; e += blockDim.x) {
+        const int i = e / PPAD, j = e - i * PPAD;
+        s_m[e] = (i < P && j < P) ? m[i * P + j] : 0.f;
+    }
+    if (threadIdx.x == 0) s_nan = 0;
+    float mn = INFINITY, mx = -INFINITY;
+    bool has_nan = false;
+    float *Tc = T + ((size_t)b * C + c) * H * PPAD;
+    for (int y0 = 0; y0 < H; y0 += rows_chunk) {
+        const int rows = min(rows_chunk, H - y0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < rows * PPAD; e += blockDim.x) {   // T[y][j] = sum_i Ay[y][i] m[i][j]
+            const int y = e / PPAD, j = e - y * PPAD;
+            const float *a = Ay + (size_t)(y0 + y) * PPAD;
+            float acc = 0.f;
+            for (int i = 0; i < P; ++i) acc = fmaf(__ldg(a + i), s_m[i * PPAD + j], acc);
+            s_T[e] = acc;
+            Tc[(size_t)y0 * PPAD + e] = acc;
+        }
+        __syncthreads();
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            float ax[PPAD];
+#pragma unroll
+            for (int j = 0; j < PPAD; ++j) ax[j] = __ldg(AxT + (size_t)j * W + x);
+            for (int y = 0; y < rows; ++y) {
+                const float v = lr_dot<PPAD>(s_T + y * PPAD, ax);
+                has_nan = has_nan || (v != v);
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (has_nan) s_nan = 1;
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = mn; s_red[1][threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)((blockDim.x + 31) >> 5); ++w) { mn = fminf(mn, s_red[0][w]); mx = fmaxf(mx, s_red[1][w]); }
+        if (s_nan) mn = mx = __int_as_float(0x7fc00000);
+        const size_t k = (size_t)b * C + c;
+        norm[2 * k + 0] = mn;
+        norm[2 * k + 1] = __fdiv_rn(1.0f, __fsub_rn(mx, mn));   // 1/0 = inf: a constant map normalises to 0 * inf = NaN (0/0 in DRV:1152)
+        if (minmax_out) {
+            const size_t ko = (size_t)b * out_channels + out_channel_offset + c;
+            minmax_out[2 * ko + 0] = mn;
+            minmax_out[2 * ko + 1] = mx;
+        }
+    }
+}
+
+constexpr float kUnaryClipHi = 11.512925464970229f;  // -log(1e-5): np.clip(p, 1e-5, 1) seen from the log side
+
+template <int PPAD>
+__global__ void __launch_bounds__(128) lowrank_unary_kernel(const float *__restrict__ T, const float *__restrict__ AxT,
+                                                            const float *__restrict__ norm, const float *__restrict__ bg_blur,
+                                                            const float *__restrict__ bg_minmax, float *__restrict__ unary,
+                                                            int32_t *__restrict__ labels, float *__restrict__ maps_out, int C, int H,
+                                                            int W, int with_bg, int Cp) {
+    extern __shared__ __align__(16) float lr_smem[];
+    const int TP = blockDim.x;
+    const int Cc = C + with_bg;
+    const int pitch = Cp + 1;
+    float *s_T = lr_smem;                        // [C][PPAD] row y of every channel's T
+    float *s_norm = s_T + (size_t)C * PPAD;      // [C][2]
+    float *s_tile = s_norm + 2 * C;              // [TP][Cp + 1]
+    const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * TP;
+    const int x = x0 + threadIdx.x;
+    const size_t N = (size_t)H * W;
+    for (int e = threadIdx.x; e < C * PPAD; e += TP) {
+        const int c = e / PPAD, j = e - c * PPAD;
+        s_T[e] = T[(((size_t)b * C + c) * H + y) * PPAD + j];
+    }
+    for (int e = threadIdx.x; e < 2 * C; e += TP) s_norm[e] = norm[(size_t)b * C * 2 + e];
+    __syncthreads();
+    float *row = s_tile + threadIdx.x * pitch;
+    if (x < W) {
+        float ax[PPAD];
+#pragma unroll
+        for (int j = 0; j < PPAD; ++j) ax[j] = __ldg(AxT + (size_t)j * W + x);
+        float mxv = -INFINITY;
+        bool has_nan = false;
+        if (with_bg) {
+            const float mn = bg_minmax[2 * b], hi = bg_minmax[2 * b + 1];
+            const float v = __fmul_rn(__fsub_rn(bg_blur[(size_t)b * N + (size_t)y * W + x], mn), __fdiv_rn(1.0f, __fsub_rn(hi, mn)));
+            row[0] = v;
+            has_nan = v != v;
+            mxv = fmaxf(mxv, v);
+        }
+        for (int c = 0; c < C; ++c) {
+            const float yv = lr_dot<PPAD>(s_T + c * PPAD, ax);
+            const float v = __fmul_rn(__fsub_rn(yv, s_norm[2 * c]), s_norm[2 * c + 1]);   // (y - min) / (max - min), DRV:1151-1152
+            row[with_bg + c] = v;
+            has_nan = has_nan || (v != v);
+            mxv = fmaxf(mxv, v);
+        }
+        if (maps_out) {
+            float *mo = maps_out + (size_t)b * Cc * N + (size_t)y * W + x;
+            for (int c = 0; c < Cc; ++c) mo[(size_t)c * N] = row[c];
+        }
+        if (labels) {   // np.argmax / torch.argmax: first maximum, NaN counts as the maximum and the first NaN wins
+            float best = row[0];
+            int bi = 0;
+            for (int c = 1; c < Cc; ++c) {
+                const float v = row[c];
+                if (!(best != best) && (v > best || v != v)) { best = v; bi = c; }
+            }
+            labels[(size_t)b * N + (size_t)y * W + x] = bi;
+        }
+        if (unary) {
+            // U_c = -log(clip(softmax_c(v), 1e-5, 1)) = clamp(log(sum_k e^(v_k - max)) - (v_c - max), 0, -log 1e-5): one log per
+            // pixel and no division instead of a division and a log per channel
+            float sum = 0.f;
+            for (int c = 0; c < Cc; ++c) sum += __expf(row[c] - mxv);
+            const float lse = __logf(sum);
+            for (int c = 0; c < Cc; ++c) {
+                const float u = fminf(fmaxf(lse - (row[c] - mxv), 0.f), kUnaryClipHi);
+                row[c] = has_nan ? __int_as_float(0x7fc00000) : u;   // softmax of a column holding a NaN is NaN everywhere
+            }
+            for (int c = Cc; c < Cp; ++c) row[c] = 0.f;
+        }
+    }
+    if (!unary) return;
+    __syncthreads();
+    const int n_here = min(TP, W - x0);
+    float *ub = unary + ((size_t)b * N + (size_t)y * W + x0) * Cp;
+    for (int i = threadIdx.x; i < n_here * Cp; i += TP) {
+        const int pp = i / Cp, c = i - pp * Cp;
+        ub[i] = s_tile[pp * pitch + c];
+    }
+}
+
 static inline int blur_radius(double sigma) { return (int)(4.0 * sigma + 0.5); }  // scipy: int(truncate * sd + 0.5)
 static inline int blur_padded_taps(int lw) { return (int)align_up((size_t)(2 * lw + 1), 8) + kTapPad; }
 
@@ -513,9 +726,8 @@ bool make_blur_plan(int n_maps, int H, int W, double sigma, BlurPlan &p) {
         p.smem_v_tma = (p.n_w_padded + (p.tile_rows_tma + fixed_rows) * kTCols) * sizeof(float);
     }
     // pass H: full rows if they fit, else column tiles
-    // one warp per 16-column group so that a tile is one sweep (336 columns: 21 warps instead of 16 + 5 in two sweeps);
-    // PNP_BLUR_H_GROUPS caps the warps per CTA (16 = the former fixed shape)
-    static const int groups_cap = std::min(kHGroupsMax, std::max(1, getenv("PNP_BLUR_H_GROUPS") ? atoi(getenv("PNP_BLUR_H_GROUPS")) : kHGroupsMax));
+    // one warp per 16-column group so that a tile is one sweep (336 columns: 21 warps instead of 16 + 5 in two sweeps)
+    const int groups_cap = kHGroupsMax;
     size_t out_floats = (size_t)kHRows * (groups_cap * kHCols + 1);  // worst case while the tile width is being chosen
     size_t max_pitch = (kSmemBudget - (p.n_w_padded + out_floats) * sizeof(float)) / (kHRows * sizeof(float));
     size_t fixed_cols = 2 * (size_t)p.lw + kTapPad + kHCols;
@@ -541,29 +753,26 @@ extern "C" size_t pnp_gaussian_blur_workspace_bytes(int n_maps, int H, int W, do
     return make_blur_plan(n_maps, H, W, sigma, p) ? p.total : 0;
 }
 
-extern "C" int pnp_gaussian_blur(const float *in, float *out, float *minmax, void *workspace, size_t workspace_bytes,
-                                 int n_maps, int H, int W, double sigma, int normalize, pnp_stream_t stream) {
-    BlurPlan p;
-    if (!in || !out || !minmax || !workspace || in == out || !make_blur_plan(n_maps, H, W, sigma, p)) return PNP_ERR_INVALID_ARGUMENT;
-    if (workspace_bytes < p.total) return PNP_ERR_WORKSPACE;
-    if (n_maps == 0) return PNP_OK;
-    if (n_maps > 65535) return PNP_ERR_INVALID_ARGUMENT;
-    cudaStream_t st = as_stream(stream);
-    char *ws = reinterpret_cast<char *>(workspace);
-    float *weights = reinterpret_cast<float *>(ws);
-    unsigned *keys = reinterpret_cast<unsigned *>(ws + p.off_keys);
-    float *tmp = reinterpret_cast<float *>(ws + p.off_tmp);
-    cudaError_t e = cudaFuncSetAttribute(blur_vertical_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_v);
+namespace {
+// one-time opt-in to > 48 KB of dynamic shared memory per kernel (a function attribute, not data: set once per process)
+template <typename K>
+inline cudaError_t allow_smem(K kernel, size_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// enqueue prologue (weights + key reset) + pass V + pass H + key decode (+ normalisation)
+int blur_impl(const float *in, float *out, float *minmax, float *weights, unsigned *keys, float *tmp, const BlurPlan &p, int n_maps,
+              int H, int W, double sigma, int normalize, cudaStream_t st) {
+    cudaError_t e = allow_smem(blur_vertical_kernel, p.smem_v);
     if (e != cudaSuccess) return cuda_err(e);
     // up to 21 warps (tiles of <= 336 columns) two CTAs share an SM: cap the registers for that; wider tiles own the SM
     const bool h_pair = p.h_groups <= 21 && 2 * (p.smem_h + 1024) <= 227 * 1024;
-    e = h_pair ? cudaFuncSetAttribute(blur_horizontal_kernel<21, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_h)
-               : cudaFuncSetAttribute(blur_horizontal_kernel<kHGroupsMax, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_h);
+    e = h_pair ? allow_smem(blur_horizontal_kernel<21, 2>, p.smem_h) : allow_smem(blur_horizontal_kernel<kHGroupsMax, 1>, p.smem_h);
     if (e != cudaSuccess) return cuda_err(e);
     blur_prologue_kernel<<<1, 256, 0, st>>>(weights, keys, n_maps, p.lw, p.n_w_padded, sigma);
     const bool tma_ok = p.tile_rows_tma > 0 && (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
     if (tma_ok) {
-        e = cudaFuncSetAttribute(blur_vertical_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_v_tma);
+        e = allow_smem(blur_vertical_tma_kernel, p.smem_v_tma);
         if (e != cudaSuccess) return cuda_err(e);
         PNP_LAUNCH(kBlurVertical, st, blur_vertical_tma_kernel<<<dim3(ceil_div(W, kTCols), ceil_div(H, p.tile_rows_tma), n_maps), kTCols * kTGroups, p.smem_v_tma, st>>>(
             in, tmp, weights, H, W, p.lw, p.tile_rows_tma, p.n_w_padded));
@@ -585,4 +794,138 @@ extern "C" int pnp_gaussian_blur(const float *in, float *out, float *minmax, voi
         PNP_LAUNCH(kBlurNormalize, st, blur_normalize_kernel<<<grid, 256, 0, st>>>(out, minmax, (long long)H * W, total));
     }
     return launch_status();
+}
+}  // namespace
+
+extern "C" int pnp_gaussian_blur(const float *in, float *out, float *minmax, void *workspace, size_t workspace_bytes,
+                                 int n_maps, int H, int W, double sigma, int normalize, pnp_stream_t stream) {
+    BlurPlan p;
+    if (!in || !out || !minmax || !workspace || in == out || !make_blur_plan(n_maps, H, W, sigma, p)) return PNP_ERR_INVALID_ARGUMENT;
+    if (workspace_bytes < p.total) return PNP_ERR_WORKSPACE;
+    if (n_maps == 0) return PNP_OK;
+    if (n_maps > 65535) return PNP_ERR_INVALID_ARGUMENT;
+    char *ws = reinterpret_cast<char *>(workspace);
+    return blur_impl(in, out, minmax, reinterpret_cast<float *>(ws), reinterpret_cast<unsigned *>(ws + p.off_keys),
+                     reinterpret_cast<float *>(ws + p.off_tmp), p, n_maps, H, W, sigma, normalize, as_stream(stream));
+}
+
+// ------------------------------------------------------------------------------------------------ fused low-rank entry point
+namespace {
+struct LowrankPlan {
+    BlurPlan blur;   // direct blur of the B background maps
+    int PPAD, rows_chunk, threads_a, tile_pix;
+    size_t smem_a, smem_b;
+    size_t off_masked, off_params, off_ay, off_axt, off_T, off_norm, off_bg, off_bgblur, off_bgmm, off_blur_ws, total;
+};
+
+bool make_lowrank_plan(int B, int C, int P, int H, int W, double sigma, int with_background, LowrankPlan &p) {
+    if (B < 0 || C < 1 || P < 1 || P > kLrMaxP || H < 1 || W < 1) return false;
+    if (!make_blur_plan(with_background ? B : 0, H, W, sigma, p.blur)) return false;
+    p.PPAD = P <= 24 ? 24 : (P <= 28 ? 28 : 32);
+    p.rows_chunk = std::min(H, 512);   // <= 64 KB of T per chunk
+    {   // pass A: one thread per column, as few sweeps over x as possible
+        const int sweeps = (W + 511) / 512;
+        p.threads_a = std::min(512, std::max(64, (int)align_up((size_t)((W + sweeps - 1) / sweeps), 32)));
+    }
+    p.smem_a = ((size_t)p.PPAD * p.PPAD + (size_t)p.rows_chunk * p.PPAD) * sizeof(float);
+    const int Cp = (C + (with_background ? 1 : 0) + 3) / 4 * 4;
+    p.tile_pix = Cp <= 64 ? 128 : 64;
+    p.smem_b = ((size_t)C * p.PPAD + 2 * (size_t)C + (size_t)p.tile_pix * (Cp + 1)) * sizeof(float);
+    if (p.smem_b > 200 * 1024) {
+        p.tile_pix = 32;
+        p.smem_b = ((size_t)C * p.PPAD + 2 * (size_t)C + (size_t)p.tile_pix * (Cp + 1)) * sizeof(float);
+        if (p.smem_b > 200 * 1024) return false;
+    }
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    p.off_masked = take((size_t)B * C * P * P * sizeof(float));
+    p.off_params = take((size_t)B * C * 2 * sizeof(float));
+    p.off_ay = take((size_t)H * p.PPAD * sizeof(float));
+    p.off_axt = take((size_t)W * p.PPAD * sizeof(float));
+    p.off_T = take((size_t)B * C * H * p.PPAD * sizeof(float));
+    p.off_norm = take((size_t)B * C * 2 * sizeof(float));
+    p.off_bg = take(with_background ? (size_t)B * H * W * sizeof(float) : 0);
+    p.off_bgblur = take(with_background ? (size_t)B * H * W * sizeof(float) : 0);
+    p.off_bgmm = take(with_background ? (size_t)B * 2 * sizeof(float) : 0);
+    p.off_blur_ws = take(with_background ? p.blur.total : 0);
+    p.total = off;
+    return true;
+}
+
+template <int PPAD>
+int launch_lowrank(const LowrankPlan &p, char *ws, float *unary, int32_t *labels, float *maps_out, float *minmax_out, int B, int C,
+                   int P, int H, int W, int with_background, cudaStream_t st) {
+    const float *masked = reinterpret_cast<const float *>(ws + p.off_masked);
+    const float *Ay = reinterpret_cast<const float *>(ws + p.off_ay), *AxT = reinterpret_cast<const float *>(ws + p.off_axt);
+    float *T = reinterpret_cast<float *>(ws + p.off_T), *norm = reinterpret_cast<float *>(ws + p.off_norm);
+    const int Cc = C + (with_background ? 1 : 0), Cp = (Cc + 3) / 4 * 4;
+    cudaError_t e = allow_smem(lowrank_minmax_kernel<PPAD>, p.smem_a);
+    if (e != cudaSuccess) return cuda_err(e);
+    e = allow_smem(lowrank_unary_kernel<PPAD>, p.smem_b);
+    if (e != cudaSuccess) return cuda_err(e);
+    PNP_LAUNCH(kLowrankBlur, st, (lowrank_minmax_kernel<PPAD><<<dim3(C, B), p.threads_a, p.smem_a, st>>>(
+        masked, Ay, AxT, T, norm, minmax_out, C, P, H, W, p.rows_chunk, with_background ? 1 : 0, Cc)));
+    PNP_LAUNCH(kLowrankUnary, st, (lowrank_unary_kernel<PPAD><<<dim3(ceil_div(W, p.tile_pix), H, B), p.tile_pix, p.smem_b, st>>>(
+        T, AxT, norm, with_background ? reinterpret_cast<const float *>(ws + p.off_bgblur) : nullptr,
+        with_background ? reinterpret_cast<const float *>(ws + p.off_bgmm) : nullptr, unary, labels, maps_out, C, H, W,
+        with_background ? 1 : 0, Cp)));
+    return launch_status();
+}
+}  // namespace
+
+extern "C" size_t pnp_lowrank_blur_workspace_bytes(int B, int C, int P, int H, int W, double sigma, int with_background) {
+    LowrankPlan p;
+    return make_lowrank_plan(B, C, P, H, W, sigma, with_background, p) ? p.total : 0;
+}
+
+extern "C" int pnp_lowrank_blur_unary(const float *class_maps, float *unary, int32_t *labels, float *maps_out, float *minmax_out,
+                                      void *workspace, size_t workspace_bytes, int B, int C, int P, int H, int W, float threshold,
+                                      int rescale, int with_background, double sigma, pnp_stream_t stream) {
+    LowrankPlan p;
+    if (!class_maps || !workspace || (!unary && !labels && !maps_out) || B > 65535 || H > 65535 ||
+        !make_lowrank_plan(B, C, P, H, W, sigma, with_background, p))
+        return PNP_ERR_INVALID_ARGUMENT;
+    if (workspace_bytes < p.total) return PNP_ERR_WORKSPACE;
+    if (B == 0) return PNP_OK;
+    cudaStream_t st = as_stream(stream);
+    char *ws = reinterpret_cast<char *>(workspace);
+    float *masked = reinterpret_cast<float *>(ws + p.off_masked), *params = reinterpret_cast<float *>(ws + p.off_params);
+    // Scale_0_1 only matters for the background test (it cancels in every class channel, see above); with ONE class the
+    // reference's rescale silently does not happen (DRV:1079-1080), as in pnp_threshold_upsample
+    const int bg_rescale = (rescale && with_background && C > 1) ? 1 : 0;
+    char *bws = ws + p.off_blur_ws;
+    lowrank_operator_kernel<<<ceil_div(H + W, 128), 128, 0, st>>>(reinterpret_cast<float *>(ws + p.off_ay), reinterpret_cast<float *>(ws + p.off_axt),
+                                                                 reinterpret_cast<unsigned *>(bws + p.blur.off_keys), 0, H, W, P, p.PPAD,
+                                                                 p.blur.lw, sigma);
+    PNP_LAUNCH(kThresholdPrep, st, threshold_prep_kernel<<<dim3(C, B), 256, 0, st>>>(class_maps, masked, params, C, P, H, W, threshold, bg_rescale));
+    int rc = launch_status();
+    if (rc != PNP_OK) return rc;
+    if (with_background) {
+        float *bg = reinterpret_cast<float *>(ws + p.off_bg);
+        const bool vec = (W % 4 == 0);
+        const int per = vec ? H * (W / 4) : H * W;
+        const int gx = std::max(1, std::min(ceil_div(per, 256), ceil_div(kNumSMs * 8, B)));
+        if (vec)
+            PNP_LAUNCH(kUpsampleWrite, st, (upsample_write_kernel<4, true><<<dim3(gx, B), 256, 0, st>>>(masked, params, bg, C, P, H, W, bg_rescale, 1)));
+        else
+            PNP_LAUNCH(kUpsampleWrite, st, (upsample_write_kernel<1, true><<<dim3(gx, B), 256, 0, st>>>(masked, params, bg, C, P, H, W, bg_rescale, 1)));
+        const bool timed = prof::on(kBackgroundBlur, st);
+        if (timed) prof::begin(kBackgroundBlur, st);
+        rc = blur_impl(bg, reinterpret_cast<float *>(ws + p.off_bgblur), reinterpret_cast<float *>(ws + p.off_bgmm),
+                       reinterpret_cast<float *>(bws), reinterpret_cast<unsigned *>(bws + p.blur.off_keys),
+                       reinterpret_cast<float *>(bws + p.blur.off_tmp), p.blur, B, H, W, sigma, 0, st);
+        if (timed) prof::end(kBackgroundBlur, st);
+        if (rc != PNP_OK) return rc;
+        if (minmax_out) {   // channel 0 of each image = the background map's (min, max)
+            const int Cc = C + 1;
+            cudaError_t e = cudaMemcpy2DAsync(minmax_out, (size_t)Cc * 2 * sizeof(float), ws + p.off_bgmm, 2 * sizeof(float),
+                                              2 * sizeof(float), B, cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return cuda_err(e);
+        }
+    }
+    switch (p.PPAD) {
+        case 24: return launch_lowrank<24>(p, ws, unary, labels, maps_out, minmax_out, B, C, P, H, W, with_background, st);
+        case 28: return launch_lowrank<28>(p, ws, unary, labels, maps_out, minmax_out, B, C, P, H, W, with_background, st);
+        default: return launch_lowrank<32>(p, ws, unary, labels, maps_out, minmax_out, B, C, P, H, W, with_background, st);
+    }
 }

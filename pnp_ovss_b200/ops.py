@@ -145,6 +145,39 @@ def gaussian_blur(maps, sigma, normalize=True):
     return out, minmax
 
 
+def lowrank_blur_unary(class_maps, H, W, threshold, rescale, with_background, sigma, unary=True, labels=False, maps=False, minmax=False):
+    """Fused threshold -> upsample -> background -> blur -> min-max -> {CRF unary | argmax labels | maps} for class_maps
+    [B,C,P,P] (pnp_lowrank_blur_unary).  Returns a dict with the requested outputs: "unary" [B,N,Cp], "labels" int32 [B,N],
+    "maps" [B,C',H,W], "minmax" [B*C',2]."""
+    _req(class_maps, torch.float32, "class_maps", 4)
+    B, C, P, P2 = class_maps.shape
+    if P != P2:
+        raise PnpError("class_maps must be [B,C,P,P]")
+    lib = _lib.load()
+    ws_bytes = lib.pnp_lowrank_blur_workspace_bytes(B, C, P, int(H), int(W), float(sigma), int(bool(with_background)))
+    if ws_bytes == 0:
+        raise PnpError("unsupported low-rank blur configuration (P=%d, H=%d, W=%d, sigma=%r)" % (P, H, W, sigma))
+    dev = class_maps.device
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    Cc = C + (1 if with_background else 0)
+    N = int(H) * int(W)
+    out = {}
+    if unary:
+        out["unary"] = torch.empty((B, N, crf_pad_channels(Cc)), dtype=torch.float32, device=dev)
+    if labels:
+        out["labels"] = torch.empty((B, N), dtype=torch.int32, device=dev)
+    if maps:
+        out["maps"] = torch.empty((B, Cc, int(H), int(W)), dtype=torch.float32, device=dev)
+    if minmax:
+        out["minmax"] = torch.empty((B * Cc, 2), dtype=torch.float32, device=dev)
+    if not (unary or labels or maps):
+        raise PnpError("nothing to compute")
+    check(lib.pnp_lowrank_blur_unary(_p(class_maps), _p(out.get("unary")), _p(out.get("labels")), _p(out.get("maps")), _p(out.get("minmax")),
+                                     _p(ws), ws_bytes, B, C, P, int(H), int(W), float(threshold), int(bool(rescale)),
+                                     int(bool(with_background)), float(sigma), _stream()), "pnp_lowrank_blur_unary")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- (e)
 class LatticeHandle:
     """A finished permutohedral lattice in device memory (owns its storage tensor)."""

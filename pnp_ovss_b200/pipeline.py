@@ -11,6 +11,10 @@ from ._lib import PnpError
 CRF_DEFAULTS = dict(n_iter=10, pos_w=7.0, pos_xy_std=3.0, bi_w=10.0, bi_xy_std=50.0, bi_rgb_std=5.0)  # DRV:1036-1041
 BLUR_SCALE = 0.05  # DRV:1009
 SAVE_LEN = 10      # DRV:643
+# Blurred maps (--postprocess blur / blur+crf) take the fused low-rank kernel group (pnp_lowrank_blur_unary).  False selects the
+# direct kernels (full-resolution upsample, tap-by-tap blur of every channel, separate unary): ~10x slower, same results to
+# 5e-6 on the maps; kept because its summation order is the one the bit-exact golden confusion matrices were recorded with.
+USE_LOWRANK_BLUR = True
 
 
 # ---------------------------------------------------------------------------------------------- (c) loop
@@ -126,23 +130,35 @@ def postprocess_batch(class_maps, guides, gts, luts, hist, *, threshold, rescale
     luts int32 [B,C'] (composed relabel tables).  mode: the --postprocess string ('', 'blur', 'crf', 'blur+crf').
     bilateral: a lattice already built over `guides` (the two reference passes of one batch share it)."""
     B, C = class_maps.shape[:2]
+    P_grid = class_maps.shape[-1]
     H, W = gts.shape[1:]
     N = H * W
-    x = ops.threshold_upsample(class_maps.contiguous(), H, W, threshold, rescale, with_background)
-    _mark(stats, "upsample")
-    Cc = x.shape[1]
-    minmax = None
     use_blur = bool(mode) and "blur" in mode
     use_crf = bool(mode) and "crf" in mode
-    if use_blur:
-        x, minmax = ops.gaussian_blur(x, BLUR_SCALE * max(H, W), normalize=not use_crf)
-        _mark(stats, "blur")
-    if use_crf:
-        p = dict(CRF_DEFAULTS)
-        p.update(crf or {})
-        U = ops.crf_unary_from_maps(x.view(B, Cc, N), minmax if use_blur else None)
+    p = dict(CRF_DEFAULTS)
+    p.update(crf or {})
+    Cc = C + (1 if with_background else 0)
+    labels = U = None
+    if use_blur and P_grid <= 32 and USE_LOWRANK_BLUR:
+        # blurred maps: the whole (d) group as one fused low-rank launch group that emits the CRF unary (or the labels) directly
+        out = ops.lowrank_blur_unary(class_maps.contiguous(), H, W, threshold, rescale, with_background, BLUR_SCALE * max(H, W),
+                                     unary=use_crf, labels=not use_crf)
+        U, labels = out.get("unary"), out.get("labels")
+        _mark(stats, "upsample+blur+unary")
+    else:
+        x = ops.threshold_upsample(class_maps.contiguous(), H, W, threshold, rescale, with_background)
+        _mark(stats, "upsample")
+        minmax = None
+        if use_blur:
+            x, minmax = ops.gaussian_blur(x, BLUR_SCALE * max(H, W), normalize=not use_crf)
+            _mark(stats, "blur")
+        if use_crf:
+            U = ops.crf_unary_from_maps(x.view(B, Cc, N), minmax if use_blur else None)
+            _mark(stats, "unary")
+        else:
+            labels = ops.argmax_channels(x.view(B, Cc, N))
         del x
-        _mark(stats, "unary")
+    if use_crf:
         lat_s = _SPATIAL.get(H, W, p["pos_xy_std"], U.device)
         lat_b = bilateral if bilateral is not None else ops.build_lattice(H, W, p["bi_xy_std"], rgb=guides, srgb=p["bi_rgb_std"])
         if stats is not None:
@@ -150,8 +166,6 @@ def postprocess_batch(class_maps, guides, gts, luts, hist, *, threshold, rescale
         _mark(stats, "lattice")
         _, labels = ops.crf_inference([lat_s, lat_b], [p["pos_w"], p["bi_w"]], U, Cc, p["n_iter"], want_labels=True)
         _mark(stats, "crf")
-    else:
-        labels = ops.argmax_channels(x.view(B, Cc, N))
     pred = torch.empty((B, N), dtype=torch.float32, device=labels.device) if return_labels else None
     ops.confusion_accumulate(labels, gts.view(B, N), n_class, hist, lut=luts, pred_out=pred, bad_count=bad_count)
     _mark(stats, "confusion")

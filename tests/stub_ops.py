@@ -52,6 +52,21 @@ def make(ops_module):
             x = torch.cat([(x.max(1, keepdim=True)[0] == 0).float(), x], 1)
         return x.contiguous()
 
+    def lowrank_blur_unary(class_maps, H, W, threshold, rescale, with_background, sigma, unary=True, labels=False, maps=False, minmax=False):
+        log("lowrank_blur_unary")
+        x = threshold_upsample(class_maps, H, W, threshold, rescale, with_background)
+        ns.calls.pop()
+        B, Cc = x.shape[:2]
+        out = {}
+        if unary:
+            out["unary"] = crf_unary_from_maps(x.view(B, Cc, H * W))
+            ns.calls.pop()
+        if labels:
+            out["labels"] = x.view(B, Cc, H * W).argmax(1).to(torch.int32)
+        if maps:
+            out["maps"] = x
+        return out
+
     def gaussian_blur(maps, sigma, normalize=True):
         log("gaussian_blur")
         n = maps.numel() // (maps.shape[-1] * maps.shape[-2])

@@ -260,10 +260,14 @@ def test_other_baseline_configs_properties(dev, ops, name, C, S, with_bg):
         assert int(bad.item()) == 0
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
     assert out[0][0].sum().item() == ((gts >= 0) & (gts < n)).sum().item()
-    # the fused path agrees with the step-by-step entry points (pack -> inference -> unpack -> argmax)
+    # the fused path agrees with the step-by-step entry points (unary -> inference -> unpack -> argmax)
+    U = ops.lowrank_blur_unary(maps, S, S, 0.15, True, with_bg, 0.05 * S)["unary"]
+    # ... and the direct kernels (full-resolution upsample, tap-by-tap blur, separate unary) give the same unary to fp32 rounding
     x = ops.threshold_upsample(maps, S, S, 0.15, True, with_bg)
     xb, mm = ops.gaussian_blur(x, 0.05 * S, normalize=False)
-    U = ops.crf_unary_from_maps(xb.view(B, Cc, S * S), mm)
+    U_direct = ops.crf_unary_from_maps(xb.view(B, Cc, S * S), mm)
+    assert not bool(U.isnan().any()) and (U - U_direct).abs().max().item() <= 5e-5
+    del x, xb, U_direct
     lat_s = ops.build_lattice(S, S, 3.0, device=dev)
     lat_b = ops.build_lattice(S, S, 50.0, rgb=guides, srgb=5.0)
     Q, labels = ops.crf_inference([lat_s, lat_b], [7.0, 10.0], U, Cc, 10)

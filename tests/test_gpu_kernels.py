@@ -390,3 +390,109 @@ def test_tripled_tf32_gemm_is_fp32_grade(dev, ops):
     torch.backends.cuda.matmul.allow_tf32 = prev
     assert err3 <= 4 * err32 + 1e-6, (err3, err32)
     assert err3 * 20 <= err_tf32, (err3, err_tf32)
+
+
+# ------------------------------------------------------------------------------------------------ (d) fused low-rank group
+def _oracle_blurred_maps(O, cm, thr, H, W, rescale, with_bg):
+    """DRV:424-455 then DRV:1005-1011 on the CPU: threshold, torch bilinear upsample, [Scale_0_1], background, scipy blur + min-max."""
+    with np.errstate(all="ignore"):
+        x = O.threshold_upsample(cm.clone(), thr, (H, W), rescale, with_bg)
+        return O.blur_channels(x.float(), (H, W)).numpy()
+
+
+LOWRANK_CASES = [  # C, P, H, W, rescale, with_background
+    (3, 21, 336, 336, False, True), (20, 21, 336, 336, True, True), (5, 21, 333, 500, False, False), (2, 24, 384, 384, True, True),
+    (7, 28, 448, 448, False, True), (4, 32, 512, 512, True, False), (1, 21, 100, 75, True, True), (9, 21, 500, 375, True, True)]
+
+
+@pytest.mark.parametrize("C,P,H,W,rescale,with_bg", LOWRANK_CASES)
+def test_lowrank_blur_matches_the_reference_chain(dev, ops, O, C, P, H, W, rescale, with_bg):
+    """One fused launch group against the reference's own chain (torch interpolate + scipy gaussian_filter + min-max): the
+    normalised blurred maps within 5e-6, the per-channel (min, max) of the raw blur, the CRF unary and the blur-only labels."""
+    B = 2
+    cms = torch.stack([synth.saliency_maps(100 * C + b + P, C, P) for b in range(B)])
+    out = ops.lowrank_blur_unary(cms.to(dev), H, W, 0.15, rescale, with_bg, 0.05 * max(H, W), unary=True, labels=True, maps=True, minmax=True)
+    Cc = C + (1 if with_bg else 0)
+    assert out["maps"].shape == (B, Cc, H, W) and out["unary"].shape == (B, H * W, (Cc + 3) // 4 * 4)
+    for b in range(B):
+        want = _oracle_blurred_maps(O, cms[b], 0.15, H, W, rescale, with_bg)
+        got = out["maps"][b].cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        assert np.abs(got[ok] - want[ok]).max() <= 5e-6, np.abs(got[ok] - want[ok]).max()
+        # unary = -log(clip(softmax_c, 1e-5, 1)) of those maps (DRV:1057-1063), pixel-major, padding channels zero
+        with np.errstate(all="ignore"):
+            sm = torch.softmax(torch.from_numpy(want), 0).numpy()
+            U = -np.log(np.clip(sm, 1e-5, 1.0)).reshape(Cc, H * W).T
+        gotU = out["unary"][b].cpu().numpy()
+        assert np.array_equal(np.isnan(gotU[:, :Cc]), np.isnan(U))
+        okU = ~np.isnan(U)      # (with Scale_0_1 and many classes the background channel is empty -> 0/0 -> every unary is NaN)
+        assert not okU.any() or np.abs(gotU[:, :Cc][okU] - U[okU]).max() <= 3e-5
+        assert not gotU[:, Cc:].any()
+        # blur-only labels: argmax of the normalised maps; a handful of pixels may sit on a numerical tie
+        lab = out["labels"][b].cpu().numpy().reshape(H, W)
+        if not np.isnan(want).any():
+            assert (lab != want.argmax(0)).mean() <= 2e-4
+            srt = np.sort(want, 0)
+            clear = (srt[-1] - srt[-2] > 1e-4) if Cc > 1 else np.ones((H, W), bool)
+            assert np.array_equal(lab[clear], want.argmax(0)[clear])          # wherever the winner is clear the label is exact
+    # background indicator: bit-exact wherever the direct kernels' upsample says so (it is the same arithmetic)
+    if with_bg:
+        direct = ops.threshold_upsample(cms.to(dev), H, W, 0.15, rescale, True)
+        blurred, mm = ops.gaussian_blur(direct[:, :1].contiguous(), 0.05 * max(H, W), normalize=False)
+        got_mm = out["minmax"].view(B, Cc, 2)[:, 0]
+        assert torch.equal(got_mm, mm.view(B, 2))
+
+
+def test_lowrank_blur_equals_the_direct_kernels(dev, ops):
+    """The fused path against the direct one (pnp_threshold_upsample -> pnp_gaussian_blur -> pnp_crf_unary_from_maps) at the
+    benchmark shape: same unary within 3e-5 -- the two differ only in fp32 summation order."""
+    B, C, P, S = 3, 20, 21, 336
+    cms = torch.stack([synth.saliency_maps(7 + b, C, P) for b in range(B)])
+    cms[:, :, :5, :5] = 0     # a corner no class claims: the background channel is not empty (an empty one is 0/0 = NaN everywhere)
+    cms = cms.to(dev)
+    for rescale in (False, True):
+        out = ops.lowrank_blur_unary(cms, S, S, 0.15, rescale, True, 0.05 * S, unary=True, maps=True)
+        x = ops.threshold_upsample(cms, S, S, 0.15, rescale, True)
+        xb, mm = ops.gaussian_blur(x, 0.05 * S, normalize=False)
+        U = ops.crf_unary_from_maps(xb.view(B, C + 1, S * S), mm)
+        assert torch.equal(out["unary"].isnan(), U.isnan())
+        assert torch.nan_to_num(out["unary"] - U).abs().max().item() <= 3e-5
+        xn, _ = ops.gaussian_blur(x, 0.05 * S, normalize=True)
+        assert torch.equal(out["maps"].isnan(), xn.isnan())
+        assert torch.nan_to_num(out["maps"] - xn).abs().max().item() <= 5e-6
+        if not rescale:
+            assert not bool(U.isnan().any())        # the comparison is not vacuous
+
+
+def test_lowrank_blur_nan_and_single_class_quirks(dev, ops, O):
+    """A class whose map is constant thresholds to all zeros (0/0 -> NaN -> False, DRV:425-433): its blurred channel is 0/0 = NaN
+    (DRV:1151-1152), the unary of every channel of those pixels is NaN and argmax picks the first NaN channel -- as in the
+    reference chain.  With one class Scale_0_1 silently does not happen (DRV:1079-1080)."""
+    P, S = 21, 96
+    cm = synth.saliency_maps(5, 3, P)
+    cm[1] = 0.25                                    # constant -> dropped class
+    out = ops.lowrank_blur_unary(cm[None].to(dev), S, S, 0.15, True, True, 0.05 * S, unary=True, labels=True, maps=True)
+    want = _oracle_blurred_maps(O, cm, 0.15, S, S, True, True)
+    got = out["maps"][0].cpu().numpy()
+    assert np.isnan(want[2]).all() and np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert ok.any() and np.abs(got[ok] - want[ok]).max() <= 5e-6
+    assert bool(out["unary"][0, :, :4].isnan().all()) and not out["unary"][0, :, 4:].any()
+    first_nan = int(np.isnan(want).all(axis=(1, 2)).argmax())
+    assert bool((out["labels"][0] == first_nan).all())      # numpy/torch argmax: the (first) NaN channel wins
+    one = synth.saliency_maps(6, 1, P)
+    out1 = ops.lowrank_blur_unary(one[None].to(dev), S, S, 0.15, True, True, 0.05 * S, unary=False, maps=True)
+    want1 = _oracle_blurred_maps(O, one, 0.15, S, S, True, True)
+    assert np.abs(out1["maps"][0].cpu().numpy() - want1).max() <= 5e-6
+
+
+def test_lowrank_blur_rejects_bad_arguments(dev, ops):
+    from pnp_ovss_b200 import PnpError
+    cm = torch.zeros(1, 2, 33, 33, device=dev)
+    with pytest.raises(PnpError):
+        ops.lowrank_blur_unary(cm, 64, 64, 0.15, False, True, 3.2)            # P > 32
+    with pytest.raises(PnpError):
+        ops.lowrank_blur_unary(torch.zeros(1, 2, 21, 21, device=dev), 64, 64, 0.15, False, True, 0.0)   # sigma must be positive
+    with pytest.raises(PnpError):
+        ops.lowrank_blur_unary(torch.zeros(1, 2, 21, 21), 64, 64, 0.15, False, True, 3.2)               # CPU tensor

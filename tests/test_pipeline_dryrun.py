@@ -56,7 +56,8 @@ def test_batch_confusion_composes_on_the_host(pipe, mode, drop_iter, coco):
     assert all(v.shape == (3, 48, 48) for v in labels.values())
     assert stub.calls.count("token_merge") == n_passes == stub.calls.count("confusion_accumulate")
     assert stub.calls.count("crf_inference") == (n_passes if "crf" in mode else 0)
-    assert stub.calls.count("gaussian_blur") == (n_passes if "blur" in mode else 0)
+    assert stub.calls.count("lowrank_blur_unary") == (n_passes if "blur" in mode else 0)     # the fused (d) group
+    assert stub.calls.count("gaussian_blur") == 0 and stub.calls.count("threshold_upsample") == (0 if "blur" in mode else n_passes)
     assert stub.calls.count("build_lattice") == (2 if "crf" in mode else 0)          # one bilateral (shared by both passes) + one spatial
     assert stub.calls.count("salience_dropout_round") == (drop_iter if drop_iter > 1 else 0)
     assert (chosen is None) == (drop_iter == 1)
