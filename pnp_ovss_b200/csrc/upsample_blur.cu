@@ -131,6 +131,14 @@ __global__ void __launch_bounds__(256) upsample_write_kernel(const float *__rest
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { vmax[v] = -INFINITY; vnan[v] = false; }
         for (int c = 0; c < C; ++c) {
+            if (kBgOnly) {
+                // background = (no NaN) && (max over classes == 0): a pixel is decided (not background) as soon as one class
+                // is positive or NaN, and dense maps decide every pixel within the first few classes
+                bool all_decided = true;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) all_decided = all_decided && (vnan[v] || vmax[v] > 0.f);
+                if (all_decided) break;
+            }
             const float *g = grid0 + c * PP;
             float mn = 0.f, rg = 1.f;
             if (rescale) { mn = scale_params[((long long)b * C + c) * 2]; rg = scale_params[((long long)b * C + c) * 2 + 1]; }
@@ -467,13 +475,26 @@ __global__ void __launch_bounds__(256) blur_normalize_kernel(float *__restrict__
 //                                         or the argmax label (blur-only mode, DRV:1018-1025), or the maps themselves.
 constexpr int kLrMaxP = 32;
 
-__global__ void lowrank_operator_kernel(float *__restrict__ Ay, float *__restrict__ AxT, unsigned *__restrict__ bg_keys, int n_bg, int H,
-                                        int W, int P, int PPAD, int lw, double sigma) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n_bg) {  // reset the background maps' min/max keys (they are reduced by pass H of the direct blur)
-        bg_keys[2 * t + 0] = 0xffffffffu;
-        bg_keys[2 * t + 1] = 0u;
+__global__ void __launch_bounds__(128) lowrank_operator_kernel(float *__restrict__ Ay, float *__restrict__ AxT, int H, int W, int P,
+                                                               int PPAD, int lw, double sigma) {
+    extern __shared__ double s_w[];   // [2 lw + 1] Gaussian weights (float64, scipy _gaussian_kernel1d), built by the whole CTA
+    __shared__ double s_part[128];
+    const int taps = 2 * lw + 1;
+    double part = 0.0;
+    for (int j = threadIdx.x; j < taps; j += blockDim.x) {
+        const double x = (double)(j - lw);
+        const double w = exp(-0.5 / (sigma * sigma) * (x * x));
+        s_w[j] = w;
+        part += w;
     }
+    s_part[threadIdx.x] = part;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s_part[threadIdx.x] += s_part[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double inv_sum = 1.0 / s_part[0];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= H + W) return;
     const bool is_y = t < H;
     const int n = is_y ? H : W, pos = is_y ? t : t - H;
@@ -481,11 +502,9 @@ __global__ void lowrank_operator_kernel(float *__restrict__ Ay, float *__restric
     double acc[kLrMaxP];
 #pragma unroll
     for (int i = 0; i < kLrMaxP; ++i) acc[i] = 0.0;
-    double wsum = 0.0;
-    for (int j = -lw; j <= lw; ++j) wsum += exp(-0.5 / (sigma * sigma) * (double)(j * j));
-    for (int j = -lw; j <= lw; ++j) {
-        const double w = exp(-0.5 / (sigma * sigma) * (double)(j * j)) / wsum;   // scipy _gaussian_kernel1d, float64
-        const int src = reflect_index(pos + j, n);
+    for (int j = 0; j < taps; ++j) {
+        const double w = s_w[j] * inv_sum;
+        const int src = reflect_index(pos + j - lw, n);
         const float sp = r * src;
         const int i0 = min((int)sp, P - 1), i1 = min(i0 + 1, P - 1);
         const float l = fminf(fmaxf(sp - i0, 0.f), 1.f), h = 1.f - l;
@@ -550,7 +569,15 @@ __global__ void __launch_bounds__(512) lowrank_minmax_kernel(const float *__rest
             float ax[PPAD];
 #pragma unroll
             for (int j = 0; j < PPAD; ++j) ax[j] = __ldg(AxT + (size_t)j * W + x);
-            for (int y = 0; y < rows; ++y) {
+            int y = 0;
+            for (; y + 1 < rows; y += 2) {   // two independent FMA chains in flight
+                const float v0 = lr_dot<PPAD>(s_T + y * PPAD, ax);
+                const float v1 = lr_dot<PPAD>(s_T + (y + 1) * PPAD, ax);
+                has_nan = has_nan || (v0 != v0) || (v1 != v1);
+                mn = fminf(mn, fminf(v0, v1));
+                mx = fmaxf(mx, fmaxf(v0, v1));
+            }
+            if (y < rows) {
                 const float v = lr_dot<PPAD>(s_T + y * PPAD, ax);
                 has_nan = has_nan || (v != v);
                 mn = fminf(mn, v);
@@ -590,18 +617,21 @@ __global__ void __launch_bounds__(128) lowrank_unary_kernel(const float *__restr
     extern __shared__ __align__(16) float lr_smem[];
     const int TP = blockDim.x;
     const int Cc = C + with_bg;
-    const int pitch = Cp + 1;
+    const int pitch = Cp + 1;                    // odd: thread-per-row accesses hit 32 different banks
     float *s_T = lr_smem;                        // [C][PPAD] row y of every channel's T
-    float *s_norm = s_T + (size_t)C * PPAD;      // [C][2]
-    float *s_tile = s_norm + 2 * C;              // [TP][Cp + 1]
+    float2 *s_norm = reinterpret_cast<float2 *>(s_T + (size_t)C * PPAD);   // [C] (min, 1/(max-min))
+    float *s_tile = reinterpret_cast<float *>(s_norm + C);                 // [TP][Cp + 1]
     const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * TP;
     const int x = x0 + threadIdx.x;
     const size_t N = (size_t)H * W;
-    for (int e = threadIdx.x; e < C * PPAD; e += TP) {
-        const int c = e / PPAD, j = e - c * PPAD;
-        s_T[e] = T[(((size_t)b * C + c) * H + y) * PPAD + j];
+    {   // T rows of all channels: C segments of PPAD contiguous floats, copied as float4
+        const int q_per = PPAD / 4;
+        for (int e = threadIdx.x; e < C * q_per; e += TP) {
+            const int c = e / q_per, q = e - c * q_per;
+            reinterpret_cast<float4 *>(s_T)[e] = __ldg(reinterpret_cast<const float4 *>(T + (((size_t)b * C + c) * H + y) * PPAD) + q);
+        }
     }
-    for (int e = threadIdx.x; e < 2 * C; e += TP) s_norm[e] = norm[(size_t)b * C * 2 + e];
+    for (int e = threadIdx.x; e < C; e += TP) s_norm[e] = __ldg(reinterpret_cast<const float2 *>(norm) + (size_t)b * C + e);
     __syncthreads();
     float *row = s_tile + threadIdx.x * pitch;
     if (x < W) {
@@ -609,19 +639,19 @@ __global__ void __launch_bounds__(128) lowrank_unary_kernel(const float *__restr
 #pragma unroll
         for (int j = 0; j < PPAD; ++j) ax[j] = __ldg(AxT + (size_t)j * W + x);
         float mxv = -INFINITY;
-        bool has_nan = false;
         if (with_bg) {
             const float mn = bg_minmax[2 * b], hi = bg_minmax[2 * b + 1];
             const float v = __fmul_rn(__fsub_rn(bg_blur[(size_t)b * N + (size_t)y * W + x], mn), __fdiv_rn(1.0f, __fsub_rn(hi, mn)));
             row[0] = v;
-            has_nan = v != v;
             mxv = fmaxf(mxv, v);
         }
+        float *rc = row + with_bg;
+#pragma unroll 2
         for (int c = 0; c < C; ++c) {
             const float yv = lr_dot<PPAD>(s_T + c * PPAD, ax);
-            const float v = __fmul_rn(__fsub_rn(yv, s_norm[2 * c]), s_norm[2 * c + 1]);   // (y - min) / (max - min), DRV:1151-1152
-            row[with_bg + c] = v;
-            has_nan = has_nan || (v != v);
+            const float2 nm = s_norm[c];
+            const float v = __fmul_rn(__fsub_rn(yv, nm.x), nm.y);   // (y - min) / (max - min), DRV:1151-1152
+            rc[c] = v;
             mxv = fmaxf(mxv, v);
         }
         if (maps_out) {
@@ -639,24 +669,31 @@ __global__ void __launch_bounds__(128) lowrank_unary_kernel(const float *__restr
         }
         if (unary) {
             // U_c = -log(clip(softmax_c(v), 1e-5, 1)) = clamp(log(sum_k e^(v_k - max)) - (v_c - max), 0, -log 1e-5): one log per
-            // pixel and no division instead of a division and a log per channel
+            // pixel and no division instead of a division and a log per channel.  A NaN in any channel (fmaxf skips it) turns
+            // the sum, hence every channel's unary, into NaN -- the softmax of a column holding a NaN.
             float sum = 0.f;
             for (int c = 0; c < Cc; ++c) sum += __expf(row[c] - mxv);
-            const float lse = __logf(sum);
+            const bool has_nan = sum != sum;
+            const float shift = __logf(sum) + mxv;
             for (int c = 0; c < Cc; ++c) {
-                const float u = fminf(fmaxf(lse - (row[c] - mxv), 0.f), kUnaryClipHi);
-                row[c] = has_nan ? __int_as_float(0x7fc00000) : u;   // softmax of a column holding a NaN is NaN everywhere
+                const float u = fminf(fmaxf(shift - row[c], 0.f), kUnaryClipHi);
+                row[c] = has_nan ? __int_as_float(0x7fc00000) : u;
             }
             for (int c = Cc; c < Cp; ++c) row[c] = 0.f;
         }
     }
     if (!unary) return;
     __syncthreads();
+    // coalesced copy-out of the [n_here][Cp] block; (pixel, channel) advance incrementally -- no division per element
     const int n_here = min(TP, W - x0);
     float *ub = unary + ((size_t)b * N + (size_t)y * W + x0) * Cp;
+    const int step_p = TP / Cp, step_c = TP - step_p * Cp;
+    int pp = threadIdx.x / Cp, c = threadIdx.x - pp * Cp;
     for (int i = threadIdx.x; i < n_here * Cp; i += TP) {
-        const int pp = i / Cp, c = i - pp * Cp;
         ub[i] = s_tile[pp * pitch + c];
+        pp += step_p;
+        c += step_c;
+        if (c >= Cp) { c -= Cp; ++pp; }
     }
 }
 
@@ -830,10 +867,10 @@ bool make_lowrank_plan(int B, int C, int P, int H, int W, double sigma, int with
     p.smem_a = ((size_t)p.PPAD * p.PPAD + (size_t)p.rows_chunk * p.PPAD) * sizeof(float);
     const int Cp = (C + (with_background ? 1 : 0) + 3) / 4 * 4;
     p.tile_pix = Cp <= 64 ? 128 : 64;
-    p.smem_b = ((size_t)C * p.PPAD + 2 * (size_t)C + (size_t)p.tile_pix * (Cp + 1)) * sizeof(float);
+    p.smem_b = ((size_t)C * p.PPAD + 2 * (size_t)C + (size_t)p.tile_pix * (Cp + 1)) * sizeof(float);  // s_T, s_norm (float2), s_tile
     if (p.smem_b > 200 * 1024) {
         p.tile_pix = 32;
-        p.smem_b = ((size_t)C * p.PPAD + 2 * (size_t)C + (size_t)p.tile_pix * (Cp + 1)) * sizeof(float);
+        p.smem_b = ((size_t)C * p.PPAD + 2 * (size_t)C + (size_t)p.tile_pix * (Cp + 1)) * sizeof(float);  // s_T, s_norm (float2), s_tile
         if (p.smem_b > 200 * 1024) return false;
     }
     size_t off = 0;
@@ -894,9 +931,8 @@ extern "C" int pnp_lowrank_blur_unary(const float *class_maps, float *unary, int
     // reference's rescale silently does not happen (DRV:1079-1080), as in pnp_threshold_upsample
     const int bg_rescale = (rescale && with_background && C > 1) ? 1 : 0;
     char *bws = ws + p.off_blur_ws;
-    lowrank_operator_kernel<<<ceil_div(H + W, 128), 128, 0, st>>>(reinterpret_cast<float *>(ws + p.off_ay), reinterpret_cast<float *>(ws + p.off_axt),
-                                                                 reinterpret_cast<unsigned *>(bws + p.blur.off_keys), 0, H, W, P, p.PPAD,
-                                                                 p.blur.lw, sigma);
+    lowrank_operator_kernel<<<ceil_div(H + W, 128), 128, (2 * p.blur.lw + 1) * sizeof(double), st>>>(
+        reinterpret_cast<float *>(ws + p.off_ay), reinterpret_cast<float *>(ws + p.off_axt), H, W, P, p.PPAD, p.blur.lw, sigma);
     PNP_LAUNCH(kThresholdPrep, st, threshold_prep_kernel<<<dim3(C, B), 256, 0, st>>>(class_maps, masked, params, C, P, H, W, threshold, bg_rescale));
     int rc = launch_status();
     if (rc != PNP_OK) return rc;

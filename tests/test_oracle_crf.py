@@ -112,3 +112,62 @@ def test_bilateral_filter_approximates_the_bilateral_gaussian():
     e[12 * W + 8] = 1.0
     r = lat.compute(e)[:, 0].reshape(H, W)
     assert r[:, W // 2:].sum() < 1e-3 * r[:, : W // 2].sum()
+
+
+# ------------------------------------------------------------------------------------------------ second opinion: exact O(N^2) mean-field
+def _restatement(img, U, C, H, W, n_iter, pos_w=7, bi_w=10):
+    d = D.DenseCRF2D(W, H, C)
+    d.setUnaryEnergy(np.ascontiguousarray(U))
+    if pos_w:
+        d.addPairwiseGaussian(sxy=3, compat=pos_w)
+    if bi_w:
+        d.addPairwiseBilateral(sxy=50, srgb=5, rgbim=img, compat=bi_w)
+    return np.array(d.inference(n_iter))
+
+
+def test_restatement_tracks_the_exact_dense_crf_and_not_its_wrong_variants():
+    """oracle/densecrf.c against an independent O(N^2) mean-field with the TRUE Gaussian kernels (oracle/exact_meanfield.py,
+    no shared code) on <= 32x32 images.  The lattice is an approximation, so the bound is loose (a few 1e-2) -- but every
+    deliberately wrong model (no normalisation, row instead of symmetric normalisation, the lattice's alpha forgotten, the
+    Potts sign flipped, kernel widths off, weights swapped) is several times further away than the right one."""
+    import crf_cases
+    from oracle.exact_meanfield import exact_dense_crf
+    for name, (_, H, W, C) in crf_cases.CASES.items():
+        img, p = crf_cases.make_case(name)
+        U = D.unary_from_softmax(p)
+        for pos_w, bi_w in ((7, 10), (7, 0), (0, 10)):
+            Ql = _restatement(img, U, C, H, W, 1, pos_w, bi_w)
+            kw = dict(pos_w=pos_w, bi_w=bi_w)
+            err = lambda **k: float(np.abs(Ql - exact_dense_crf(img, U, 1, **dict(kw, **k))).mean())
+            right = err()
+            assert right <= 0.006 and float(np.abs(Ql - exact_dense_crf(img, U, 1, **kw)).max()) <= 0.06, (name, pos_w, bi_w, right)
+            assert err(normalize=None) >= 10 * right, "an unnormalised kernel must be far away"
+            assert err(msg_scale=-1.0) >= 10 * right, "the Potts message has the wrong sign"
+            assert err(normalize="row") >= 1.5 * right
+            if pos_w and not bi_w:   # d = 2: alpha = 0.8 (the d = 5 lattice's 1/(1+2^-5) = 0.97 is too close to 1 to see)
+                assert err(msg_scale=1.0 + 2.0 ** -2) >= 2.5 * right, "alpha = 1/(1+2^-d) of the lattice is missing"
+            if pos_w:
+                assert err(pos_xy_std=4.5) >= 3 * right, "spatial kernel width"
+            if bi_w and not pos_w:
+                assert err(bi_rgb_std=10.0) >= 1.3 * right, "colour kernel width"
+            if pos_w and bi_w:
+                assert err(pos_w=bi_w, bi_w=pos_w) >= 4 * right, "kernel weights swapped"
+        # three iterations in: still close (the error grows as the marginals saturate), labels agree
+        Q3, E3 = _restatement(img, U, C, H, W, 3), exact_dense_crf(img, U, 3)
+        assert float(np.abs(Q3 - E3).mean()) <= 0.012 and float((Q3.argmax(0) == E3.argmax(0)).mean()) >= 0.97
+
+
+def test_crf_restatement_fixture_is_current():
+    """tests/golden/crf_restatement.npz holds inputs + outputs of oracle/densecrf.c (made by make_crf_restatement.py) so that a
+    pydensecrf build can be diffed in one command (tests/golden/diff_pydensecrf.py); it must describe today's restatement."""
+    import os
+    import crf_cases
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "crf_restatement.npz"))
+    for name, (_, H, W, C) in crf_cases.CASES.items():
+        img, p = crf_cases.make_case(name)
+        assert np.array_equal(g[name + "_image"], img)
+        U = D.unary_from_softmax(p)
+        assert np.allclose(g[name + "_unary"], U, rtol=0, atol=1e-6)
+        for it in (1, 3, 10):
+            assert np.allclose(g["%s_Q%d" % (name, it)], _restatement(img, g[name + "_unary"], C, H, W, it), rtol=0, atol=2e-6)
+        assert np.array_equal(g[name + "_map"], g[name + "_Q10"].argmax(0))
