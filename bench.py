@@ -77,13 +77,23 @@ def parse_args(argv=None):
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the native-fp32 comparison leg and the fp64 accuracy probe")
     ap.add_argument("--no-parity", action="store_true", help="skip the GPU-vs-oracle label comparison of one bench batch")
-    ap.add_argument("--no-overlap", action="store_true", help="run the round-0 pass on the main stream instead of a side stream")
+    ap.add_argument("--schedule", default="serial", choices=["serial", "overlap", "pipelined"],
+                    help="serial (default): everything on one stream; overlap: lattice build + round-0 pass on a second stream under "
+                         "DropOut rounds 1..R-1; pipelined: also the accumulated-map pass of batch k under the first model pass of batch "
+                         "k+1.  With the model's GEMMs on the tensor cores the part runs at its 1 kW power cap and the serial schedule is "
+                         "the fastest (measured A/B/A, --overlap-ab: 371 / 380 / 384 ms per step)")
+    ap.add_argument("--overlap-ab", action="store_true", help="also time serial / overlap / pipelined schedules back to back (A/B/A)")
+    ap.add_argument("--main-priority", type=int, default=-1,
+                    help="CUDA priority of the stream the model passes run on when a second stream is in use (-1: above the "
+                         "post-processing stream, so GEMM CTAs are scheduled first; 0: same priority)")
     ap.add_argument("--classes", default="all", choices=["all", "all20", "live"],
                     help="all: every image is captioned with every class of the configuration (BASELINE configs); live (config 1): "
                          "classes per image drawn from the reference's own GPT-4o answers for VOC (mean 1.40)")
     a = ap.parse_args(argv)
     if a.classes == "all20":
         a.classes = "all"
+    a.no_overlap = a.schedule == "serial"
+    a.no_pipeline = a.schedule != "pipelined"
     return a
 
 
@@ -316,6 +326,8 @@ def run_ours(args):
             torch.set_num_threads(1)   # one intra-op host thread per rank (OpenMP teams of N ranks starve the launch threads)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    if args.main_priority != 0 and (not args.no_overlap or args.overlap_ab):   # model passes above the post-processing stream: GEMM CTAs are scheduled first
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=args.main_priority))
     cfg = CONFIGS[args.config]
     strong = args.scaling == "strong"
     B = cfg["B"]
@@ -334,29 +346,44 @@ def run_ours(args):
         torch.backends.cudnn.allow_tf32 = True
     T = max(len(w["tok"].encode(c)) for c in w["captions"])
 
+    pipelined = not args.no_overlap and not args.no_pipeline
+    side = pipeline.side_stream(dev)
+
     class Slot:
-        """One batch: pinned host buffers (e2e), resident device copies (value), token tables."""
+        """One batch: pinned host buffers (e2e), resident device copies (value), token tables.  Guide images and ground truth
+        are double-buffered on the device: with cross-batch pipelining the post-processing of step k still reads them while
+        step k+1's host->device copies arrive."""
 
         def __init__(self, wl):
             self.w = wl
             self.imgs_h, self.guides_h, self.gts_h = wl["imgs"].pin_memory(), torch.from_numpy(wl["guides"]).pin_memory(), torch.from_numpy(wl["gts"]).pin_memory()
             self.imgs_src = self.imgs_h.to(dev)
-            self.imgs_d, self.guides_d, self.gts_d = torch.empty_like(self.imgs_src), self.guides_h.to(dev), self.gts_h.to(dev)
+            self.imgs_d = torch.empty_like(self.imgs_src)
+            self.guides_d = [self.guides_h.to(dev), self.guides_h.to(dev)]
+            self.gts_d = [self.gts_h.to(dev), self.gts_h.to(dev)]
+            self.free_ev = [None, None]      # side-stream event after which buffer i may be overwritten
+            self.turn = 0
             self.tokens_dev = wl["tokens"].to(dev)
             self.token_ids = wl["tokens"].input_ids.tolist()
 
     slots = [Slot(wl) for wl in workloads]
     total_hist = torch.zeros((n_cls, n_cls), dtype=torch.int64, device=dev)
-    hist_host = torch.empty((n_cls, n_cls), dtype=torch.int64).pin_memory()
+    hist_host = [torch.empty((n_cls, n_cls), dtype=torch.int64).pin_memory() for _ in range(2)]
+    d2h_events = []
     bad = torch.zeros(1, dtype=torch.int32, device=dev)
     scored = "all_drop" if cfg["drop_iter"] > 1 else "round0"
 
-    def run_batch(s, e2e, stats=None, labels_out=None, overlap=None):
+    def run_batch(s, e2e, stats=None, labels_out=None, overlap=None, defer=False):
         wl = s.w
+        i = 0
         if e2e:  # host buffers in
+            i = s.turn % 2
+            s.turn += 1
+            if s.free_ev[i] is not None:     # the batch that last read buffer i (two steps ago) must have finished with it
+                torch.cuda.current_stream().wait_event(s.free_ev[i])
             s.imgs_d.copy_(s.imgs_h, non_blocking=True)
-            s.guides_d.copy_(s.guides_h, non_blocking=True)
-            s.gts_d.copy_(s.gts_h, non_blocking=True)
+            s.guides_d[i].copy_(s.guides_h, non_blocking=True)
+            s.gts_d[i].copy_(s.gts_h, non_blocking=True)
         else:    # inputs already resident; DropOut zeroes pixel blocks in place, so restore the working copy
             s.imgs_d.copy_(s.imgs_src)
 
@@ -364,21 +391,41 @@ def run_ours(args):
             return model.gradcam(x, wl["captions"], s.tokens_dev, layer=cfg["layer"], head=cfg["head"])[0]
 
         h0, hagg, _ = pipeline.batch_confusion(gradcam_fn, s.imgs_d, s.token_ids, wl["tok"].decode, wl["class_lists"], wl["dataset_ids"],
-                                               s.gts_d, s.guides_d, drop_iter=cfg["drop_iter"], patch_num=cfg["P"],
+                                               s.gts_d[i], s.guides_d[i], drop_iter=cfg["drop_iter"], patch_num=cfg["P"],
                                                threshold=cfg["threshold"], data_type=cfg["data_type"], mode=cfg["mode"], coco=cfg["coco"],
                                                n_class=n_cls, stats=stats, overlap=(not args.no_overlap) if overlap is None else overlap,
-                                               labels_out=labels_out, bad_count=bad)
+                                               labels_out=labels_out, bad_count=bad, defer=defer)
+        if defer and e2e:
+            s.free_ev[i] = side.record_event()
         return h0, (hagg if hagg is not None else h0)
 
-    def step(e2e, stats=None):
-        """One step: every batch this rank owns (one in weak scaling)."""
+    def step(e2e, stats=None, serial=False, mode=None):
+        """One step: every batch this rank owns (one in weak scaling).  Pipelined: the step returns once its last model pass is
+        enqueued; its matrix is folded into the accumulator (and, end to end, copied to the host) on the side stream, and the
+        host waits for the PREVIOUS step's copy, so every step's result is read back inside the timed region.
+        serial: everything on the main stream, nothing overlapped (the roofline leg: each kernel owns the GPU while it runs)."""
         h = None
+        if mode is not None:      # --overlap-ab: force one of the three schedules
+            serial, defer = mode == "serial", mode == "pipelined"
+        else:
+            defer = pipelined and stats is None and not serial
         for s in slots:
-            _, h = run_batch(s, e2e, stats)
-            total_hist.add_(h)
+            _, h = run_batch(s, e2e, stats, defer=defer, overlap=False if serial else (True if mode is not None else None))
+            if defer:
+                with torch.cuda.stream(side):
+                    total_hist.add_(h)
+            else:
+                total_hist.add_(h)
         if e2e and h is not None:   # host result out (the step's confusion matrix)
-            hist_host.copy_(h, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            if defer:
+                with torch.cuda.stream(side):
+                    hist_host[len(d2h_events) % 2].copy_(h, non_blocking=True)
+                    d2h_events.append(side.record_event())
+                if len(d2h_events) > 1:
+                    d2h_events[-2].synchronize()
+            else:
+                hist_host[0].copy_(h, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
         return h
 
     def barrier():
@@ -387,7 +434,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(e2e, n_steps):
+    def timed(e2e, n_steps, serial=False, mode=None):
         """(ms, reduced int64 matrix of exactly these n_steps).  The all-reduce -- the path's one exchange step -- runs once,
         on a COPY of the accumulator, inside the timed region."""
         total_hist.zero_()
@@ -395,7 +442,11 @@ def run_ours(args):
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(n_steps):
-            step(e2e)
+            step(e2e, serial=serial, mode=mode)
+        pipeline.join_side_stream(dev)           # deferred post-processing of the last steps
+        if e2e and d2h_events:
+            d2h_events[-1].synchronize()
+            del d2h_events[:]
         reduced = total_hist.clone()
         if world > 1:
             dist.all_reduce(reduced, op=dist.ReduceOp.SUM)
@@ -436,19 +487,39 @@ def run_ours(args):
     # ---- timed region (inputs resident), dominant kernel bracketed by events in situ
     sampler = ClockSampler(local_rank)
     sampler.start()
-    # kernels of the round-0 pass run on a side stream under the model's GEMMs; the roofline is taken from the launches on
-    # the main stream (the all-drop pass), which own the GPU while they run
-    lib.pnp_profile_filter_stream(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), 1)
+    # In the timed region the post-processing runs on the side stream UNDER the model's GEMMs (that is where the throughput
+    # comes from), so a launch timed there shares the GPU with a GEMM: reported as `overlapped_avg_launch_ms`.  The roofline
+    # itself is taken in a second timed region of the same steps run serially on the main stream, right after: every launch
+    # of the dominant kernel is bracketed by events on its own stream and owns the GPU while it runs.
+    lib.pnp_profile_filter_stream(ctypes.c_void_p(side.cuda_stream if pipelined else torch.cuda.current_stream().cuda_stream), 1)
     lib.pnp_profile_start(ctypes.c_uint(1 << dom_id))
     ms_total, reduced = timed(False, args.steps)
     lib.pnp_profile_stop(tot, cnt, n_ids)
     lib.pnp_profile_filter_stream(ctypes.c_void_p(0), 0)
     clocks = sampler.stop()
+    dom_ms_overlapped = float(tot[dom_id]) / max(int(cnt[dom_id]), 1) if pipelined else None
+    if pipelined:
+        roof_steps = max(1, min(args.steps, 3))
+        lib.pnp_profile_start(ctypes.c_uint(1 << dom_id))
+        roof_ms, _ = timed(False, roof_steps, serial=True)
+        lib.pnp_profile_stop(tot, cnt, n_ids)
+    else:
+        roof_steps, roof_ms = args.steps, ms_total
     dom_ms = float(tot[dom_id]) / max(int(cnt[dom_id]), 1)
     dom_launches = int(cnt[dom_id])
     ms_per_step = ms_total / args.steps
     imgs_per_step = (STRONG_IMAGES // B) * B if strong else world * B
     value = imgs_per_step * args.steps / (ms_total / 1e3)
+
+    # ---- optional A/B/A of the three schedules in this process (power-capped parts: overlap is not automatically a win)
+    overlap_ab = None
+    if args.overlap_ab:
+        overlap_ab = {}
+        for rep in range(2):
+            for mode in ("serial", "overlap", "pipelined"):
+                step(False, mode=mode)
+                ms, _ = timed(False, args.steps, mode=mode)
+                overlap_ab.setdefault(mode, []).append(round(ms / args.steps, 2))
 
     # ---- the reduced matrix must hold exactly the valid pixels of every rank's every step (a garbage sum cannot pass)
     valid_local = torch.tensor([sum(s.w["valid_pixels"] for s in slots)], dtype=torch.int64, device=dev)
@@ -483,7 +554,7 @@ def run_ours(args):
         e2e_ms, _ = timed(True, args.steps)
         per_batch_h2d = int(w["imgs"].numel() * 4 + w["guides"].size + w["gts"].size * 4)
         e2e = {"value": imgs_per_step * args.steps / (e2e_ms / 1e3), "unit": "images/s",
-               "h2d_bytes_per_step": per_batch_h2d * max(len(slots), 1), "d2h_bytes_per_step": int(hist_host.numel() * 8),
+               "h2d_bytes_per_step": per_batch_h2d * max(len(slots), 1), "d2h_bytes_per_step": int(hist_host[0].numel() * 8),
                "ms_per_step": e2e_ms / args.steps}
 
     # ---- the same steps on torch's native fp32 SIMT GEMMs, and both modes against an fp64 autograd pass
@@ -547,6 +618,10 @@ def run_ours(args):
                 "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                 "frac_on_real_traffic": (traffic / (dom_ms * 1e-3) / 1e9 / peak) if traffic else None,
                 "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": dom_ms, "launches_timed": dom_launches,
+                "timed_region": ("%d steps run serially on the main stream (%.1f ms per step) right after the pipelined timed region: "
+                                 "each launch owns the GPU" % (roof_steps, roof_ms / roof_steps)) if pipelined else
+                                "the timed region itself (launches on the main stream)",
+                "overlapped_avg_launch_ms": dom_ms_overlapped,
                 "share_of_step": per_kernel[dominant][0] / ms_per_step,
                 "scope": "largest post-processing kernel class (SURVEY 8 rows a5-a10); every class is listed under `kernels`"}
 
@@ -581,13 +656,17 @@ def run_ours(args):
                        "model": "BLIP ITM-large shape, random init, torch %s GEMMs, trimmed backward" % args.gemm,
                        "passes": ("all_drop only (DRVC:420)" if cfg["coco"] and cfg["drop_iter"] >= 3 else
                                   "round0 only (drop_iter 1)" if cfg["drop_iter"] == 1 else "round0 + all_drop (DRV:348-403, 424-481)"),
-                       "overlap": "off" if args.no_overlap else "lattice build + round-0 pass on a side stream under DropOut rounds 1-3",
+                       "schedule": args.schedule,
+                       "overlap": ("off (one stream: fastest on this power-capped part, see --overlap-ab)" if args.no_overlap else
+                                   "lattice build + round-0 pass on a side stream under DropOut rounds 1-3" +
+                                   ("; accumulated-map pass of step k under the first model pass of step k+1 (main stream priority %d)" % args.main_priority
+                                    if pipelined else "")),
                        "parallelism": "dp%d over images" % world, "host_threads_per_rank": torch.get_num_threads(),
                        "M_s": stats.get("M_s"), "M_b_per_batch": stats.get("M_b"),
                        "l2": "per-step working set (>3 GB) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "ref_gpu": ref_gpu, "native_fp32": native, "gemm_accuracy": accuracy,
-            "parity": parity, "allreduce_check": allreduce_check,
+            "parity": parity, "allreduce_check": allreduce_check, "overlap_ab_ms_per_step": overlap_ab,
             "custom_kernels": {"ms_per_step": round(custom_ms, 3), "postprocess_ms_per_step": round(post_ms, 3),
                                "postprocess_images_per_s": round(B * len(slots) / (post_ms * 1e-3), 1) if post_ms else None,
                                "note": "sum of the in-situ event times of every pnp:: kernel in one (warm-up) step, serialised on one "

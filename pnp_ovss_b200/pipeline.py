@@ -192,8 +192,8 @@ def _side_stream(dev):
 
 
 def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_ids, gts, guides, *, drop_iter, patch_num,
-                    threshold, data_type, mode, n_class, coco=False, crf=None, norm_imgs=None, stats=None, overlap=True,
-                    labels_out=None, bad_count=None):
+                    threshold, data_type, mode, n_class, coco=False, crf=None, norm_imgs=None, stats=None, overlap=False,
+                    labels_out=None, bad_count=None, defer=False):
     """One batch of save_img_union_attention: returns (hist_round0 or None, hist_all_drop or None, chosen) with the
     matrices as int64 CUDA tensors [n,n] -- what the reference saves to hist_withfiltered_caption/ and
     all_drop_hist_with_filtered_caption/ (DRV:495-520).  `coco` selects the COCO driver's deltas (DRVC:420, 527, 602).
@@ -204,6 +204,15 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
 
     overlap: the bilateral lattice build and the whole round-0 pass (which needs only the round-0 map) run on a second
     CUDA stream while DropOut rounds 1..R-1 (model passes) occupy the main stream; results are identical either way.
+    Off by default: with the model's GEMMs on the tensor cores a B200 runs this workload at its power cap, and co-scheduling
+    the memory-bound post-processing under the GEMMs costs more than it hides (bench.py --overlap-ab: 371 ms serial, 380 ms
+    overlapped, 384 ms pipelined per step); with SIMT fp32 GEMMs (round 1) the overlap was worth 1.3 %.
+
+    defer (needs overlap and bad_count): ALSO the accumulated-map pass is enqueued on the second stream and the function
+    returns as soon as the last model pass has been enqueued, so that the caller's NEXT batch starts its first model pass
+    while this batch's post-processing still runs underneath it (cross-batch software pipelining).  The returned matrices
+    are then complete only after `pipeline.side_stream(dev)` has been waited for (`join_side_stream`), and the caller must
+    not overwrite gts / guides before that.
 
     labels_out: a dict that receives {"round0" / "all_drop": float32 [B,H,W] relabelled maps} (uniform batches only).
     bad_count: an int32 [1] CUDA tensor that accumulates the number of relabelled ids outside [0, n_class); when given,
@@ -212,7 +221,8 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
     B = imgs.shape[0]
     round0_scored = not coco or drop_iter < 3
     timed_stages = stats is not None and "events" in stats
-    use_side = bool(overlap) and drop_iter > 1 and round0_scored and not timed_stages
+    defer = bool(defer) and bool(overlap) and bad_count is not None and not timed_stages
+    use_side = bool(overlap) and not timed_stages and ((drop_iter > 1 and round0_scored) or defer)
     main = torch.cuda.current_stream(dev) if use_side else None
     side = _side_stream(dev) if use_side else None
     use_crf = bool(mode) and "crf" in mode
@@ -263,22 +273,38 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
                     raise PnpError("labels_out needs a uniform batch (one bucket)")
                 labels_out[name] = pred
 
-    def after_round0(g0):
+    def side_prologue():
+        """First use of the side stream for this batch: inputs visible, lattices built (under the running model pass)."""
         nonlocal ev_lattices
+        side.wait_event(ev_inputs)
+        for t in (bad,) + tuple(hists.values()) + tuple(x for v in inputs.values() for x in v) + tuple(segs[:3]):
+            t.record_stream(side)
+        build_lattices()                           # the host waits for the build only (pnp_lattice_finish reads M back)
+        ev_lattices = side.record_event()
+
+    def after_round0(g0):
         if not use_side:
             return
         ev_r0 = main.record_event()
         with torch.cuda.stream(side):
-            side.wait_event(ev_inputs)
-            build_lattices()                       # runs under round 0's model pass; host waits for the build only
-            ev_lattices = side.record_event()
-            side.wait_event(ev_r0)
-            for t in (g0, bad, hists["round0"]) + tuple(x for v in inputs.values() for x in v) + tuple(segs[:3]):
-                t.record_stream(side)
-            run_pass("round0", g0, True)           # 1-round path applies Scale_0_1 (DRV:362)
+            side_prologue()
+            if round0_scored:
+                side.wait_event(ev_r0)
+                g0.record_stream(side)
+                run_pass("round0", g0, True)       # 1-round path applies Scale_0_1 (DRV:362)
 
     g0, agg, chosen = salience_dropout_loop(gradcam_fn, imgs, norm_imgs, drop_iter, patch_num, after_round0=after_round0)
     _mark(stats, "model+gradcam+dropout")
+    if use_side and drop_iter == 1:                # the loop made no callback: the only pass there is goes to the side stream now
+        after_round0(g0)
+    if use_side and defer:
+        if agg is not None:
+            ev_agg = main.record_event()
+            with torch.cuda.stream(side):
+                side.wait_event(ev_agg)
+                agg.record_stream(side)
+                run_pass("all_drop", agg, coco)
+        return hists.get("round0"), hists.get("all_drop"), chosen
     if use_side:
         main.wait_event(ev_lattices)
         for lat in lattices.values():
@@ -294,6 +320,17 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
     if bad_count is None and int(bad.item()):
         raise PnpError("a relabelled id fell outside [0, n_class)")
     return hists.get("round0"), hists.get("all_drop"), chosen
+
+
+def side_stream(dev):
+    """The second CUDA stream batch_confusion overlaps post-processing on (one per device)."""
+    return _side_stream(torch.device(dev) if not isinstance(dev, torch.device) else dev)
+
+
+def join_side_stream(dev):
+    """Make the current stream wait for everything deferred batches have enqueued on the side stream."""
+    dev = torch.device(dev) if not isinstance(dev, torch.device) else dev
+    torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
 
 
 # ---------------------------------------------------------------------------------------------- multi-GPU + files

@@ -466,3 +466,27 @@ def test_cuda_crf_against_the_exact_dense_crf_and_the_stored_restatement(dev):
                 assert np.abs(Q - E).mean() <= 0.006 and np.abs(Q - E).max() <= 0.06
             if it == 10:
                 assert (Q.argmax(0) != g[name + "_map"]).mean() <= 2e-3
+
+
+def test_schedules_give_identical_matrices(dev):
+    """One stream (default), lattice build + round-0 pass on a second stream, and the fully deferred schedule (everything after
+    the model passes on the second stream, joined by the caller) produce bit-identical confusion matrices."""
+    from pnp_ovss_b200 import pipeline
+    c = smoke_case.case_inputs("voc_r4")
+    outs = []
+    for kw in (dict(overlap=False), dict(overlap=True), dict(overlap=True, defer=True)):
+        fn = synth.SynthGradcamFn(31, len(c["class_lists"]), c["T"], c["P"])
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        gts = torch.from_numpy(np.stack(c["gts"])).to(dev)
+        guides = torch.from_numpy(np.stack(c["guides"])).to(dev)
+        h0, hagg, chosen = pipeline.batch_confusion(lambda x: fn(x.cpu(), c["rows"]).to(dev), c["imgs"].clone().to(dev),
+                                                    c["tokens"].input_ids.tolist(), c["tok"].decode, c["class_lists"], c["ids"], gts, guides,
+                                                    drop_iter=c["R"], patch_num=c["P"], threshold=0.15, data_type=c["data_type"], mode="blur+crf",
+                                                    n_class=c["n_class"], coco=c["coco"], bad_count=bad, **kw)
+        pipeline.join_side_stream(dev)
+        torch.cuda.synchronize()
+        assert int(bad.item()) == 0
+        outs.append((h0.cpu(), hagg.cpu(), chosen.cpu()))
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], o))
+    assert int(outs[0][1].sum()) == sum(int(((g >= 0) & (g < c["n_class"])).sum()) for g in c["gts"])
