@@ -12,8 +12,8 @@ instead) and the int64 confusion matrices are all-reduced once over NCCL at the 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config k]      # our arm (CUDA kernels through the C ABI)
     python bench.py --impl reference [--steps K] [--warmup W] [--config k] # the reference's CPU path on the host cores
 
-Model GEMMs: by default fp32-grade products on the TF32 tensor cores (`--gemm 3xtf32`: exact hi/lo split of both operands,
-three TF32 products, fp32 accumulate -- measured closer to an fp64 pass than torch's default fp32 path, see `gemm_accuracy`
+Model GEMMs: by default fp32-grade products on the fp16 tensor cores (`--gemm 3xfp16`, or `3xtf32`: exact hi/lo split of both operands,
+three products, fp32 accumulate -- measured closer to an fp64 pass than torch's default fp32 path, see `gemm_accuracy`
 in the line); `--gemm fp32` runs torch's native fp32 SIMT GEMMs and is timed beside it as `native_fp32`.
 """
 import argparse
@@ -65,9 +65,10 @@ def parse_args(argv=None):
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=1, choices=range(len(CONFIGS)), help="index into BASELINE.json configs")
-    ap.add_argument("--gemm", default="3xtf32", choices=["fp32", "3xtf32", "tf32", "bf16"],
-                    help="the model's torch GEMMs: 3xtf32 = fp32-grade error-compensated TF32 tensor-core products (default), "
-                         "fp32 = native SIMT fp32; tf32 / bf16 are narrower than the reference and only for comparison")
+    ap.add_argument("--gemm", default="3xfp16", choices=["fp32", "3xtf32", "3xfp16", "tf32", "bf16"],
+                    help="the model's torch GEMMs: 3xfp16 (default) / 3xtf32 = fp32-grade error-compensated products on the fp16 / TF32 "
+                         "tensor cores (exact hi/lo split of both operands, three products, fp32 accumulate), fp32 = native SIMT fp32; "
+                         "tf32 / bf16 are narrower than the reference and only for comparison")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one batch per rank per step; strong: a fixed %d-image list split over the ranks per step" % STRONG_IMAGES)
     ap.add_argument("--guide", default="natural", choices=["natural", "noise"], help="CRF guide image flavour (SURVEY 8d)")
@@ -305,6 +306,8 @@ def gradcam_fp64(model, imgs, captions, tokens, layer, head, P):
 
 DTYPE_NAMES = {
     "3xtf32": "f32 (model GEMMs as error-compensated 3xTF32 tensor-core products, fp32 accumulate; custom kernels fp32)",
+    "3xfp16": "f32 (model GEMMs as error-compensated 3xFP16 tensor-core products on an exact 22-bit hi/lo split, fp32 accumulate; "
+              "custom kernels fp32)",
     "fp32": "f32", "tf32": "tf32 GEMMs (narrower than the reference), fp32 elsewhere", "bf16": "bf16 ViT autocast (narrower than the reference)"}
 
 
@@ -530,6 +533,7 @@ def run_ours(args):
         raise SystemExit("bench.py: reduced confusion matrix sums to %d, expected %d valid pixels" % (hist_total, hist_expected))
     if int(bad.item()):
         raise SystemExit("bench.py: a relabelled id fell outside [0, n_class)")
+    model.check_fp16_overflow()      # 3xFP16 operands: raised if an activation ever left fp16's range (never read per step)
 
     # ---- multi-GPU: rank 0 recomputes every rank's shard itself and compares with the all-reduced matrix, bit for bit
     allreduce_check = None
@@ -559,7 +563,7 @@ def run_ours(args):
 
     # ---- the same steps on torch's native fp32 SIMT GEMMs, and both modes against an fp64 autograd pass
     native = accuracy = None
-    if args.gemm == "3xtf32" and not args.no_alt:
+    if args.gemm in ("3xtf32", "3xfp16") and not args.no_alt:
         model.gemm_precision = "fp32"
         step(False)
         nat_steps = max(1, min(args.steps, 3))
@@ -571,7 +575,7 @@ def run_ours(args):
             probe = slots[0].imgs_src[:n].contiguous()
             tokn = w["tok"](w["captions"][:n], padding="max_length", max_length=500).to(dev)
             cam = {}
-            for mode in ("fp32", "3xtf32"):
+            for mode in ("fp32", "3xtf32", "3xfp16"):
                 model.gemm_precision = mode
                 cam[mode] = model.gradcam(probe, w["captions"][:n], tokn, layer=cfg["layer"], head=cfg["head"])[0]
             torch.backends.cudnn.allow_tf32 = False
@@ -582,6 +586,7 @@ def run_ours(args):
                 truth = gradcam_fp64(model, probe, w["captions"][:n], tokn, cfg["layer"], cfg["head"], cfg["P"])
                 sc = truth.abs().max()
                 accuracy = {"what": "max |GradCAM - fp64 autograd pass| / max |GradCAM|, %d images, block %d head %d" % (n, cfg["layer"] + 1, cfg["head"]),
+                            "3xfp16": float(((cam["3xfp16"].double() - truth).abs().max() / sc).item()),
                             "3xtf32": float(((cam["3xtf32"].double() - truth).abs().max() / sc).item()),
                             "native_fp32_torch_defaults": float(((cam["fp32"].double() - truth).abs().max() / sc).item()),
                             "native_fp32_strict_no_cudnn_tf32": float(((cam["fp32_strict"].double() - truth).abs().max() / sc).item()),

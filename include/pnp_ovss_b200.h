@@ -244,6 +244,21 @@ int pnp_layernorm_tf32_split3(const float *x, const float *residual, const float
                               const float *gamma, const float *beta, float eps, float *out3, float *out1,
                               long long M, int K, pnp_stream_t stream);
 
+/* The same three producers for the "3xFP16" form: x = h + l 2^-11 with h = fp16(x), l = fp16((x - h) 2^11), written as fp16
+ * [h * hi_scale | l | h] ([M,3K] halves).  Against a weight operand [W_h 2^b | W_h | W_l] with hi_scale * 2^b = 2^11, ONE fp16
+ * tensor-core GEMM with fp32 accumulation yields 2^11 * (x W^T) at fp32-grade accuracy; the consumer takes the factor back
+ * through in_scale / residual_scale (x is multiplied by in_scale before anything else; the residual by residual_scale).
+ * *overflow_flag (device int, optional) is set to 1 when a value does not fit fp16 (|x| * hi_scale > 65504, inf or NaN):
+ * the caller checks it once per run and falls back to the TF32 form.  K % 4 == 0; out3 8-byte aligned. */
+int pnp_fp16_split3(const float *x, float in_scale, float hi_scale, uint16_t *out3, int *overflow_flag, long long M,
+                    int K, pnp_stream_t stream);
+int pnp_gelu_fp16_split3(const float *x, float in_scale, const float *bias, float hi_scale, uint16_t *out3,
+                         int *overflow_flag, long long M, int K, pnp_stream_t stream);
+int pnp_layernorm_fp16_split3(const float *x, const float *residual, float residual_scale,
+                              const float *residual_bias, float *x_out, const float *gamma, const float *beta,
+                              float eps, float hi_scale, uint16_t *out3, float *out1, int *overflow_flag, long long M,
+                              int K, pnp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * In-situ kernel timing for bench.py's roofline (the one piece of process-global state in the library):
  * between start and stop, every launch of a kernel class whose bit is set in kernel_mask is bracketed by

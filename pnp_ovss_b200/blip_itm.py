@@ -74,6 +74,28 @@ def _w3(weight):
     return torch.cat([w_hi, w_hi, w_lo], 1).contiguous()
 
 
+FP16_OUT_SCALE = 2048.0     # 2^11: the factor a 3xFP16 product carries (see _w16 / _mm16)
+
+
+def _w16(weight):
+    """[N,K] frozen weight -> (fp16 [N,3K] = [W_h 2^b | W_h | W_l], 2^a) with W = W_h + W_l 2^-11 (W_h = fp16(W), W_l =
+    fp16((W - W_h) 2^11)) and a + b = 11: the right-hand operand of the 3xFP16 GEMM whose left operand is
+    [x_h 2^a | x_l | x_h] (ops.fp16_split3 and its fused producers).  b is as large as the largest |W| allows, so a is 0
+    (no loss of activation range) unless a weight exceeds 32."""
+    w = weight.detach().contiguous().float()
+    wmax = float(w.abs().max())
+    b = 11 if wmax == 0 else max(0, min(11, int(math.floor(math.log2(65504.0 / wmax)))))
+    w_h = w.half()
+    w_l = ((w - w_h.float()) * FP16_OUT_SCALE).half()
+    return torch.cat([(w_h.float() * (2.0 ** b)).half(), w_h, w_l], 1).contiguous(), 2.0 ** (11 - b)
+
+
+def _mm16(x16, w16):
+    """2^11 * (x W^T) at fp32-grade accuracy as ONE fp16 tensor-core GEMM (fp32 accumulate and output) over the tripled
+    operands: x_h W_h 2^11 + x_l W_h + x_h W_l, with x = x_h + x_l 2^-11.  The caller takes the 2^11 back (a power of two)."""
+    return torch.mm(x16.reshape(-1, x16.shape[-1]), w16.t(), out_dtype=torch.float32).view(*x16.shape[:-1], w16.shape[0])
+
+
 MM3_SEPARATE_CORRECTION = True
 
 
@@ -279,66 +301,109 @@ class BlipITM(nn.Module):
                 return self.visual_encoder(imgs).float()
         return self.visual_encoder(imgs)
 
-    # ---- "3xtf32": the frozen-weight encoder pass with every large GEMM on the TF32 tensor cores at fp32-grade accuracy
-    def _weights3(self):
-        """Tripled TF32 splits of the frozen weights ([W_hi | W_hi | W_lo], see _w3), rebuilt when a parameter changes."""
+    # ---- "3xtf32" / "3xfp16": the frozen-weight encoder pass with every large GEMM on the tensor cores at fp32-grade accuracy
+    SPLIT_MODES = ("3xtf32", "3xfp16")
+
+    def _weights3(self, mode="3xtf32"):
+        """Tripled splits of the frozen weights for `mode` ([W_hi | W_hi | W_lo] fp32, see _w3; or fp16 with its activation
+        scale, see _w16), rebuilt when a parameter changes."""
         ve = self.visual_encoder
         params = [ve.patch_embed.weight] + [p for blk in ve.blocks for p in (blk.qkv.weight, blk.proj.weight, blk.fc1.weight, blk.fc2.weight)]
         params += [p for lyr in self.layer for p in (lyr.crossattention.self.key.weight, lyr.crossattention.self.value.weight)]
         stamp = tuple((p.data_ptr(), p._version) for p in params)
-        cache = self.__dict__.get("_w3_cache")
+        caches = self.__dict__.setdefault("_w3_cache", {})
+        cache = caches.get(mode)
         if cache is None or cache["stamp"] != stamp:
+            prep = _w16 if mode == "3xfp16" else (lambda w: (_w3(w), 1.0))
             with torch.no_grad():
                 xs = [lyr.crossattention.self for lyr in self.layer]
                 cache = {
                     "stamp": stamp,
-                    "patch": _w3(ve.patch_embed.weight.reshape(ve.patch_embed.weight.shape[0], -1)),
-                    "blocks": [tuple(_w3(l.weight) for l in (blk.qkv, blk.proj, blk.fc1, blk.fc2)) for blk in ve.blocks],
+                    "patch": prep(ve.patch_embed.weight.reshape(ve.patch_embed.weight.shape[0], -1)),
+                    "blocks": [tuple(prep(l.weight) for l in (blk.qkv, blk.proj, blk.fc1, blk.fc2)) for blk in ve.blocks],
                     # key/value projections of all cross-attention blocks as one [layers*2*hidden, 3*enc_width] operand
-                    "kv": _w3(torch.cat([w for x in xs for w in (x.key.weight, x.value.weight)], 0)),
+                    "kv": prep(torch.cat([w for x in xs for w in (x.key.weight, x.value.weight)], 0)),
                     "kv_bias": torch.cat([b for x in xs for b in (x.key.bias, x.value.bias)], 0).contiguous(),
                 }
-            self.__dict__["_w3_cache"] = cache
+            caches[mode] = cache
         return cache
 
-    def _vit3(self, imgs, want_plain=False):
+    def fp16_overflow_flag(self, device):
+        """Device int32 raised by the 3xFP16 operand kernels when an activation does not fit fp16; read it once per run
+        (`check_fp16_overflow`), not per pass."""
+        flags = self.__dict__.setdefault("_fp16_flags", {})
+        key = str(device)
+        if key not in flags:
+            flags[key] = torch.zeros(1, dtype=torch.int32, device=device)
+        return flags[key]
+
+    def check_fp16_overflow(self):
+        for flag in self.__dict__.get("_fp16_flags", {}).values():
+            if int(flag.item()):
+                raise ops.PnpError("an activation left fp16's range in a 3xFP16 GEMM operand: use gemm_precision='3xtf32' for this model")
+
+    def _vit3(self, imgs, want_plain=False, mode="3xtf32"):
         """ViT-L forward (VIT:274-290) under no_grad with the GEMM operands prepared by the fused split kernels:
-        residual add + LayerNorm + split, GELU + split, plain split.  Returns (enc3 [B,L,3D] split, enc [B,L,D] or None)."""
+        residual add + LayerNorm + split, GELU + split, plain split.  Returns (enc3 [B,L,3D] split, enc [B,L,D] or None).
+        mode "3xfp16": the products carry a factor 2^11 that the next fused kernel takes back (inv)."""
         ve = self.visual_encoder
-        w = self._weights3()
+        w = self._weights3(mode)
+        half = mode == "3xfp16"
+        inv = 1.0 / FP16_OUT_SCALE if half else 1.0
+        flag = self.fp16_overflow_flag(imgs.device) if half else None
+        mm = _mm16 if half else _mm3
+
+        def split(x, in_scale, wt):
+            return ops.fp16_split3(x, in_scale, wt[1], flag) if half else ops.tf32_split3(x)
+
+        def ln(x, norm, wt, r=None, rb=None, **kw):
+            if half:
+                return ops.layernorm_fp16_split3(x, norm.weight, norm.bias, norm.eps, residual=r, residual_scale=inv, residual_bias=rb,
+                                                 hi_scale=wt[1], flag=flag, **kw)
+            return ops.layernorm_tf32_split3(x, norm.weight, norm.bias, norm.eps, residual=r, residual_bias=rb, **kw)
+
         B, _, S, _ = imgs.shape
         ps = ve.patch_embed.kernel_size[0]
         G = S // ps
         D = ve.pos_embed.shape[-1]
-        patches = imgs.view(B, 3, G, ps, G, ps).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, 3 * ps * ps)
-        pe = _mm3(ops.tf32_split3(patches.contiguous()), w["patch"], ve.patch_embed.bias).view(B, G * G, D)
+        patches = imgs.view(B, 3, G, ps, G, ps).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, 3 * ps * ps).contiguous()
+        pe = torch.add(ve.patch_embed.bias, mm(split(patches, 1.0, w["patch"]), w["patch"][0]), alpha=inv).view(B, G * G, D)
         x = (torch.cat([ve.cls_token.expand(B, -1, -1), pe], 1) + ve.pos_embed).contiguous()
         L = x.shape[1]
         r = rb = None
         for blk, (w_qkv, w_proj, w_fc1, w_fc2) in zip(ve.blocks, w["blocks"]):
-            h3, _ = ops.layernorm_tf32_split3(x, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, residual=r, residual_bias=rb)
-            qkv = _mm3(h3, w_qkv, blk.qkv.bias).view(B, L, 3, blk.heads, D // blk.heads).permute(2, 0, 3, 1, 4)
+            h3, _ = ln(x, blk.norm1, w_qkv, r, rb)
+            if half:
+                qkv = torch.add(blk.qkv.bias, mm(h3, w_qkv[0]), alpha=inv)
+            else:
+                qkv = _mm3(h3, w_qkv[0], blk.qkv.bias)
+            qkv = qkv.view(B, L, 3, blk.heads, D // blk.heads).permute(2, 0, 3, 1, 4)
             a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
-            r = _mm3(ops.tf32_split3(a.transpose(1, 2).reshape(B, L, D).contiguous()), w_proj)
-            h3, _ = ops.layernorm_tf32_split3(x, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, residual=r, residual_bias=blk.proj.bias)
-            g3 = ops.gelu_tf32_split3(_mm3(h3, w_fc1), blk.fc1.bias)
-            r, rb = _mm3(g3, w_fc2), blk.fc2.bias
-        return ops.layernorm_tf32_split3(x, ve.norm.weight, ve.norm.bias, ve.norm.eps, residual=r, residual_bias=rb,
-                                         split=True, plain=want_plain)
+            r = mm(split(a.transpose(1, 2).reshape(B, L, D).contiguous(), 1.0, w_proj), w_proj[0])
+            h3, _ = ln(x, blk.norm2, w_fc1, r, blk.proj.bias)
+            f = mm(h3, w_fc1[0])
+            g3 = (ops.gelu_fp16_split3(f, blk.fc1.bias, inv, w_fc2[1], flag) if half else ops.gelu_tf32_split3(f, blk.fc1.bias))
+            r, rb = mm(g3, w_fc2[0]), blk.fc2.bias
+        return ln(x, ve.norm, w["kv"], r, rb, split=True, plain=want_plain)
 
-    def _cross_kv3(self, enc3):
+    def _cross_kv3(self, enc3, mode="3xtf32"):
         """key(enc) / value(enc) of every cross-attention block (MED:201-221) in one GEMM -> list of (k, v) [B,L,hidden]."""
-        w = self._weights3()
+        w = self._weights3(mode)
         n = len(self.layer)
-        kv = _mm3(enc3, w["kv"], w["kv_bias"]).view(enc3.shape[0], enc3.shape[1], n, 2, -1)
+        if mode == "3xfp16":
+            kv = torch.add(w["kv_bias"], _mm16(enc3, w["kv"][0]), alpha=1.0 / FP16_OUT_SCALE)
+        else:
+            kv = _mm3(enc3, w["kv"][0], w["kv_bias"])
+        kv = kv.view(enc3.shape[0], enc3.shape[1], n, 2, -1)
         return [(kv[:, :, i, 0], kv[:, :, i, 1]) for i in range(n)]
 
     def _encode(self, imgs):
         """(enc or None, per-block cross-attention (k, v) or [None]*n) for the current gemm_precision."""
-        if self.gemm_precision == "3xtf32" and imgs.is_cuda and not any(p.requires_grad for p in self.visual_encoder.parameters()):
+        mode = self.gemm_precision
+        if mode in self.SPLIT_MODES and imgs.is_cuda and not any(p.requires_grad for p in self.visual_encoder.parameters()):
             with torch.no_grad():
-                enc3, _ = self._vit3(imgs)
-                return None, self._cross_kv3(enc3)
+                enc3, _ = self._vit3(imgs, mode=mode)
+                return None, self._cross_kv3(enc3, mode)
         return self._vit(imgs), [None] * len(self.layer)
 
     def forward(self, visual_input, text_input=None, match_head="itm"):

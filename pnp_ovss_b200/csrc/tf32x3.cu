@@ -10,6 +10,14 @@
 //     layernorm_split3  LayerNorm(x) (VIT:70-71) -> [hi | lo | hi]   (one warp per row, row held in registers)
 //     gelu_split3       GELU(x + bias) (exact erf, VIT:35-40)  -> [hi | lo | hi]
 // All three are pure HBM streams (4 B read, 12 B written per element) with 128-bit accesses.
+//
+// "3xFP16" is the same idea on the fp16 tensor cores (twice the TF32 rate, half the operand bytes):
+//     x = h + l 2^-11 with h = fp16(x), l = fp16((x - h) 2^11)  (22-23 significant bits; fp16's range: |x| <= 65504 / 2^a)
+//     [h 2^a | l | h] (M x 3K)  times  [W_h 2^b | W_h | W_l]^T,  a + b = 11   =   2^11 (h W_h + 2^-11 (l W_h + h W_l))
+// i.e. ONE fp16 GEMM with fp32 accumulation whose result carries a factor 2^11 that the consumer kernels here take back
+// (in_scale / residual_scale) -- powers of two, so nothing is rounded by the scaling.  b is chosen per weight matrix as large
+// as its largest entry allows, which leaves a = 0 (no loss of activation range) for any realistic weight.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -22,53 +30,95 @@ __device__ __forceinline__ float tf32_hi(float x) {
     return (fabsf(hi) <= 3.402823466e38f) ? hi : x;
 }
 
-__device__ __forceinline__ void store_split3(float *__restrict__ row_out, int K, int k, float4 v) {
-    float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-    // lo = v - hi exactly; where hi fell back to v itself (inf, NaN, overflow) the difference is defined as 0, not inf - inf
-    float4 lo = make_float4(hi.x == v.x ? 0.f : v.x - hi.x, hi.y == v.y ? 0.f : v.y - hi.y, hi.z == v.z ? 0.f : v.z - hi.z,
-                            hi.w == v.w ? 0.f : v.w - hi.w);
-    stg_stream4(row_out + k, hi);
-    stg_stream4(row_out + K + k, lo);
-    stg_stream4(row_out + 2 * K + k, hi);
-}
+// ---- operand writers.  kHalf == false: fp32 [hi | lo | hi] for the 3xTF32 GEMM; kHalf == true: fp16 [hi*2^a | lo*2^11 | hi]
+// for the 3xFP16 GEMM (see the header of this file), `hi_scale` = 2^a, `flag` raised when a value does not fit fp16.
+template <bool kHalf>
+struct Split3;
 
-__global__ void __launch_bounds__(256) split3_kernel(const float *__restrict__ x, float *__restrict__ out, long long M, int K) {
-    const int kq = K >> 2;
-    const long long total = M * kq;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long m = i / kq;
-        const int k = (int)(i - m * kq) * 4;
-        store_split3(out + m * 3 * K, K, k, ldg_stream4(x + m * K + k));
+template <>
+struct Split3<false> {
+    typedef float out_t;
+    static __device__ __forceinline__ void store(float *__restrict__ row_out, int K, int k, float4 v, float, int *) {
+        float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+        // lo = v - hi exactly; where hi fell back to v itself (inf, NaN, overflow) the difference is defined as 0, not inf - inf
+        float4 lo = make_float4(hi.x == v.x ? 0.f : v.x - hi.x, hi.y == v.y ? 0.f : v.y - hi.y, hi.z == v.z ? 0.f : v.z - hi.z,
+                                hi.w == v.w ? 0.f : v.w - hi.w);
+        stg_stream4(row_out + k, hi);
+        stg_stream4(row_out + K + k, lo);
+        stg_stream4(row_out + 2 * K + k, hi);
     }
+};
+
+__device__ __forceinline__ void split_half(float x, float hi_scale, __half &hs, __half &l, __half &h, bool &bad) {
+    h = __float2half_rn(x);
+    const float hf = __half2float(h);
+    l = __float2half_rn((x - hf) * 2048.0f);          // x - hf is exact in fp32; |(x - hf) * 2^11| <= |x| / 2
+    hs = __float2half_rn(hf * hi_scale);              // a power of two: exact unless it overflows
+    bad = bad || !(fabsf(hf * hi_scale) <= 65504.0f); // also catches NaN / inf inputs
 }
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+template <>
+struct Split3<true> {
+    typedef __half out_t;
+    static __device__ __forceinline__ void store(__half *__restrict__ row_out, int K, int k, float4 v, float hi_scale, int *flag) {
+        __half hs[4], l[4], h[4];
+        bool bad = false;
+        split_half(v.x, hi_scale, hs[0], l[0], h[0], bad);
+        split_half(v.y, hi_scale, hs[1], l[1], h[1], bad);
+        split_half(v.z, hi_scale, hs[2], l[2], h[2], bad);
+        split_half(v.w, hi_scale, hs[3], l[3], h[3], bad);
+        *reinterpret_cast<uint2 *>(row_out + k) = *reinterpret_cast<const uint2 *>(hs);
+        *reinterpret_cast<uint2 *>(row_out + K + k) = *reinterpret_cast<const uint2 *>(l);
+        *reinterpret_cast<uint2 *>(row_out + 2 * K + k) = *reinterpret_cast<const uint2 *>(h);
+        if (bad && flag) *flag = 1;
+    }
+};
 
-__global__ void __launch_bounds__(256) gelu_split3_kernel(const float *__restrict__ x, const float *__restrict__ bias,
-                                                          float *__restrict__ out, long long M, int K) {
+template <bool kHalf>
+__global__ void __launch_bounds__(256) split3_kernel(const float *__restrict__ x, typename Split3<kHalf>::out_t *__restrict__ out,
+                                                     long long M, int K, float in_scale, float hi_scale, int *__restrict__ flag) {
     const int kq = K >> 2;
     const long long total = M * kq;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long m = i / kq;
         const int k = (int)(i - m * kq) * 4;
         float4 v = ldg_stream4(x + m * K + k);
+        v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
+        Split3<kHalf>::store(out + m * 3 * K, K, k, v, hi_scale, flag);
+    }
+}
+
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+template <bool kHalf>
+__global__ void __launch_bounds__(256) gelu_split3_kernel(const float *__restrict__ x, const float *__restrict__ bias,
+                                                          typename Split3<kHalf>::out_t *__restrict__ out, long long M, int K,
+                                                          float in_scale, float hi_scale, int *__restrict__ flag) {
+    const int kq = K >> 2;
+    const long long total = M * kq;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / kq;
+        const int k = (int)(i - m * kq) * 4;
+        float4 v = ldg_stream4(x + m * K + k);
+        v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
         if (bias) {
             const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + k));
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
         }
-        store_split3(out + m * 3 * K, K, k, make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w)));
+        Split3<kHalf>::store(out + m * 3 * K, K, k, make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w)), hi_scale, flag);
     }
 }
 
 // One warp per row; the row (K <= 128*kChunks floats) stays in registers between the mean, the variance and the write.
-// Optional residual: x = x + res (+ res_bias) is formed first and written back to x_out (the running hidden state), so the
-// residual add, the LayerNorm and the operand split are one pass.
-template <int kChunks>
-__global__ void __launch_bounds__(256) layernorm_split3_kernel(const float *__restrict__ x, const float *__restrict__ res,
+// Optional residual: x = x + res * res_scale (+ res_bias) is formed first and written back to x_out (the running hidden state),
+// so the residual add, the LayerNorm and the operand split are one pass.
+template <int kChunks, bool kHalf>
+__global__ void __launch_bounds__(256) layernorm_split3_kernel(const float *__restrict__ x, const float *__restrict__ res, float res_scale,
                                                                const float *__restrict__ res_bias, float *__restrict__ x_out,
                                                                const float *__restrict__ gamma, const float *__restrict__ beta,
-                                                               float eps, float *__restrict__ out3, float *__restrict__ out1,
-                                                               long long M, int K) {
+                                                               float eps, typename Split3<kHalf>::out_t *__restrict__ out3,
+                                                               float *__restrict__ out1, long long M, int K, float hi_scale,
+                                                               int *__restrict__ flag) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (long long m = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * wpb) {
@@ -81,7 +131,7 @@ __global__ void __launch_bounds__(256) layernorm_split3_kernel(const float *__re
                 float4 t = ldg_stream4(x + m * K + k);
                 if (res) {
                     const float4 r = ldg_stream4(res + m * K + k);
-                    t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+                    t.x = fmaf(r.x, res_scale, t.x); t.y = fmaf(r.y, res_scale, t.y); t.z = fmaf(r.z, res_scale, t.z); t.w = fmaf(r.w, res_scale, t.w);
                     if (res_bias) {
                         const float4 b = __ldg(reinterpret_cast<const float4 *>(res_bias + k));
                         t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
@@ -112,7 +162,7 @@ __global__ void __launch_bounds__(256) layernorm_split3_kernel(const float *__re
                 const float4 b = __ldg(reinterpret_cast<const float4 *>(beta + k));
                 const float4 y = make_float4((v[c].x - mean) * rstd * g.x + b.x, (v[c].y - mean) * rstd * g.y + b.y,
                                              (v[c].z - mean) * rstd * g.z + b.z, (v[c].w - mean) * rstd * g.w + b.w);
-                if (out3) store_split3(out3 + m * 3 * K, K, k, y);
+                if (out3) Split3<kHalf>::store(out3 + m * 3 * K, K, k, y, hi_scale, flag);
                 if (out1) stg_stream4(out1 + m * K + k, y);
             }
         }
@@ -125,46 +175,97 @@ using namespace pnp;
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+namespace {
+template <bool kHalf>
+int run_split3(const float *x, void *out3, long long M, int K, float in_scale, float hi_scale, int *flag, cudaStream_t st) {
+    const long long total = M * (K / 4);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16));
+    typedef typename Split3<kHalf>::out_t out_t;
+    PNP_LAUNCH(kTf32Split, st, (split3_kernel<kHalf><<<grid, 256, 0, st>>>(x, reinterpret_cast<out_t *>(out3), M, K, in_scale, hi_scale, flag)));
+    return launch_status();
+}
+template <bool kHalf>
+int run_gelu_split3(const float *x, const float *bias, void *out3, long long M, int K, float in_scale, float hi_scale, int *flag,
+                    cudaStream_t st) {
+    const long long total = M * (K / 4);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16));
+    typedef typename Split3<kHalf>::out_t out_t;
+    PNP_LAUNCH(kGeluSplit, st, (gelu_split3_kernel<kHalf><<<grid, 256, 0, st>>>(x, bias, reinterpret_cast<out_t *>(out3), M, K, in_scale, hi_scale, flag)));
+    return launch_status();
+}
+template <bool kHalf>
+int run_layernorm_split3(const float *x, const float *residual, float res_scale, const float *residual_bias, float *x_out,
+                         const float *gamma, const float *beta, float eps, void *out3, float *out1, long long M, int K,
+                         float hi_scale, int *flag, cudaStream_t st) {
+    const int wpb = 8;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((M + wpb - 1) / wpb, (long long)kNumSMs * 8));
+    const int chunks = (K + 127) / 128;
+    typedef typename Split3<kHalf>::out_t out_t;
+#define PNP_LN(C)                                                                                                             \
+    PNP_LAUNCH(kLayernormSplit, st, (layernorm_split3_kernel<C, kHalf><<<grid, 32 * wpb, 0, st>>>(                             \
+                                        x, residual, res_scale, residual_bias, x_out, gamma, beta, eps, reinterpret_cast<out_t *>(out3), \
+                                        out1, M, K, hi_scale, flag)))
+    if (chunks <= 6) PNP_LN(6);
+    else if (chunks <= 8) PNP_LN(8);
+    else PNP_LN(16);
+#undef PNP_LN
+    return launch_status();
+}
+bool ln_args_ok(const float *x, const float *residual, const float *residual_bias, const float *x_out, const float *gamma,
+                const float *beta, const void *out3, const float *out1, long long M, int K) {
+    return x && gamma && beta && (out3 || out1) && M >= 0 && K >= 4 && K % 4 == 0 && K <= 128 * 16 && aligned16(x) &&
+           (!out3 || aligned16(out3)) && (!out1 || aligned16(out1)) && aligned16(gamma) && aligned16(beta) &&
+           (!residual || aligned16(residual)) && (!residual_bias || (residual && aligned16(residual_bias))) &&
+           (!x_out || (residual && aligned16(x_out)));
+}
+}  // namespace
+
 extern "C" int pnp_tf32_split3(const float *x, float *out3, long long M, int K, pnp_stream_t stream) {
     if (!x || !out3 || M < 0 || K < 4 || K % 4 || !aligned16(x) || !aligned16(out3)) return PNP_ERR_INVALID_ARGUMENT;
     if (M == 0) return PNP_OK;
-    cudaStream_t st = as_stream(stream);
-    const long long total = M * (K / 4);
-    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16));
-    PNP_LAUNCH(kTf32Split, st, split3_kernel<<<grid, 256, 0, st>>>(x, out3, M, K));
-    return launch_status();
+    return run_split3<false>(x, out3, M, K, 1.0f, 1.0f, nullptr, as_stream(stream));
 }
 
 extern "C" int pnp_gelu_tf32_split3(const float *x, const float *bias, float *out3, long long M, int K, pnp_stream_t stream) {
     if (!x || !out3 || M < 0 || K < 4 || K % 4 || !aligned16(x) || !aligned16(out3) || (bias && !aligned16(bias)))
         return PNP_ERR_INVALID_ARGUMENT;
     if (M == 0) return PNP_OK;
-    cudaStream_t st = as_stream(stream);
-    const long long total = M * (K / 4);
-    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16));
-    PNP_LAUNCH(kGeluSplit, st, gelu_split3_kernel<<<grid, 256, 0, st>>>(x, bias, out3, M, K));
-    return launch_status();
+    return run_gelu_split3<false>(x, bias, out3, M, K, 1.0f, 1.0f, nullptr, as_stream(stream));
 }
 
 extern "C" int pnp_layernorm_tf32_split3(const float *x, const float *residual, const float *residual_bias, float *x_out,
                                          const float *gamma, const float *beta, float eps, float *out3, float *out1, long long M,
                                          int K, pnp_stream_t stream) {
+    if (!ln_args_ok(x, residual, residual_bias, x_out, gamma, beta, out3, out1, M, K)) return PNP_ERR_INVALID_ARGUMENT;
+    if (M == 0) return PNP_OK;
+    return run_layernorm_split3<false>(x, residual, 1.0f, residual_bias, x_out, gamma, beta, eps, out3, out1, M, K, 1.0f, nullptr,
+                                       as_stream(stream));
+}
+
+extern "C" int pnp_fp16_split3(const float *x, float in_scale, float hi_scale, uint16_t *out3, int *overflow_flag, long long M, int K,
+                               pnp_stream_t stream) {
+    if (!x || !out3 || M < 0 || K < 4 || K % 4 || !aligned16(x) || (reinterpret_cast<uintptr_t>(out3) & 7)) return PNP_ERR_INVALID_ARGUMENT;
+    if (M == 0) return PNP_OK;
+    return run_split3<true>(x, out3, M, K, in_scale, hi_scale, overflow_flag, as_stream(stream));
+}
+
+extern "C" int pnp_gelu_fp16_split3(const float *x, float in_scale, const float *bias, float hi_scale, uint16_t *out3,
+                                    int *overflow_flag, long long M, int K, pnp_stream_t stream) {
+    if (!x || !out3 || M < 0 || K < 4 || K % 4 || !aligned16(x) || (reinterpret_cast<uintptr_t>(out3) & 7) || (bias && !aligned16(bias)))
+        return PNP_ERR_INVALID_ARGUMENT;
+    if (M == 0) return PNP_OK;
+    return run_gelu_split3<true>(x, bias, out3, M, K, in_scale, hi_scale, overflow_flag, as_stream(stream));
+}
+
+extern "C" int pnp_layernorm_fp16_split3(const float *x, const float *residual, float residual_scale, const float *residual_bias,
+                                         float *x_out, const float *gamma, const float *beta, float eps, float hi_scale,
+                                         uint16_t *out3, float *out1, int *overflow_flag, long long M, int K, pnp_stream_t stream) {
     if (!x || !gamma || !beta || (!out3 && !out1) || M < 0 || K < 4 || K % 4 || K > 128 * 16 || !aligned16(x) ||
-        (out3 && !aligned16(out3)) || (out1 && !aligned16(out1)) || !aligned16(gamma) || !aligned16(beta) ||
+        (out3 && (reinterpret_cast<uintptr_t>(out3) & 7)) || (out1 && !aligned16(out1)) || !aligned16(gamma) || !aligned16(beta) ||
         (residual && !aligned16(residual)) || (residual_bias && (!residual || !aligned16(residual_bias))) ||
         (x_out && (!residual || !aligned16(x_out))))
         return PNP_ERR_INVALID_ARGUMENT;
     if (M == 0) return PNP_OK;
-    cudaStream_t st = as_stream(stream);
-    const int wpb = 8;
-    const int grid = (int)std::max<long long>(1, std::min<long long>((M + wpb - 1) / wpb, (long long)kNumSMs * 8));
-    const int chunks = (K + 127) / 128;
-#define PNP_LN(C)                                                                                                      \
-    PNP_LAUNCH(kLayernormSplit, st, layernorm_split3_kernel<C><<<grid, 32 * wpb, 0, st>>>(x, residual, residual_bias, x_out, gamma, \
-                                                                                          beta, eps, out3, out1, M, K))
-    if (chunks <= 6) PNP_LN(6);
-    else if (chunks <= 8) PNP_LN(8);
-    else PNP_LN(16);
-#undef PNP_LN
-    return launch_status();
+    return run_layernorm_split3<true>(x, residual, residual_scale, residual_bias, x_out, gamma, beta, eps, out3, out1, M, K, hi_scale,
+                                      overflow_flag, as_stream(stream));
 }

@@ -383,6 +383,60 @@ def layernorm_tf32_split3(x, gamma, beta, eps, residual=None, residual_bias=None
     return out3, out1
 
 
+def fp16_split3(x, in_scale=1.0, hi_scale=1.0, flag=None):
+    """x [..., K] fp32 -> fp16 [..., 3K] = [h*hi_scale | (x-h)*2^11 | h] of x*in_scale (pnp_fp16_split3)."""
+    _req(x, torch.float32, "x")
+    K = x.shape[-1]
+    M = x.numel() // K
+    out = torch.empty(x.shape[:-1] + (3 * K,), dtype=torch.float16, device=x.device)
+    check(_lib.load().pnp_fp16_split3(_p(x), float(in_scale), float(hi_scale), _p(out), _p(flag), M, K, _stream()), "pnp_fp16_split3")
+    return out
+
+
+def gelu_fp16_split3(x, bias=None, in_scale=1.0, hi_scale=1.0, flag=None):
+    """fp16 [h*hi_scale | l | h] split of GELU(x*in_scale + bias) (exact erf form)."""
+    _req(x, torch.float32, "x")
+    K = x.shape[-1]
+    M = x.numel() // K
+    if bias is not None:
+        _req(bias, torch.float32, "bias", 1)
+        if bias.shape[0] != K:
+            raise PnpError("bias must be [K]")
+    out = torch.empty(x.shape[:-1] + (3 * K,), dtype=torch.float16, device=x.device)
+    check(_lib.load().pnp_gelu_fp16_split3(_p(x), float(in_scale), _p(bias), float(hi_scale), _p(out), _p(flag), M, K, _stream()),
+          "pnp_gelu_fp16_split3")
+    return out
+
+
+def layernorm_fp16_split3(x, gamma, beta, eps, residual=None, residual_scale=1.0, residual_bias=None, hi_scale=1.0, split=True,
+                          plain=False, flag=None):
+    """LayerNorm over the last dim of x (or of x + residual*residual_scale + residual_bias, which then REPLACES x in place).
+    Returns (fp16 split [..., 3K] or None, plain fp32 [..., K] or None)."""
+    _req(x, torch.float32, "x")
+    K = x.shape[-1]
+    M = x.numel() // K
+    _req(gamma, torch.float32, "gamma", 1)
+    _req(beta, torch.float32, "beta", 1)
+    if gamma.shape[0] != K or beta.shape[0] != K:
+        raise PnpError("gamma/beta must be [K]")
+    if residual is not None:
+        _req(residual, torch.float32, "residual")
+        if residual.shape != x.shape:
+            raise PnpError("residual shape mismatch")
+    if residual_bias is not None:
+        _req(residual_bias, torch.float32, "residual_bias", 1)
+        if residual is None or residual_bias.shape[0] != K:
+            raise PnpError("residual_bias needs a residual and must be [K]")
+    if not (split or plain):
+        raise PnpError("nothing to compute")
+    out3 = torch.empty(x.shape[:-1] + (3 * K,), dtype=torch.float16, device=x.device) if split else None
+    out1 = torch.empty_like(x) if plain else None
+    check(_lib.load().pnp_layernorm_fp16_split3(_p(x), _p(residual), float(residual_scale), _p(residual_bias),
+                                                _p(x if residual is not None else None), _p(gamma), _p(beta), float(eps), float(hi_scale),
+                                                _p(out3), _p(out1), _p(flag), M, K, _stream()), "pnp_layernorm_fp16_split3")
+    return out3, out1
+
+
 # ----------------------------------------------------------------------------------------------- (f)
 def argmax_channels(maps):
     """maps [B,C,N] -> int32 [B,N]; first max wins, NaN counts as max (DRV:387, DRV:1073)."""

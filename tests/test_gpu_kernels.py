@@ -496,3 +496,72 @@ def test_lowrank_blur_rejects_bad_arguments(dev, ops):
         ops.lowrank_blur_unary(torch.zeros(1, 2, 21, 21, device=dev), 64, 64, 0.15, False, True, 0.0)   # sigma must be positive
     with pytest.raises(PnpError):
         ops.lowrank_blur_unary(torch.zeros(1, 2, 21, 21), 64, 64, 0.15, False, True, 3.2)               # CPU tensor
+
+
+# ------------------------------------------------------------------------------------------------ 3xFP16 operand kernels
+def _split16_ref(t, hi_scale=1.0):
+    h = t.half()
+    l = ((t - h.float()) * 2048.0).half()
+    return torch.cat([(h.float() * hi_scale).half(), l, h], -1)
+
+
+@pytest.mark.parametrize("M,K,hi_scale", [(1, 4, 1.0), (37, 768, 1.0), (442 * 3, 1024, 8.0), (50, 4096, 1.0)])
+def test_fp16_split3_is_exact(dev, ops, M, K, hi_scale):
+    """[h*2^a | (x-h)*2^11 | h]: bit-equal to the torch restatement; h + l 2^-11 reproduces x to 2^-22 relative."""
+    x = (torch.randn(M, K, generator=torch.Generator().manual_seed(M + K)) * 3).to(dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    got = ops.fp16_split3(x, 1.0, hi_scale, flag)
+    assert got.dtype == torch.float16 and got.shape == (M, 3 * K)
+    assert torch.equal(got, _split16_ref(x, hi_scale)) and int(flag.item()) == 0
+    back = got[:, 2 * K:].double() + got[:, K:2 * K].double() / 2048.0
+    assert ((back - x.double()).abs() <= 2.0 ** -21 * x.double().abs() + 1e-10).all()      # (+ fp16's subnormal floor for tiny |x|)
+    scaled = ops.fp16_split3(x, 0.25, hi_scale, flag)                      # in_scale: the split of x/4, exactly
+    assert torch.equal(scaled, _split16_ref(x * 0.25, hi_scale))
+    big = x.clone()
+    big[0, 0] = 70000.0                                                    # beyond fp16: the flag is raised, nothing else
+    ops.fp16_split3(big, 1.0, hi_scale, flag)
+    assert int(flag.item()) == 1
+
+
+def test_fused_fp16_producers_match_torch(dev, ops):
+    g = torch.Generator().manual_seed(11)
+    M, K = 200, 1024
+    x, res = torch.randn(M, K, generator=g).to(dev) * 2 + 0.3, torch.randn(M, K, generator=g).to(dev) * 2048.0
+    gamma, beta, rb = (torch.randn(K, generator=g).to(dev) for _ in range(3))
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    xin = x.clone()
+    s3, plain = ops.layernorm_fp16_split3(xin, gamma, beta, 1e-6, residual=res, residual_scale=1.0 / 2048.0, residual_bias=rb, hi_scale=1.0,
+                                          split=True, plain=True, flag=flag)
+    want_x = x + res / 2048.0 + rb
+    _close(xin.cpu(), want_x.cpu(), rtol=1e-6, atol=1e-6)
+    want = torch.nn.functional.layer_norm(xin.double(), (K,), gamma.double(), beta.double(), 1e-6)
+    _close(plain.cpu(), want.cpu(), rtol=1e-5, atol=2e-6)
+    assert torch.equal(s3, _split16_ref(plain)) and int(flag.item()) == 0
+    f, b = torch.randn(64, 4096, generator=g).to(dev) * 3 * 2048.0, torch.randn(4096, generator=g).to(dev)
+    got = ops.gelu_fp16_split3(f, b, 1.0 / 2048.0, 1.0, flag)
+    want = torch.nn.functional.gelu((f / 2048.0 + b).double())
+    back = got[:, 8192:].double() + got[:, 4096:8192].double() / 2048.0
+    _close(back.cpu(), want.cpu(), rtol=1e-5, atol=1e-6)
+
+
+def test_tripled_fp16_gemm_is_fp32_grade(dev, ops):
+    """One fp16 GEMM over [x_h|x_l|x_h] x [W_h 2^11|W_h|W_l]^T (fp32 accumulate) against an fp64 product: an error of the order
+    of a native fp32 GEMM's, far below a plain fp16 product's."""
+    from pnp_ovss_b200.blip_itm import FP16_OUT_SCALE, _mm16, _w16
+    g = torch.Generator().manual_seed(2)
+    x, w = torch.randn(512, 1024, generator=g).to(dev), (torch.randn(768, 1024, generator=g) * 0.02).to(dev)
+    truth = x.double() @ w.double().t()
+    w16, hi_scale = _w16(w)
+    assert hi_scale == 1.0                                       # realistic weights leave the activations their full fp16 range
+    y = _mm16(ops.fp16_split3(x, 1.0, hi_scale), w16) / FP16_OUT_SCALE
+    err3 = (y.double() - truth).abs().max().item()
+    err32 = (x @ w.t()).double().sub(truth).abs().max().item()
+    err16 = (x.half() @ w.half().t()).double().sub(truth).abs().max().item()
+    assert err3 <= 12 * err32 + 1e-6, (err3, err32)              # tensor-core accumulation truncates: a few times native fp32
+    assert err3 * 30 <= err16, (err3, err16)
+    wbig = w.clone()
+    wbig[0, 0] = 100.0                                           # a weight above 32 moves part of the 2^11 to the activation side
+    w16b, hi_b = _w16(wbig)
+    assert hi_b == 4.0 and bool(torch.isfinite(w16b.float()).all())
+    yb = _mm16(ops.fp16_split3(x, 1.0, hi_b), w16b) / FP16_OUT_SCALE
+    assert (yb.double() - x.double() @ wbig.double().t()).abs().max().item() <= 1e-4 * 100
