@@ -254,10 +254,12 @@ int pnp_fp16_split3(const float *x, float in_scale, float hi_scale, uint16_t *ou
                     int K, pnp_stream_t stream);
 int pnp_gelu_fp16_split3(const float *x, float in_scale, const float *bias, float hi_scale, uint16_t *out3,
                          int *overflow_flag, long long M, int K, pnp_stream_t stream);
+/* ld_out3 = row stride of out3 in halves: 3K, or 3K + 8 to append the bias columns [bias_one, 1, 0 x 6] to every row -- against
+ * the weight rows [b_h 2^11 / bias_one, b_l, 0 x 6] (b = b_h + b_l 2^-11) the GEMM then adds the layer's bias by itself. */
 int pnp_layernorm_fp16_split3(const float *x, const float *residual, float residual_scale,
                               const float *residual_bias, float *x_out, const float *gamma, const float *beta,
-                              float eps, float hi_scale, uint16_t *out3, float *out1, int *overflow_flag, long long M,
-                              int K, pnp_stream_t stream);
+                              float eps, float hi_scale, uint16_t *out3, int ld_out3, float bias_one, float *out1,
+                              int *overflow_flag, long long M, int K, pnp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * In-situ kernel timing for bench.py's roofline (the one piece of process-global state in the library):

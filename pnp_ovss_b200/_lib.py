@@ -66,7 +66,7 @@ SIGNATURES = {
     "pnp_fp16_split3": (c_int, [c_void_p, c_float, c_float, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     "pnp_gelu_fp16_split3": (c_int, [c_void_p, c_float, c_void_p, c_float, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     "pnp_layernorm_fp16_split3": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,
-                                          c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
+                                          c_int, c_float, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     "pnp_profile_num_kernels": (c_int, []),
     "pnp_profile_start": (c_int, [ctypes.c_uint]),
     "pnp_profile_stop": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int), c_int]),

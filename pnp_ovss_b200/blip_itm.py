@@ -77,17 +77,34 @@ def _w3(weight):
 FP16_OUT_SCALE = 2048.0     # 2^11: the factor a 3xFP16 product carries (see _w16 / _mm16)
 
 
-def _w16(weight):
+FP16_BIAS_ONE = 64.0        # the constant the operand kernels write into the first bias column (see _w16)
+
+
+def _w16(weight, bias=None):
     """[N,K] frozen weight -> (fp16 [N,3K] = [W_h 2^b | W_h | W_l], 2^a) with W = W_h + W_l 2^-11 (W_h = fp16(W), W_l =
     fp16((W - W_h) 2^11)) and a + b = 11: the right-hand operand of the 3xFP16 GEMM whose left operand is
     [x_h 2^a | x_l | x_h] (ops.fp16_split3 and its fused producers).  b is as large as the largest |W| allows, so a is 0
-    (no loss of activation range) unless a weight exceeds 32."""
+    (no loss of activation range) unless a weight exceeds 32.
+
+    bias: 8 more columns [bias_h 2^11 / FP16_BIAS_ONE | bias_l | 0 x 6] -> [N,3K+8]; against the operand columns
+    [FP16_BIAS_ONE, 1, 0 x 6] (ops.layernorm_fp16_split3(bias_one=...)) the GEMM adds 2^11 * bias by itself."""
     w = weight.detach().contiguous().float()
     wmax = float(w.abs().max())
     b = 11 if wmax == 0 else max(0, min(11, int(math.floor(math.log2(65504.0 / wmax)))))
     w_h = w.half()
     w_l = ((w - w_h.float()) * FP16_OUT_SCALE).half()
-    return torch.cat([(w_h.float() * (2.0 ** b)).half(), w_h, w_l], 1).contiguous(), 2.0 ** (11 - b)
+    cols = [(w_h.float() * (2.0 ** b)).half(), w_h, w_l]
+    if bias is not None:
+        bv = bias.detach().float()
+        if float(bv.abs().max()) * FP16_OUT_SCALE / FP16_BIAS_ONE > 65000.0:
+            raise OverflowError("bias too large for the fp16 bias columns")
+        b_h = bv.half()
+        b_l = ((bv - b_h.float()) * FP16_OUT_SCALE).half()
+        tail = torch.zeros((w.shape[0], 8), dtype=torch.float16, device=w.device)
+        tail[:, 0] = (b_h.float() * (FP16_OUT_SCALE / FP16_BIAS_ONE)).half()
+        tail[:, 1] = b_l
+        cols.append(tail)
+    return torch.cat(cols, 1).contiguous(), 2.0 ** (11 - b)
 
 
 def _mm16(x16, w16):
@@ -184,11 +201,12 @@ class CrossAttentionSelf(nn.Module):
         return x.view(B, L, self.heads, D // self.heads).permute(0, 2, 1, 3)
 
     def forward(self, hidden, enc, enc_mask=None, kv=None):
-        """kv: (key(enc), value(enc)) [B,L,hidden] each, precomputed for all blocks in one GEMM (3xTF32 mode)."""
-        k, v = kv if kv is not None else (self.key(enc), self.value(enc))
+        """kv: (key(enc), value(enc), s) precomputed for all blocks in one tensor-core GEMM, both [B,L,hidden] and both carrying
+        the power-of-two factor s (1, or 2^11 in the 3xFP16 form), which the score scale and the context take back exactly."""
+        k, v, kv_s = kv if kv is not None else (self.key(enc), self.value(enc), 1.0)
         q, k, v = self._split(self.query(hidden)), self._split(k), self._split(v)
         scores = torch.matmul(q, k.transpose(-1, -2))                       # MED:228
-        scale = 1.0 / math.sqrt(q.shape[-1])                                 # MED:267
+        scale = 1.0 / math.sqrt(q.shape[-1]) / kv_s                          # MED:267
         if self.save_attention:
             probs = FusedXattnSoftmax.apply(scores, enc_mask, scale, self.capture)   # MED:269-283 fused
             if self.detach_probs:
@@ -200,6 +218,8 @@ class CrossAttentionSelf(nn.Module):
                 s = s + enc_mask[:, None, None, :]
             probs = torch.softmax(s, -1)
         ctx = torch.matmul(probs, v)                                         # MED:300
+        if kv_s != 1.0:
+            ctx = ctx * (1.0 / kv_s)
         B, h, T, d = ctx.shape
         return ctx.permute(0, 2, 1, 3).reshape(B, T, h * d)
 
@@ -314,16 +334,20 @@ class BlipITM(nn.Module):
         caches = self.__dict__.setdefault("_w3_cache", {})
         cache = caches.get(mode)
         if cache is None or cache["stamp"] != stamp:
-            prep = _w16 if mode == "3xfp16" else (lambda w: (_w3(w), 1.0))
+            half = mode == "3xfp16"
+            prep = (lambda w, b=None: _w16(w, b)) if half else (lambda w, b=None: (_w3(w), 1.0))
             with torch.no_grad():
                 xs = [lyr.crossattention.self for lyr in self.layer]
+                kv_bias = torch.cat([b for x in xs for b in (x.key.bias, x.value.bias)], 0).contiguous()
                 cache = {
                     "stamp": stamp,
                     "patch": prep(ve.patch_embed.weight.reshape(ve.patch_embed.weight.shape[0], -1)),
-                    "blocks": [tuple(prep(l.weight) for l in (blk.qkv, blk.proj, blk.fc1, blk.fc2)) for blk in ve.blocks],
-                    # key/value projections of all cross-attention blocks as one [layers*2*hidden, 3*enc_width] operand
-                    "kv": prep(torch.cat([w for x in xs for w in (x.key.weight, x.value.weight)], 0)),
-                    "kv_bias": torch.cat([b for x in xs for b in (x.key.bias, x.value.bias)], 0).contiguous(),
+                    # (qkv with its bias folded into the operand in the fp16 form, proj, fc1, fc2)
+                    "blocks": [(prep(blk.qkv.weight, blk.qkv.bias), prep(blk.proj.weight), prep(blk.fc1.weight), prep(blk.fc2.weight))
+                               for blk in ve.blocks],
+                    # key/value projections of all cross-attention blocks as one [layers*2*hidden, 3*enc_width (+8)] operand
+                    "kv": prep(torch.cat([w for x in xs for w in (x.key.weight, x.value.weight)], 0), kv_bias),
+                    "kv_bias": kv_bias,
                 }
             caches[mode] = cache
         return cache
@@ -356,10 +380,10 @@ class BlipITM(nn.Module):
         def split(x, in_scale, wt):
             return ops.fp16_split3(x, in_scale, wt[1], flag) if half else ops.tf32_split3(x)
 
-        def ln(x, norm, wt, r=None, rb=None, **kw):
+        def ln(x, norm, wt, r=None, rb=None, fold_bias=False, **kw):
             if half:
                 return ops.layernorm_fp16_split3(x, norm.weight, norm.bias, norm.eps, residual=r, residual_scale=inv, residual_bias=rb,
-                                                 hi_scale=wt[1], flag=flag, **kw)
+                                                 hi_scale=wt[1], flag=flag, bias_one=FP16_BIAS_ONE if fold_bias else None, **kw)
             return ops.layernorm_tf32_split3(x, norm.weight, norm.bias, norm.eps, residual=r, residual_bias=rb, **kw)
 
         B, _, S, _ = imgs.shape
@@ -372,30 +396,29 @@ class BlipITM(nn.Module):
         L = x.shape[1]
         r = rb = None
         for blk, (w_qkv, w_proj, w_fc1, w_fc2) in zip(ve.blocks, w["blocks"]):
-            h3, _ = ln(x, blk.norm1, w_qkv, r, rb)
-            if half:
-                qkv = torch.add(blk.qkv.bias, mm(h3, w_qkv[0]), alpha=inv)
-            else:
-                qkv = _mm3(h3, w_qkv[0], blk.qkv.bias)
+            h3, _ = ln(x, blk.norm1, w_qkv, r, rb, fold_bias=True)
+            # fp16 form: the GEMM adds the bias itself (operand columns) and q, k, v come out times 2^11 -- a power of two that
+            # the attention's scale (2^-22 / sqrt(d)) and the next split (2^-11) take back exactly
+            qkv = mm(h3, w_qkv[0]) if half else _mm3(h3, w_qkv[0], blk.qkv.bias)
             qkv = qkv.view(B, L, 3, blk.heads, D // blk.heads).permute(2, 0, 3, 1, 4)
-            a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
-            r = mm(split(a.transpose(1, 2).reshape(B, L, D).contiguous(), 1.0, w_proj), w_proj[0])
+            a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=inv * inv / math.sqrt(D // blk.heads))
+            r = mm(split(a.transpose(1, 2).reshape(B, L, D).contiguous(), inv, w_proj), w_proj[0])
             h3, _ = ln(x, blk.norm2, w_fc1, r, blk.proj.bias)
             f = mm(h3, w_fc1[0])
             g3 = (ops.gelu_fp16_split3(f, blk.fc1.bias, inv, w_fc2[1], flag) if half else ops.gelu_tf32_split3(f, blk.fc1.bias))
             r, rb = mm(g3, w_fc2[0]), blk.fc2.bias
-        return ln(x, ve.norm, w["kv"], r, rb, split=True, plain=want_plain)
+        return ln(x, ve.norm, w["kv"], r, rb, fold_bias=True, split=True, plain=want_plain)
 
     def _cross_kv3(self, enc3, mode="3xtf32"):
-        """key(enc) / value(enc) of every cross-attention block (MED:201-221) in one GEMM -> list of (k, v) [B,L,hidden]."""
+        """key(enc) / value(enc) of every cross-attention block (MED:201-221) in one GEMM -> list of (k, v, s) with k, v
+        [B,L,hidden] carrying the factor s (2^11 in the fp16 form: the cross-attention takes it back, see CrossAttentionSelf)."""
         w = self._weights3(mode)
         n = len(self.layer)
-        if mode == "3xfp16":
-            kv = torch.add(w["kv_bias"], _mm16(enc3, w["kv"][0]), alpha=1.0 / FP16_OUT_SCALE)
-        else:
-            kv = _mm3(enc3, w["kv"][0], w["kv_bias"])
+        half = mode == "3xfp16"
+        kv = _mm16(enc3, w["kv"][0]) if half else _mm3(enc3, w["kv"][0], w["kv_bias"])
         kv = kv.view(enc3.shape[0], enc3.shape[1], n, 2, -1)
-        return [(kv[:, :, i, 0], kv[:, :, i, 1]) for i in range(n)]
+        s = FP16_OUT_SCALE if half else 1.0
+        return [(kv[:, :, i, 0], kv[:, :, i, 1], s) for i in range(n)]
 
     def _encode(self, imgs):
         """(enc or None, per-block cross-attention (k, v) or [None]*n) for the current gemm_precision."""

@@ -118,10 +118,19 @@ __global__ void __launch_bounds__(256) layernorm_split3_kernel(const float *__re
                                                                const float *__restrict__ gamma, const float *__restrict__ beta,
                                                                float eps, typename Split3<kHalf>::out_t *__restrict__ out3,
                                                                float *__restrict__ out1, long long M, int K, float hi_scale,
-                                                               int *__restrict__ flag) {
+                                                               int *__restrict__ flag, int ld3, float tail_one) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (long long m = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); m < M; m += (long long)gridDim.x * wpb) {
+        if (kHalf && out3 && ld3 > 3 * K && lane == 0) {
+            // bias columns of the GEMM operand: [tail_one, 1, 0 x 6] against the weight rows [b_h 2^11 / tail_one, b_l, 0 x 6]
+            __half t[8];
+            t[0] = __float2half_rn(tail_one);
+            t[1] = __float2half_rn(1.0f);
+#pragma unroll
+            for (int i = 2; i < 8; ++i) t[i] = __float2half_rn(0.f);
+            *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(out3) + m * ld3 + 3 * K) = *reinterpret_cast<const uint4 *>(t);
+        }
         float4 v[kChunks];
         float sum = 0.f;
 #pragma unroll
@@ -162,7 +171,7 @@ __global__ void __launch_bounds__(256) layernorm_split3_kernel(const float *__re
                 const float4 b = __ldg(reinterpret_cast<const float4 *>(beta + k));
                 const float4 y = make_float4((v[c].x - mean) * rstd * g.x + b.x, (v[c].y - mean) * rstd * g.y + b.y,
                                              (v[c].z - mean) * rstd * g.z + b.z, (v[c].w - mean) * rstd * g.w + b.w);
-                if (out3) Split3<kHalf>::store(out3 + m * 3 * K, K, k, y, hi_scale, flag);
+                if (out3) Split3<kHalf>::store(out3 + m * ld3, K, k, y, hi_scale, flag);
                 if (out1) stg_stream4(out1 + m * K + k, y);
             }
         }
@@ -196,7 +205,7 @@ int run_gelu_split3(const float *x, const float *bias, void *out3, long long M, 
 template <bool kHalf>
 int run_layernorm_split3(const float *x, const float *residual, float res_scale, const float *residual_bias, float *x_out,
                          const float *gamma, const float *beta, float eps, void *out3, float *out1, long long M, int K,
-                         float hi_scale, int *flag, cudaStream_t st) {
+                         float hi_scale, int *flag, int ld3, float tail_one, cudaStream_t st) {
     const int wpb = 8;
     const int grid = (int)std::max<long long>(1, std::min<long long>((M + wpb - 1) / wpb, (long long)kNumSMs * 8));
     const int chunks = (K + 127) / 128;
@@ -204,7 +213,7 @@ int run_layernorm_split3(const float *x, const float *residual, float res_scale,
 #define PNP_LN(C)                                                                                                             \
     PNP_LAUNCH(kLayernormSplit, st, (layernorm_split3_kernel<C, kHalf><<<grid, 32 * wpb, 0, st>>>(                             \
                                         x, residual, res_scale, residual_bias, x_out, gamma, beta, eps, reinterpret_cast<out_t *>(out3), \
-                                        out1, M, K, hi_scale, flag)))
+                                        out1, M, K, hi_scale, flag, ld3, tail_one)))
     if (chunks <= 6) PNP_LN(6);
     else if (chunks <= 8) PNP_LN(8);
     else PNP_LN(16);
@@ -239,7 +248,7 @@ extern "C" int pnp_layernorm_tf32_split3(const float *x, const float *residual, 
     if (!ln_args_ok(x, residual, residual_bias, x_out, gamma, beta, out3, out1, M, K)) return PNP_ERR_INVALID_ARGUMENT;
     if (M == 0) return PNP_OK;
     return run_layernorm_split3<false>(x, residual, 1.0f, residual_bias, x_out, gamma, beta, eps, out3, out1, M, K, 1.0f, nullptr,
-                                       as_stream(stream));
+                                       3 * K, 0.f, as_stream(stream));
 }
 
 extern "C" int pnp_fp16_split3(const float *x, float in_scale, float hi_scale, uint16_t *out3, int *overflow_flag, long long M, int K,
@@ -259,7 +268,9 @@ extern "C" int pnp_gelu_fp16_split3(const float *x, float in_scale, const float 
 
 extern "C" int pnp_layernorm_fp16_split3(const float *x, const float *residual, float residual_scale, const float *residual_bias,
                                          float *x_out, const float *gamma, const float *beta, float eps, float hi_scale,
-                                         uint16_t *out3, float *out1, int *overflow_flag, long long M, int K, pnp_stream_t stream) {
+                                         uint16_t *out3, int ld_out3, float bias_one, float *out1, int *overflow_flag, long long M,
+                                         int K, pnp_stream_t stream) {
+    if (out3 && ld_out3 != 3 * K && (ld_out3 != 3 * K + 8 || !aligned16(out3))) return PNP_ERR_INVALID_ARGUMENT;
     if (!x || !gamma || !beta || (!out3 && !out1) || M < 0 || K < 4 || K % 4 || K > 128 * 16 || !aligned16(x) ||
         (out3 && (reinterpret_cast<uintptr_t>(out3) & 7)) || (out1 && !aligned16(out1)) || !aligned16(gamma) || !aligned16(beta) ||
         (residual && !aligned16(residual)) || (residual_bias && (!residual || !aligned16(residual_bias))) ||
@@ -267,5 +278,5 @@ extern "C" int pnp_layernorm_fp16_split3(const float *x, const float *residual, 
         return PNP_ERR_INVALID_ARGUMENT;
     if (M == 0) return PNP_OK;
     return run_layernorm_split3<true>(x, residual, residual_scale, residual_bias, x_out, gamma, beta, eps, out3, out1, M, K, hi_scale,
-                                      overflow_flag, as_stream(stream));
+                                      overflow_flag, out3 ? ld_out3 : 3 * K, bias_one, as_stream(stream));
 }

@@ -409,9 +409,10 @@ def gelu_fp16_split3(x, bias=None, in_scale=1.0, hi_scale=1.0, flag=None):
 
 
 def layernorm_fp16_split3(x, gamma, beta, eps, residual=None, residual_scale=1.0, residual_bias=None, hi_scale=1.0, split=True,
-                          plain=False, flag=None):
+                          plain=False, flag=None, bias_one=None):
     """LayerNorm over the last dim of x (or of x + residual*residual_scale + residual_bias, which then REPLACES x in place).
-    Returns (fp16 split [..., 3K] or None, plain fp32 [..., K] or None)."""
+    Returns (fp16 split [..., 3K] or None, plain fp32 [..., K] or None).  bias_one: append the 8 bias columns
+    [bias_one, 1, 0 x 6] to every row of the split ([..., 3K + 8]) so that the GEMM adds the next layer's bias itself."""
     _req(x, torch.float32, "x")
     K = x.shape[-1]
     M = x.numel() // K
@@ -429,11 +430,13 @@ def layernorm_fp16_split3(x, gamma, beta, eps, residual=None, residual_scale=1.0
             raise PnpError("residual_bias needs a residual and must be [K]")
     if not (split or plain):
         raise PnpError("nothing to compute")
-    out3 = torch.empty(x.shape[:-1] + (3 * K,), dtype=torch.float16, device=x.device) if split else None
+    ld3 = 3 * K + (8 if bias_one is not None else 0)
+    out3 = torch.empty(x.shape[:-1] + (ld3,), dtype=torch.float16, device=x.device) if split else None
     out1 = torch.empty_like(x) if plain else None
     check(_lib.load().pnp_layernorm_fp16_split3(_p(x), _p(residual), float(residual_scale), _p(residual_bias),
                                                 _p(x if residual is not None else None), _p(gamma), _p(beta), float(eps), float(hi_scale),
-                                                _p(out3), _p(out1), _p(flag), M, K, _stream()), "pnp_layernorm_fp16_split3")
+                                                _p(out3), ld3, float(bias_one or 0.0), _p(out1), _p(flag), M, K, _stream()),
+          "pnp_layernorm_fp16_split3")
     return out3, out1
 
 
