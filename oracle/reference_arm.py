@@ -41,7 +41,7 @@ class ReferenceCrossAttention(nn.Module):
         B, L, D = x.shape
         return x.view(B, L, self.heads, D // self.heads).permute(0, 2, 1, 3)
 
-    def forward(self, hidden, enc, enc_mask=None, kv=None):
+    def forward(self, hidden, enc, enc_mask=None, kv=None, lin=None):
         q, k, v = self._split(self.query(hidden)), self._split(self.key(enc)), self._split(self.value(enc))
         scores = torch.matmul(q, k.transpose(-1, -2))          # MED:228
         scores = scores / math.sqrt(q.shape[-1])               # MED:267

@@ -139,6 +139,38 @@ def _mm3(x3, w3, bias=None):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+def _mm3_single(x3, w3, bias=None):
+    """The three products in ONE depth-3K TF32 GEMM (one launch; used for the small text-side GEMMs, which are launch-bound)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        return F.linear(x3, w3, bias)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+class _Linear3(torch.autograd.Function):
+    """y = x W^T + b for a FROZEN weight on the TF32 tensor cores at fp32 grade (exact hi/lo split, three products), forward and
+    backward: dL/dx = dL/dy W is the same kind of product against the split of W^T.  TF32 keeps fp32's exponent range, so the
+    tiny gradients of the trimmed backward (1e-6 and below) lose nothing -- which is why the text side does not use fp16."""
+
+    @staticmethod
+    def forward(ctx, x, w3, wt3, bias):
+        ctx.wt3 = wt3
+        ctx.x_shape = x.shape
+        y = _mm3(ops.tf32_split3(x.reshape(-1, x.shape[-1]).contiguous()), w3, bias)
+        return y.view(*x.shape[:-1], w3.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        gx = _mm3(ops.tf32_split3(gy.reshape(-1, gy.shape[-1]).contiguous()), ctx.wt3)
+        return gx.view(ctx.x_shape), None, None, None
+
+
+def _plain_linear(module, x):
+    return module(x)
+
+
 class _VitBlock(nn.Module):
     def __init__(self, dim, heads, mlp_ratio=4.0):
         super().__init__()
@@ -200,11 +232,11 @@ class CrossAttentionSelf(nn.Module):
         B, L, D = x.shape
         return x.view(B, L, self.heads, D // self.heads).permute(0, 2, 1, 3)
 
-    def forward(self, hidden, enc, enc_mask=None, kv=None):
+    def forward(self, hidden, enc, enc_mask=None, kv=None, lin=_plain_linear):
         """kv: (key(enc), value(enc), s) precomputed for all blocks in one tensor-core GEMM, both [B,L,hidden] and both carrying
         the power-of-two factor s (1, or 2^11 in the 3xFP16 form), which the score scale and the context take back exactly."""
         k, v, kv_s = kv if kv is not None else (self.key(enc), self.value(enc), 1.0)
-        q, k, v = self._split(self.query(hidden)), self._split(k), self._split(v)
+        q, k, v = self._split(lin(self.query, hidden)), self._split(k), self._split(v)
         scores = torch.matmul(q, k.transpose(-1, -2))                       # MED:228
         scale = 1.0 / math.sqrt(q.shape[-1]) / kv_s                          # MED:267
         if self.save_attention:
@@ -239,15 +271,15 @@ class _BertLayer(nn.Module):
         self.out = nn.Linear(inter, hidden)
         self.out_ln = nn.LayerNorm(hidden, eps=eps)
 
-    def self_attention(self, x, add_mask):
+    def self_attention(self, x, add_mask, lin=_plain_linear):
         B, T, D = x.shape
         sp = lambda t: t.view(B, T, self.heads, D // self.heads).permute(0, 2, 1, 3)
-        a = F.scaled_dot_product_attention(sp(self.q(x)), sp(self.k(x)), sp(self.v(x)), attn_mask=add_mask)
-        return self.attn_ln(self.attn_out(a.permute(0, 2, 1, 3).reshape(B, T, D)) + x)
+        a = F.scaled_dot_product_attention(sp(lin(self.q, x)), sp(lin(self.k, x)), sp(lin(self.v, x)), attn_mask=add_mask)
+        return self.attn_ln(lin(self.attn_out, a.permute(0, 2, 1, 3).reshape(B, T, D)) + x)
 
-    def cross_and_ffn(self, x, enc, kv=None):
-        x = self.cross_ln(self.cross_out(self.crossattention.self(x, enc, kv=kv)) + x)
-        return self.out_ln(self.out(F.gelu(self.inter(x))) + x)
+    def cross_and_ffn(self, x, enc, kv=None, lin=_plain_linear):
+        x = self.cross_ln(lin(self.cross_out, self.crossattention.self(x, enc, kv=kv, lin=lin)) + x)
+        return self.out_ln(lin(self.out, F.gelu(lin(self.inter, x))) + x)
 
 
 class _TextEncoderView:
@@ -288,6 +320,21 @@ class BlipITM(nn.Module):
         elif isinstance(m, nn.LayerNorm):
             nn.init.ones_(m.weight)
             nn.init.zeros_(m.bias)
+
+    _CACHES = ("_w3_cache", "_text3_cache", "_text_graphs", "_text_graph_stamp", "_vit_graphs", "_kv_buffers", "_fp16_flags")
+
+    def __deepcopy__(self, memo):
+        """Copies the module without its derived state (weight splits, K/V buffers, captured CUDA graphs): all of it is rebuilt
+        on first use, and a CUDA graph cannot be copied."""
+        import copy
+        saved = {k: self.__dict__.pop(k) for k in self._CACHES if k in self.__dict__}
+        try:
+            new = self.__class__.__new__(self.__class__)
+            memo[id(self)] = new
+            new.__dict__ = copy.deepcopy(self.__dict__, memo)
+            return new
+        finally:
+            self.__dict__.update(saved)
 
     # ---- the reference's attribute path / checkpoint ---------------------------------------------------
     @property
@@ -352,6 +399,26 @@ class BlipITM(nn.Module):
             caches[mode] = cache
         return cache
 
+    def _text_linear(self):
+        """lin(module, x) for the text side: in the tensor-core modes (frozen weights, CUDA) every nn.Linear of the BERT layers
+        runs through _Linear3 (forward and backward on the TF32 tensor cores at fp32 grade); plain module call otherwise."""
+        if self.gemm_precision not in self.SPLIT_MODES or any(p.requires_grad for p in self.layer.parameters()):
+            return _plain_linear
+        cache = self.__dict__.setdefault("_text3_cache", {})
+
+        def lin(module, x):
+            if not x.is_cuda or module.in_features % 4 or module.out_features % 4:
+                return module(x)
+            w = module.weight
+            ent = cache.get(id(module))
+            if ent is None or ent[0] != (w.data_ptr(), w._version):
+                with torch.no_grad():
+                    ent = ((w.data_ptr(), w._version), _w3(w), _w3(w.t().contiguous()))
+                cache[id(module)] = ent
+            return _Linear3.apply(x, ent[1], ent[2], module.bias)
+
+        return lin
+
     def fp16_overflow_flag(self, device):
         """Device int32 raised by the 3xFP16 operand kernels when an activation does not fit fp16; read it once per run
         (`check_fp16_overflow`), not per pass."""
@@ -415,19 +482,83 @@ class BlipITM(nn.Module):
         w = self._weights3(mode)
         n = len(self.layer)
         half = mode == "3xfp16"
-        kv = _mm16(enc3, w["kv"][0]) if half else _mm3(enc3, w["kv"][0], w["kv_bias"])
-        kv = kv.view(enc3.shape[0], enc3.shape[1], n, 2, -1)
+        # One persistent output buffer per shape: the text-pass CUDA graph reads K/V at fixed addresses, so the GEMM writes there
+        # directly and nothing is copied.  (Passes on one stream are ordered; a pass never outlives the next one's GEMM.)
+        bufs = self.__dict__.setdefault("_kv_buffers", {})
+        M, N = enc3.shape[0] * enc3.shape[1], w["kv"][0].shape[0]
+        key = (M, N, str(enc3.device))
+        if key not in bufs:
+            bufs[key] = torch.empty((M, N), dtype=torch.float32, device=enc3.device)
+        out = bufs[key]
+        x2 = enc3.reshape(M, enc3.shape[-1])
+        if half:
+            torch.mm(x2, w["kv"][0].t(), out_dtype=torch.float32, out=out)
+        else:
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = True
+            try:
+                K = w["kv"][0].shape[1] // 3
+                torch.addmm(w["kv_bias"], x2[:, :K], w["kv"][0][:, :K].t(), out=out)
+                out.addmm_(x2[:, K:], w["kv"][0][:, K:].t())
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        kv = out.view(enc3.shape[0], enc3.shape[1], n, 2, -1)
         s = FP16_OUT_SCALE if half else 1.0
         return [(kv[:, :, i, 0], kv[:, :, i, 1], s) for i in range(n)]
+
+    USE_VIT_GRAPH = True
 
     def _encode(self, imgs):
         """(enc or None, per-block cross-attention (k, v) or [None]*n) for the current gemm_precision."""
         mode = self.gemm_precision
         if mode in self.SPLIT_MODES and imgs.is_cuda and not any(p.requires_grad for p in self.visual_encoder.parameters()):
             with torch.no_grad():
+                if self.USE_VIT_GRAPH:
+                    kvs = self._encode_graphed(imgs, mode)
+                    if kvs is not None:
+                        return None, kvs
                 enc3, _ = self._vit3(imgs, mode=mode)
                 return None, self._cross_kv3(enc3, mode)
         return self._vit(imgs), [None] * len(self.layer)
+
+    def _encode_graphed(self, imgs, mode):
+        """The encoder pass + the K/V GEMM replayed from a CUDA graph (one per image shape): ~330 launches whose host-side issue
+        otherwise leaves the GPU idle for ~3 ms per pass.  The graph's only output is the persistent K/V buffer of _cross_kv3.
+        Returns None when capture is impossible here."""
+        graphs = self.__dict__.setdefault("_vit_graphs", {})
+        self._weights3(mode)                       # (re)builds the splits when a weight changed ...
+        stamp = self.__dict__["_w3_cache"][mode]["stamp"]
+        key = (tuple(imgs.shape), str(imgs.device), mode)
+        ent = graphs.get(key)
+        if ent is not None and ent is not False and ent[2] != stamp:
+            ent = None                             # ... and a graph captured with the old splits is dropped
+        if ent is False:
+            return None
+        if ent is None:
+            static = imgs.clone()
+            try:
+                cur = torch.cuda.current_stream()
+                side = torch.cuda.Stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        self._cross_kv3(self._vit3(static, mode=mode)[0], mode)
+                cur.wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    kvs = self._cross_kv3(self._vit3(static, mode=mode)[0], mode)
+                ent = (g, static, stamp, kvs)
+            except Exception as e:  # noqa: BLE001 -- eager is always correct
+                import warnings
+                warnings.warn("encoder CUDA graph capture failed (%s); running it eagerly" % str(e).splitlines()[0][:200])
+                torch.cuda.synchronize()
+                graphs[key] = False
+                return None
+            graphs[key] = ent
+        g, static, _, kvs = ent
+        static.copy_(imgs)
+        g.replay()
+        return kvs
 
     def forward(self, visual_input, text_input=None, match_head="itm"):
         """ITM logits [B,2] (BITM:217-249, match_head='itm').  Also takes the LAVIS call form
@@ -439,10 +570,90 @@ class BlipITM(nn.Module):
         ids, att = self._tokenize(text_input, visual_input.device)
         enc, kvs = self._encode(visual_input)
         add_mask = ((1.0 - att.float()) * -10000.0)[:, None, None, :]
+        lin = self._text_linear()
         x = self._embed(ids)
         for lyr, kv in zip(self.layer, kvs):
-            x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc, kv)
+            x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask, lin), enc, kv, lin)
         return self.itm_head(x[:, 0])
+
+    def _text_pass(self, ids, add_mask, token_mask, enc, kvs, layer, head, cap):
+        """The text side of the trimmed GradCAM pass: BERT layers below `layer` without grad, the block's attention
+        probabilities as the leaf, the loss differentiated w.r.t. them, the fused GradCAM kernel.  -> (cam [B,T-1,K-1], logits)."""
+        lin = self._text_linear()
+        with torch.no_grad():
+            x = self._embed(ids)
+            for lyr, kv in zip(self.layer[:layer], kvs):
+                x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask, lin), enc, kv, lin)
+            x = self.layer[layer].self_attention(x, add_mask, lin)
+        with torch.enable_grad():
+            x = self.layer[layer].cross_and_ffn(x, enc, kvs[layer], lin)   # probs become a leaf inside (detach_probs)
+            for lyr, kv in zip(self.layer[layer + 1:], kvs[layer + 1:]):
+                x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask, lin), enc, kv, lin)
+            out = self.itm_head(x[:, 0])
+            loss = out[:, 1].sum()
+            (dprobs,) = torch.autograd.grad(loss, cap.probs)
+        cap.dprobs = dprobs
+        _, cam = ops.softmax_bwd_gradcam(cap.probs.detach(), dprobs.contiguous(), token_mask, head,
+                                         1.0 / math.sqrt(64), need_dscores=False, need_gradcam=True)
+        return cam, out.detach()
+
+    # ---- the text pass as a CUDA graph -----------------------------------------------------------------
+    USE_TEXT_GRAPH = True
+
+    def _text_pass_graphed(self, ids, add_mask, token_mask, kvs, layer, head):
+        """_text_pass replayed from a CUDA graph: the text side is ~700 launches of kernels that each run for microseconds
+        (B*T = 875 rows at cfg1), so issued one by one it is bound by launch latency, not by the GPU.  One graph per
+        (shapes, block, head); inputs are copied into the graph's static buffers, the result is copied out.
+        Returns None when capture is impossible here (the caller then runs the eager pass)."""
+        graphs = self.__dict__.setdefault("_text_graphs", {})
+        stamp = tuple(p._version for p in self.layer.parameters()) + tuple(p._version for p in self.itm_head.parameters())
+        if self.__dict__.get("_text_graph_stamp") != stamp:     # a graph holds the addresses of the weight splits it was captured with
+            graphs.clear()
+            self.__dict__["_text_graph_stamp"] = stamp
+        k0, v0, s0 = kvs[0]
+        key = (tuple(ids.shape), tuple(k0.shape), k0.data_ptr(), int(layer), int(head), float(s0), str(ids.device), token_mask.shape[1],
+               self.gemm_precision)
+        ent = graphs.get(key)
+        if ent is False:
+            return None
+        if ent is None:
+            st = {"ids": ids.clone(), "add_mask": add_mask.clone(), "token_mask": token_mask.clone()}
+            skvs = kvs                             # views of the persistent K/V buffer of _cross_kv3: fixed addresses
+            xattn = self.layer[layer].crossattention.self
+
+            def run():
+                cap = GradcamCapture(head, st["token_mask"])
+                xattn.save_attention, xattn.capture, xattn.detach_probs = True, cap, True
+                try:
+                    return self._text_pass(st["ids"], st["add_mask"], st["token_mask"], None, skvs, layer, head, cap)
+                finally:
+                    xattn.save_attention, xattn.capture, xattn.detach_probs = False, None, False
+
+            try:
+                cur = torch.cuda.current_stream()
+                side = torch.cuda.Stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):      # warm-up off the capture stream (autograd buffers, cuBLAS workspaces)
+                    for _ in range(2):
+                        run()
+                cur.wait_stream(side)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st["cam"], st["out"] = run()
+                ent = (g, st)
+            except Exception as e:  # noqa: BLE001 -- a failed capture must not take the pass down; eager is always correct
+                import warnings
+                warnings.warn("text-pass CUDA graph capture failed (%s); running it eagerly" % str(e).splitlines()[0][:200])
+                torch.cuda.synchronize()
+                graphs[key] = False
+                return None
+            graphs[key] = ent
+        g, st = ent
+        st["ids"].copy_(ids)
+        st["add_mask"].copy_(add_mask)
+        st["token_mask"].copy_(token_mask)
+        g.replay()
+        return st["cam"].clone(), st["out"].clone()
 
     # ---- GradCAM of one (block, head) ----------------------------------------------------------------
     def gradcam(self, visual_input, text_input, tokenized_text, layer=7, head=9, full_backward=False):
@@ -473,20 +684,10 @@ class BlipITM(nn.Module):
             else:
                 with torch.no_grad():
                     enc, kvs = self._encode(visual_input)
-                    x = self._embed(ids)
-                    for lyr, kv in zip(self.layer[:layer], kvs):
-                        x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc, kv)
-                    x = self.layer[layer].self_attention(x, add_mask)
-                with torch.enable_grad():
-                    x = self.layer[layer].cross_and_ffn(x, enc, kvs[layer])   # probs become a leaf inside (detach_probs)
-                    for lyr, kv in zip(self.layer[layer + 1:], kvs[layer + 1:]):
-                        x = lyr.cross_and_ffn(lyr.self_attention(x, add_mask), enc, kv)
-                    out = self.itm_head(x[:, 0])
-                    loss = out[:, 1].sum()
-                    (dprobs,) = torch.autograd.grad(loss, cap.probs)
-                cap.dprobs = dprobs
-                _, cam = ops.softmax_bwd_gradcam(cap.probs.detach(), dprobs.contiguous(), token_mask, head,
-                                                 1.0 / math.sqrt(64), need_dscores=False, need_gradcam=True)
+                res = None
+                if self.USE_TEXT_GRAPH and enc is None and self._text_linear() is not _plain_linear:
+                    res = self._text_pass_graphed(ids, add_mask, token_mask, kvs, layer, head)
+                cam, out = res if res is not None else self._text_pass(ids, add_mask, token_mask, enc, kvs, layer, head, cap)
         finally:
             xattn.save_attention, xattn.capture, xattn.detach_probs = False, None, False
         P = self.patch_num

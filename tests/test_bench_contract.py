@@ -51,7 +51,7 @@ def test_every_baseline_config_has_a_workload():
     T = max(len(w["tok"].encode(c)) for c in w["captions"])
     assert T <= 500                                               # fits the reference's max_length=500 padding (DRV:317-319)
     args = bench.parse_args(["--config", "4", "--scaling", "strong"])
-    assert args.config == 4 and args.gemm == "3xtf32" and args.scaling == "strong" and bench.STRONG_IMAGES % 35 == 0
+    assert args.config == 4 and args.gemm == "3xfp16" and args.schedule == "serial" and args.scaling == "strong" and bench.STRONG_IMAGES % 35 == 0
 
 
 def test_algorithmic_bytes_cover_the_timed_kernel_classes():
