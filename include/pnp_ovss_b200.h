@@ -12,7 +12,11 @@
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and the call returns immediately;
  *   - return value: PNP_OK (0) or a negative code; no exception crosses the boundary;
  *   - tensors are dense, row-major, fp32 unless stated; shapes are written [outer, ..., inner];
- *   - one host thread per process, one process per GPU (DRV:1439 mp.spawn); no global mutable state.
+ *   - one host thread per process, one process per GPU (DRV:1439 mp.spawn).  Process-global state is limited to: the
+ *     in-situ profiler (pnp_profile_*, off by default), the per-kernel "allow > 48 KB of dynamic shared memory" function
+ *     attribute (idempotent), and tuning environment variables read once (PNP_GRID_MULT_*, PNP_BLUR_FUSE*, PNP_UPDATE_*,
+ *     PNP_VALUE_PITCH: experiment switches, unset in production).  No data is cached between calls.
+ *   - exception to "returns immediately": pnp_lattice_finish synchronises the stream (it reads the vertex count back).
  */
 #ifndef PNP_OVSS_B200_H
 #define PNP_OVSS_B200_H
@@ -261,6 +265,14 @@ int pnp_layernorm_fp16_split3(const float *x, const float *residual, float resid
                               float eps, float hi_scale, uint16_t *out3, int ld_out3, float bias_one, float *out1,
                               int *overflow_flag, long long M, int K, pnp_stream_t stream);
 
+/* Encoder self-attention softmax(Q K^T * softmax_scale) V (VIT:93-119) at fp32-grade accuracy on the fp16 tensor cores: every
+ * operand split as above, each product as three fp16 mma with fp32 accumulation (main term and corrections apart), online
+ * softmax in fp32; nothing of size L x L touches HBM.  qkv [B,L,3,H,D] fp32 exactly as the fused qkv GEMM leaves it (each value
+ * times 1/in_scale, in_scale a power of two; 1 for a plain projection); out [B,L,H*D] fp32, unscaled.  D must be 64. */
+size_t pnp_attention_fp16x3_workspace_bytes(int B, int L, int H, int D);
+int pnp_attention_fp16x3(const float *qkv, float in_scale, float softmax_scale, float *out, void *workspace,
+                         size_t workspace_bytes, int *overflow_flag, int B, int L, int H, int D, pnp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * In-situ kernel timing for bench.py's roofline (the one piece of process-global state in the library):
  * between start and stop, every launch of a kernel class whose bit is set in kernel_mask is bracketed by
@@ -269,7 +281,7 @@ int pnp_layernorm_fp16_split3(const float *x, const float *residual, float resid
  * 8 blur_horizontal, 9 blur_normalize, 10 lattice_build (all of it), 11 crf_unary, 12 crf_splat_bilateral,
  * 13 crf_blur_axis_bilateral, 14 crf_meanfield_update, 15 argmax_channels, 16 confusion, 17 crf_splat_spatial,
  * 18 crf_blur_axis_spatial, 19 tf32_split3, 20 gelu_tf32_split3, 21 layernorm_tf32_split3, 22 lowrank_blur,
- * 23 lowrank_unary, 24 background_blur (pnp_profile_kernel_name() is authoritative).
+ * 23 lowrank_unary, 24 background_blur, 25 attention_fp16x3 (pnp_profile_kernel_name() is authoritative).
  * ---------------------------------------------------------------------------------------------------- */
 int pnp_profile_num_kernels(void); /* ids are 1 .. pnp_profile_num_kernels()-1 */
 int pnp_profile_start(unsigned kernel_mask);

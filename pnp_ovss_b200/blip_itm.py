@@ -467,9 +467,15 @@ class BlipITM(nn.Module):
             # fp16 form: the GEMM adds the bias itself (operand columns) and q, k, v come out times 2^11 -- a power of two that
             # the attention's scale (2^-22 / sqrt(d)) and the next split (2^-11) take back exactly
             qkv = mm(h3, w_qkv[0]) if half else _mm3(h3, w_qkv[0], blk.qkv.bias)
-            qkv = qkv.view(B, L, 3, blk.heads, D // blk.heads).permute(2, 0, 3, 1, 4)
-            a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=inv * inv / math.sqrt(D // blk.heads))
-            r = mm(split(a.transpose(1, 2).reshape(B, L, D).contiguous(), inv, w_proj), w_proj[0])
+            hd = D // blk.heads
+            if half and self.USE_FUSED_ATTENTION and hd == 64:
+                # the attention itself on the fp16 tensor cores with the same hi/lo split (pnp_attention_fp16x3): unscaled output
+                a = ops.attention_fp16x3(qkv.view(B, L, 3, blk.heads, hd), inv, 1.0 / math.sqrt(hd), flag)
+                r = mm(split(a, 1.0, w_proj), w_proj[0])
+            else:
+                qkv = qkv.view(B, L, 3, blk.heads, hd).permute(2, 0, 3, 1, 4)
+                a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=inv * inv / math.sqrt(hd))
+                r = mm(split(a.transpose(1, 2).reshape(B, L, D).contiguous(), inv, w_proj), w_proj[0])
             h3, _ = ln(x, blk.norm2, w_fc1, r, blk.proj.bias)
             f = mm(h3, w_fc1[0])
             g3 = (ops.gelu_fp16_split3(f, blk.fc1.bias, inv, w_fc2[1], flag) if half else ops.gelu_tf32_split3(f, blk.fc1.bias))
@@ -507,6 +513,7 @@ class BlipITM(nn.Module):
         return [(kv[:, :, i, 0], kv[:, :, i, 1], s) for i in range(n)]
 
     USE_VIT_GRAPH = True
+    USE_FUSED_ATTENTION = True     # 3xfp16 mode: encoder attention through pnp_attention_fp16x3 instead of torch's fp32 SDPA
 
     def _encode(self, imgs):
         """(enc or None, per-block cross-attention (k, v) or [None]*n) for the current gemm_precision."""

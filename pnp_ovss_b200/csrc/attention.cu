@@ -1,0 +1,278 @@
+// attention.cu -- ViT self-attention softmax(Q K^T / sqrt(d)) V at fp32-grade accuracy on the fp16 tensor cores (VIT:93-119, the
+// attention of every encoder block; SURVEY 8f.1: the model pass).
+//
+// Same idea as the 3xFP16 GEMM operands (tf32x3.cu): every fp32 operand is split exactly into x = h + l 2^-11 (h = fp16(x),
+// l = fp16((x - h) 2^11)) and each product a b is evaluated as  a_h b_h + 2^-11 (a_l b_h + a_h b_l)  -- three fp16
+// mma.sync.m16n8k16 with fp32 accumulation, the main term and the two corrections in separate accumulators (the tensor core
+// adds with truncation: the 2^-11-sized corrections must not sit in the main chain).  That holds for both contractions:
+// S = Q K^T and O = P V, with the probabilities P split the same way after the fp32 online softmax.
+// Two passes.  (1) q, k, v are split once into fp16 (hi, lo) pairs in a workspace (q pre-scaled for an exp2 softmax).
+// (2) Flash-attention structure: one CTA = 64 query rows of one (image, head), 4 warps x 16 rows; K and V tiles of 64 keys
+// stream through a double-buffered cp.async pipeline in shared memory; nothing of size L x L touches HBM.
+// HBM traffic: q, k, v read once, their splits written once and read once (K/V tiles hit in L2 across the 7 query tiles of a
+// head), O written once.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pnp {
+
+constexpr int kAttD = 64;          // head dimension (ViT-L/16: 1024 / 16)
+constexpr int kAttTile = 64;       // keys per shared-memory tile = query rows per CTA
+constexpr int kAttPitch = 72;      // halves per shared row: 144 B, 16-byte aligned, conflict-free for ldmatrix and quad LDS.32
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void ldmatrix_x2_trans(unsigned &r0, unsigned &r1, const __half *row_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r0), "=r"(r1)
+                 : "r"((unsigned)__cvta_generic_to_shared(row_ptr)));
+}
+
+// (x0, x1) -> packed half2 of the hi parts and of the 2^11-scaled lo parts
+__device__ __forceinline__ void split2(float x0, float x1, unsigned &hi, unsigned &lo) {
+    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+    const __half l0 = __float2half_rn((x0 - __half2float(h0)) * 2048.0f), l1 = __float2half_rn((x1 - __half2float(h1)) * 2048.0f);
+    __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+    hi = *reinterpret_cast<unsigned *>(&hh);
+    lo = *reinterpret_cast<unsigned *>(&ll);
+}
+
+// ---- pass 1: fp32 q, k, v -> fp16 (hi, lo) pairs, [3, 2, B, H, Lp, 64] with Lp = L rounded up to the tile (rows past L zero).
+// q is pre-multiplied by softmax_scale * log2(e) (the softmax runs on exp2), k and v by in_scale (a power of two: exact).
+// Done once per (image, head) instead of once per query tile inside the main kernel (7 query tiles share every K/V tile).
+__global__ void __launch_bounds__(256) attention_split_kernel(const float *__restrict__ qkv, __half *__restrict__ ws, int L, int Lp, int H,
+                                                              int B, float in_scale, float softmax_scale, int *__restrict__ flag) {
+    const size_t plane = (size_t)B * H * Lp * kAttD;                 // one [B,H,Lp,64] fp16 array
+    const size_t total = (size_t)B * H * Lp * (kAttD / 4) * 3;
+    const float qs = in_scale * softmax_scale * 1.4426950408889634f;
+    bool bad = false;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % (kAttD / 4)) * 4;
+        size_t r = i / (kAttD / 4);
+        const int h = (int)(r % H);                                 // (c4, h, which) fastest: consecutive threads read consecutive memory
+        r /= H;
+        const int which = (int)(r % 3);                             // 0 q, 1 k, 2 v
+        r /= 3;
+        const int l = (int)(r % Lp);
+        const int b = (int)(r / Lp);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < L) v = ldg_stream4(qkv + ((((size_t)b * L + l) * 3 + which) * H + h) * kAttD + c4);
+        const float sc = which == 0 ? qs : in_scale;
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        bad = bad || !(fabsf(v.x) <= 65504.f && fabsf(v.y) <= 65504.f && fabsf(v.z) <= 65504.f && fabsf(v.w) <= 65504.f);
+        unsigned h01, l01, h23, l23;
+        split2(v.x, v.y, h01, l01);
+        split2(v.z, v.w, h23, l23);
+        const size_t o = (((size_t)b * H + h) * Lp + l) * kAttD + c4;
+        *reinterpret_cast<uint2 *>(ws + (size_t)(2 * which) * plane + o) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2 *>(ws + (size_t)(2 * which + 1) * plane + o) = make_uint2(l01, l23);
+    }
+    if (bad && flag) *flag = 1;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- pass 2: one CTA = 64 query rows of one (image, head); K/V tiles stream through a double-buffered cp.async pipeline.
+// out [B, L, H*64] fp32.
+__global__ void __launch_bounds__(128, 2) attention_fp16x3_kernel(const __half *__restrict__ ws, float *__restrict__ out, int L, int Lp,
+                                                                  int H, int B) {
+    extern __shared__ __align__(16) __half att_smem[];   // [2 stages][kh, kl, vh, vl][64][72]
+    constexpr int kArr = kAttTile * kAttPitch;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttTile;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const size_t plane = (size_t)B * H * Lp * kAttD;
+    const size_t head = ((size_t)b * H + h) * Lp * kAttD;
+    const __half *qh_g = ws + head, *ql_g = ws + plane + head;
+    const __half *src[4] = {ws + 2 * plane + head, ws + 3 * plane + head, ws + 4 * plane + head, ws + 5 * plane + head};
+
+    auto load_tile = [&](int stage, int k0) {   // 4 arrays x 64 rows x 128 B = 2048 16-byte pieces, 16 per thread
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            __half *dst = att_smem + (stage * 4 + a) * kArr;
+            const __half *s = src[a] + (size_t)k0 * kAttD;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = threadIdx.x + 128 * i;
+                const int row = idx >> 3, c8 = (idx & 7) * 8;
+                cp_async16(dst + row * kAttPitch + c8, s + row * kAttD + c8);
+            }
+        }
+        cp_async_commit();
+    };
+    load_tile(0, 0);
+
+    // ---- this warp's 16 query rows as A fragments (hi and lo)
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;     // < Lp: rows past L are zero in the workspace
+    unsigned qh[4][4], ql[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const int c = 16 * ks + 2 * tig;
+        qh[ks][0] = *reinterpret_cast<const unsigned *>(qh_g + (size_t)r0 * kAttD + c);
+        qh[ks][1] = *reinterpret_cast<const unsigned *>(qh_g + (size_t)r1 * kAttD + c);
+        qh[ks][2] = *reinterpret_cast<const unsigned *>(qh_g + (size_t)r0 * kAttD + c + 8);
+        qh[ks][3] = *reinterpret_cast<const unsigned *>(qh_g + (size_t)r1 * kAttD + c + 8);
+        ql[ks][0] = *reinterpret_cast<const unsigned *>(ql_g + (size_t)r0 * kAttD + c);
+        ql[ks][1] = *reinterpret_cast<const unsigned *>(ql_g + (size_t)r1 * kAttD + c);
+        ql[ks][2] = *reinterpret_cast<const unsigned *>(ql_g + (size_t)r0 * kAttD + c + 8);
+        ql[ks][3] = *reinterpret_cast<const unsigned *>(ql_g + (size_t)r1 * kAttD + c + 8);
+    }
+    float o_main[8][4], o_corr[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o_main[nt][i] = o_corr[nt][i] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    const int n_tiles = Lp / kAttTile;
+    for (int t = 0; t < n_tiles; ++t) {
+        const int k0 = t * kAttTile, stage = t & 1;
+        if (t + 1 < n_tiles) {
+            load_tile(stage ^ 1, k0 + kAttTile);   // the buffer read two iterations ago: its readers passed the barrier below
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const __half *s_kh = att_smem + (stage * 4 + 0) * kArr, *s_kl = att_smem + (stage * 4 + 1) * kArr;
+        const __half *s_vh = att_smem + (stage * 4 + 2) * kArr, *s_vl = att_smem + (stage * 4 + 3) * kArr;
+
+        // ---- S = Q K^T for 16 rows x 64 keys: main and correction accumulators; consecutive mma hit different accumulators
+        float s_main[8][4], s_corr[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s_main[nt][i] = s_corr[nt][i] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const __half *krow_h = s_kh + (8 * nt + g) * kAttPitch + 2 * tig + 16 * ks;
+                const __half *krow_l = s_kl + (8 * nt + g) * kAttPitch + 2 * tig + 16 * ks;
+                const unsigned bh0 = *reinterpret_cast<const unsigned *>(krow_h), bh1 = *reinterpret_cast<const unsigned *>(krow_h + 8);
+                const unsigned bl0 = *reinterpret_cast<const unsigned *>(krow_l), bl1 = *reinterpret_cast<const unsigned *>(krow_l + 8);
+                mma_16816(s_main[nt], qh[ks], bh0, bh1);
+                mma_16816(s_corr[nt], ql[ks], bh0, bh1);
+                mma_16816(s_corr[nt], qh[ks], bl0, bl1);
+            }
+        }
+        // ---- online softmax in the exp2 domain (fp32)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int key = k0 + 8 * nt + 2 * tig;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float s = fmaf(s_corr[nt][i], 1.0f / 2048.0f, s_main[nt][i]);
+                if (key + (i & 1) >= L) s = -INFINITY;
+                s_main[nt][i] = s;
+            }
+            mx0 = fmaxf(mx0, fmaxf(s_main[nt][0], s_main[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(s_main[nt][2], s_main[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);     // finite: every tile holds at least one key < L
+        const float a0 = exp2f(m0 - mn0), a1 = exp2f(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s_main[nt][0] = exp2f(s_main[nt][0] - mn0);
+            s_main[nt][1] = exp2f(s_main[nt][1] - mn0);
+            s_main[nt][2] = exp2f(s_main[nt][2] - mn1);
+            s_main[nt][3] = exp2f(s_main[nt][3] - mn1);
+            sum0 += s_main[nt][0] + s_main[nt][1];
+            sum1 += s_main[nt][2] + s_main[nt][3];
+            o_main[nt][0] *= a0; o_main[nt][1] *= a0; o_main[nt][2] *= a1; o_main[nt][3] *= a1;
+            o_corr[nt][0] *= a0; o_corr[nt][1] *= a0; o_corr[nt][2] *= a1; o_corr[nt][3] *= a1;
+        }
+        l0 = l0 * a0 + sum0;   // per-thread partial sums; reduced over the quad at the end
+        l1 = l1 * a1 + sum1;
+
+        // ---- O += P V : P (this thread's C fragments) becomes the A fragments of the next mma, split into hi / lo
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {   // keys 16 ks .. 16 ks + 15
+            unsigned ph[4], pl[4];
+            split2(s_main[2 * ks][0], s_main[2 * ks][1], ph[0], pl[0]);
+            split2(s_main[2 * ks][2], s_main[2 * ks][3], ph[1], pl[1]);
+            split2(s_main[2 * ks + 1][0], s_main[2 * ks + 1][1], ph[2], pl[2]);
+            split2(s_main[2 * ks + 1][2], s_main[2 * ks + 1][3], ph[3], pl[3]);
+            // B fragments of V[keys 16ks.., dims 8nt..]: ldmatrix.trans over the row-major [key][dim] tile; lanes 0-15 give the rows
+            const int vrow = 16 * ks + (lane & 15);
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                unsigned vh0, vh1, vl0, vl1;
+                ldmatrix_x2_trans(vh0, vh1, s_vh + vrow * kAttPitch + 8 * nt);
+                ldmatrix_x2_trans(vl0, vl1, s_vl + vrow * kAttPitch + 8 * nt);
+                mma_16816(o_main[nt], ph, vh0, vh1);
+                mma_16816(o_corr[nt], pl, vh0, vh1);
+                mma_16816(o_corr[nt], ph, vl0, vl1);
+            }
+        }
+        __syncthreads();   // everyone is done with this stage before the next iteration's prefetch overwrites the other one's successor
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    float *ob = out + (size_t)b * L * H * kAttD + (size_t)h * kAttD;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int c = 8 * nt + 2 * tig;
+        if (r0 < L)
+            *reinterpret_cast<float2 *>(ob + (size_t)r0 * H * kAttD + c) =
+                make_float2(fmaf(o_corr[nt][0], 1.0f / 2048.0f, o_main[nt][0]) * inv0, fmaf(o_corr[nt][1], 1.0f / 2048.0f, o_main[nt][1]) * inv0);
+        if (r1 < L)
+            *reinterpret_cast<float2 *>(ob + (size_t)r1 * H * kAttD + c) =
+                make_float2(fmaf(o_corr[nt][2], 1.0f / 2048.0f, o_main[nt][2]) * inv1, fmaf(o_corr[nt][3], 1.0f / 2048.0f, o_main[nt][3]) * inv1);
+    }
+}
+
+}  // namespace pnp
+
+using namespace pnp;
+
+extern "C" size_t pnp_attention_fp16x3_workspace_bytes(int B, int L, int H, int D) {
+    if (B < 0 || L < 1 || H < 1 || D != kAttD) return 0;
+    const size_t Lp = (size_t)ceil_div(L, kAttTile) * kAttTile;
+    return 6 * (size_t)B * H * Lp * kAttD * sizeof(__half);
+}
+
+extern "C" int pnp_attention_fp16x3(const float *qkv, float in_scale, float softmax_scale, float *out, void *workspace,
+                                    size_t workspace_bytes, int *overflow_flag, int B, int L, int H, int D, pnp_stream_t stream) {
+    if (!qkv || !out || !workspace || B < 0 || L < 1 || H < 1 || D != kAttD || B > 65535 || H > 65535 ||
+        (reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(workspace) & 15) ||
+        !(in_scale > 0.f))
+        return PNP_ERR_INVALID_ARGUMENT;
+    if (workspace_bytes < pnp_attention_fp16x3_workspace_bytes(B, L, H, D)) return PNP_ERR_WORKSPACE;
+    if (B == 0) return PNP_OK;
+    cudaStream_t st = as_stream(stream);
+    const int Lp = ceil_div(L, kAttTile) * kAttTile;
+    const size_t smem = 2 * 4 * (size_t)kAttTile * kAttPitch * sizeof(__half);   // 73 728 B: two CTAs per SM
+    cudaError_t e = cudaFuncSetAttribute(attention_fp16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_err(e);
+    __half *ws = reinterpret_cast<__half *>(workspace);
+    const bool timed = prof::on(kAttention, st);
+    if (timed) prof::begin(kAttention, st);
+    const size_t items = (size_t)B * H * Lp * (kAttD / 4) * 3;
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, (size_t)kNumSMs * 16));
+    attention_split_kernel<<<grid, 256, 0, st>>>(qkv, ws, L, Lp, H, B, in_scale, softmax_scale, overflow_flag);
+    attention_fp16x3_kernel<<<dim3(Lp / kAttTile, H, B), 128, smem, st>>>(ws, out, L, Lp, H, B);
+    if (timed) prof::end(kAttention, st);
+    return launch_status();
+}

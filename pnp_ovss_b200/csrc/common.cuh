@@ -73,7 +73,7 @@ enum KernelId {
     kBlurVertical = 7, kBlurHorizontal = 8, kBlurNormalize = 9, kLatticeBuild = 10, kCrfUnary = 11, kSplatBilateral = 12,
     kBlurAxisBilateral = 13, kMeanfieldUpdate = 14, kArgmax = 15, kConfusion = 16, kSplatSpatial = 17, kBlurAxisSpatial = 18,
     kTf32Split = 19, kGeluSplit = 20, kLayernormSplit = 21, kLowrankBlur = 22, kLowrankUnary = 23, kBackgroundBlur = 24,
-    kNumKernelIds = 25
+    kAttention = 25, kNumKernelIds = 26
 };
 namespace prof {
 extern unsigned g_mask;

@@ -50,7 +50,7 @@ static const char *kKernelNames[pnp::kNumKernelIds] = {
     "blur_vertical", "blur_horizontal", "blur_normalize", "lattice_build", "crf_unary", "crf_splat_bilateral",
     "crf_blur_axis_bilateral", "crf_meanfield_update", "argmax_channels", "confusion", "crf_splat_spatial",
     "crf_blur_axis_spatial", "tf32_split3", "gelu_tf32_split3", "layernorm_tf32_split3", "lowrank_blur", "lowrank_unary",
-    "background_blur"};
+    "background_blur", "attention_fp16x3"};
 
 extern "C" const char *pnp_profile_kernel_name(int kernel_id) {
     return (kernel_id > 0 && kernel_id < pnp::kNumKernelIds) ? kKernelNames[kernel_id] : "";

@@ -99,16 +99,26 @@ def salience_dropout_round(gradcam, agg, chosen, n_prev, imgs, norm_imgs, P, pat
     _req(gradcam, torch.float32, "gradcam")
     B, Tm = gradcam.shape[:2]
     _req(chosen, torch.int32, "chosen", 2)
+    if chosen.shape[0] != B or chosen.shape[1] < int(n_prev) + int(save_len):
+        raise PnpError("chosen must be [B, >= n_prev + save_len]")
+    if gradcam.numel() != B * Tm * P * P:
+        raise PnpError("gradcam must be [B,Tm,P,P]")
     if agg is not None:
         _req(agg, torch.float32, "agg")
+        if agg.shape != gradcam.shape:
+            raise PnpError("agg must have gradcam's shape")
     if imgs is not None:
         _req(imgs, torch.float32, "imgs", 4)
         if tuple(imgs.shape) != (B, 3, P * patch, P * patch):
             raise PnpError("imgs must be [B,3,P*patch,P*patch]")
-    if norm_imgs is not None:
+    if norm_imgs is not None:      # the kernel writes norm_imgs[((b*S+y)*S+x)*3+ch]: anything but [B,S,S,3] would be written out of bounds
         _req(norm_imgs, torch.float32, "norm_imgs", 4)
+        if tuple(norm_imgs.shape) != (B, P * patch, P * patch, 3):
+            raise PnpError("norm_imgs must be [B,P*patch,P*patch,3]")
     if ensemble_r is not None:
         _req(ensemble_r, torch.float32, "ensemble_r")
+        if ensemble_r.shape != gradcam.shape:
+            raise PnpError("ensemble_r must have gradcam's shape")
     check(_lib.load().pnp_salience_dropout_round(_p(gradcam), _p(ensemble_r), _p(agg), _p(chosen), chosen.shape[1], int(n_prev),
                                                  _p(imgs), _p(norm_imgs), B, Tm, int(P), int(patch), int(row_lo), int(row_hi),
                                                  int(save_len), int(round_idx), _stream()), "pnp_salience_dropout_round")
@@ -438,6 +448,22 @@ def layernorm_fp16_split3(x, gamma, beta, eps, residual=None, residual_scale=1.0
                                                 _p(out3), ld3, float(bias_one or 0.0), _p(out1), _p(flag), M, K, _stream()),
           "pnp_layernorm_fp16_split3")
     return out3, out1
+
+
+def attention_fp16x3(qkv, in_scale=1.0, softmax_scale=None, flag=None):
+    """softmax(Q K^T * softmax_scale) V for qkv [B,L,3,H,64] fp32 (each value times 1/in_scale) -> [B,L,H*64] fp32
+    (pnp_attention_fp16x3: fp32-grade on the fp16 tensor cores)."""
+    _req(qkv, torch.float32, "qkv", 5)
+    B, L, three, H, D = qkv.shape
+    if three != 3 or D != 64:
+        raise PnpError("qkv must be [B,L,3,H,64]")
+    out = torch.empty((B, L, H * D), dtype=torch.float32, device=qkv.device)
+    lib = _lib.load()
+    ws_bytes = lib.pnp_attention_fp16x3_workspace_bytes(B, L, H, D)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qkv.device)
+    check(lib.pnp_attention_fp16x3(_p(qkv), float(in_scale), float(softmax_scale if softmax_scale is not None else D ** -0.5), _p(out),
+                                   _p(ws), ws_bytes, _p(flag), B, L, H, D, _stream()), "pnp_attention_fp16x3")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- (f)

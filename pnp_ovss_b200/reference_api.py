@@ -163,7 +163,8 @@ def _fast_hist(label_true, label_pred, n_class):
 
 
 def scores(label_trues, label_preds, cats=None, n_class=None):
-    """DRV:1115-1146.  Returns ({...metrics...}, hist float64 [n,n]); the histogram is accumulated on the GPU."""
+    """DRV:1115-1146.  Returns ({...metrics...}, hist float64 [n,n]); the histogram is accumulated on the GPU.  With `cats`
+    (id -> name, as the drivers pass it) 'Class IoU' is the reference's dict keyed by class name; without it, the bare array."""
     dev = _device()
     hist = torch.zeros((n_class, n_class), dtype=torch.int64, device=dev)
     bad = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -173,7 +174,11 @@ def scores(label_trues, label_preds, cats=None, n_class=None):
         ops.confusion_accumulate(pred, gt, n_class, hist, bad_count=bad)
     if int(bad.item()):
         raise ValueError("predicted label outside [0, n_class)")
-    return metrics_from_hist(hist.cpu().numpy().astype(np.float64))
+    table, h = metrics_from_hist(hist.cpu().numpy().astype(np.float64))
+    if cats is not None:   # DRV:1130-1137: per-class IoU keyed by name, "Background" first, then cats[class_id]
+        names = ["Background"] + [cats[int(i)] for i in range(1, n_class)]
+        table["Class IoU"] = dict(zip(names, table["Class IoU"]))
+    return table, h
 
 
 def metrics_from_hist(hist):

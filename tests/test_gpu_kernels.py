@@ -279,6 +279,28 @@ def test_confusion_golden(dev, golden):
     table, hist = R.scores([gt, gt.T.copy()], [pred, pred.T.copy()], None, n)
     assert np.array_equal(hist, golden["scores_hist"])
     assert table["Mean IoU"] == float(golden["scores_miou"])
+    # with the category table the drivers pass, 'Class IoU' is the reference's dict keyed by name (DRV:1130-1137)
+    cats = {i: "class_%d" % i for i in range(1, n)}
+    named, _ = R.scores([gt, gt.T.copy()], [pred, pred.T.copy()], cats, n)
+    assert list(named["Class IoU"]) == ["Background"] + ["class_%d" % i for i in range(1, n)]
+    assert np.array_equal(np.array(list(named["Class IoU"].values())), table["Class IoU"], equal_nan=True)
+
+
+def test_salience_dropout_round_rejects_misshapen_buffers(dev, ops):
+    """The kernel writes agg / ensemble_r / norm_imgs unconditionally: wrong layouts must be refused, not written out of bounds."""
+    from pnp_ovss_b200 import PnpError
+    B, Tm, P, patch = 2, 6, 4, 16
+    g = torch.rand(B, Tm, P, P, device=dev)
+    chosen = torch.full((B, 20), -1, dtype=torch.int32, device=dev)
+    imgs = torch.zeros(B, 3, P * patch, P * patch, device=dev)
+    ok = dict(agg=torch.empty_like(g), chosen=chosen, n_prev=0, imgs=imgs, norm_imgs=torch.zeros(B, P * patch, P * patch, 3, device=dev),
+              P=P, patch=patch, row_lo=3, row_hi=Tm - 1, save_len=10, round_idx=0)
+    ops.salience_dropout_round(g, **ok)
+    for bad in (dict(norm_imgs=torch.zeros(B, 3, P * patch, P * patch, device=dev)), dict(agg=torch.empty(B, Tm - 1, P, P, device=dev)),
+                dict(ensemble_r=torch.empty(B, Tm, P, P - 1, device=dev)), dict(chosen=torch.full((B - 1, 20), -1, dtype=torch.int32, device=dev)),
+                dict(chosen=torch.full((B, 5), -1, dtype=torch.int32, device=dev))):
+        with pytest.raises(PnpError):
+            ops.salience_dropout_round(g, **dict(ok, **bad))
 
 
 def test_argmax_channels(dev, ops):
@@ -565,3 +587,27 @@ def test_tripled_fp16_gemm_is_fp32_grade(dev, ops):
     assert hi_b == 4.0 and bool(torch.isfinite(w16b.float()).all())
     yb = _mm16(ops.fp16_split3(x, 1.0, hi_b), w16b) / FP16_OUT_SCALE
     assert (yb.double() - x.double() @ wbig.double().t()).abs().max().item() <= 1e-4 * 100
+
+
+# ------------------------------------------------------------------------------------------------ encoder attention (3xFP16)
+@pytest.mark.parametrize("B,L,H", [(2, 442, 16), (1, 785, 4), (3, 64, 2), (1, 37, 1)])
+def test_attention_fp16x3_is_fp32_grade(dev, ops, B, L, H):
+    """softmax(Q K^T / 8) V on the fp16 tensor cores with hi/lo-split operands against an fp64 evaluation: error of the order
+    of torch's own fp32 attention, two orders of magnitude below a plain fp16 attention; ragged L (tail tiles) included."""
+    g = torch.Generator().manual_seed(L + H)
+    qkv = (torch.randn(B, L, 3, H, 64, generator=g) * torch.tensor([2.0, 2.0, 1.0]).view(1, 1, 3, 1, 1)).to(dev)
+    q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    truth = torch.nn.functional.scaled_dot_product_attention(q.double(), k.double(), v.double()).permute(0, 2, 1, 3).reshape(B, L, H * 64)
+    got = ops.attention_fp16x3(qkv)
+    ref32 = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B, L, H * 64)
+    ref16 = torch.nn.functional.scaled_dot_product_attention(q.half(), k.half(), v.half()).float().permute(0, 2, 1, 3).reshape(B, L, H * 64)
+    sc = truth.abs().max().item()
+    e_got, e32, e16 = ((t.double() - truth).abs().max().item() / sc for t in (got, ref32, ref16))
+    print("attention L=%d: max err / max |o|: 3xfp16 kernel %.2e, torch fp32 %.2e, plain fp16 %.2e" % (L, e_got, e32, e16))
+    assert e_got <= 20 * e32 + 1e-6 and e_got * 30 <= e16
+    # the form the encoder uses: operands carrying the 3xFP16 GEMM's factor 2^11
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    got_scaled = ops.attention_fp16x3((qkv * 2048.0).contiguous(), in_scale=1.0 / 2048.0, flag=flag)
+    assert torch.equal(got_scaled, got) and int(flag.item()) == 0
+    ops.attention_fp16x3((qkv * 1e6).contiguous(), flag=flag)            # out of fp16's range: the flag says so
+    assert int(flag.item()) == 1
