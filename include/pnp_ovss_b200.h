@@ -270,8 +270,11 @@ int pnp_layernorm_fp16_split3(const float *x, const float *residual, float resid
  * softmax in fp32; nothing of size L x L touches HBM.  qkv [B,L,3,H,D] fp32 exactly as the fused qkv GEMM leaves it (each value
  * times 1/in_scale, in_scale a power of two; 1 for a plain projection); out [B,L,H*D] fp32, unscaled.  D must be 64. */
 size_t pnp_attention_fp16x3_workspace_bytes(int B, int L, int H, int D);
-int pnp_attention_fp16x3(const float *qkv, float in_scale, float softmax_scale, float *out, void *workspace,
-                         size_t workspace_bytes, int *overflow_flag, int B, int L, int H, int D, pnp_stream_t stream);
+/* out and / or out3 (at least one): out3 [B*L, 3*H*D] fp16 is the [h * out3_hi_scale | l | h] operand split of the output
+ * (pnp_fp16_split3's layout), written straight from the accumulators for the projection GEMM that follows. */
+int pnp_attention_fp16x3(const float *qkv, float in_scale, float softmax_scale, float *out, uint16_t *out3,
+                         float out3_hi_scale, void *workspace, size_t workspace_bytes, int *overflow_flag, int B, int L,
+                         int H, int D, pnp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * In-situ kernel timing for bench.py's roofline (the one piece of process-global state in the library):

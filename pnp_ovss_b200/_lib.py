@@ -68,7 +68,8 @@ SIGNATURES = {
     "pnp_layernorm_fp16_split3": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,
                                           c_int, c_float, c_void_p, c_void_p, ctypes.c_longlong, c_int, c_void_p]),
     "pnp_attention_fp16x3_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "pnp_attention_fp16x3": (c_int, [c_void_p, c_float, c_float, c_void_p, c_void_p, c_size_t, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "pnp_attention_fp16x3": (c_int, [c_void_p, c_float, c_float, c_void_p, c_void_p, c_float, c_void_p, c_size_t, c_void_p, c_int, c_int,
+                                     c_int, c_int, c_void_p]),
     "pnp_profile_num_kernels": (c_int, []),
     "pnp_profile_start": (c_int, [ctypes.c_uint]),
     "pnp_profile_stop": (c_int, [ctypes.POINTER(c_float), ctypes.POINTER(c_int), c_int]),

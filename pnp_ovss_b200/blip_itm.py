@@ -470,8 +470,8 @@ class BlipITM(nn.Module):
             hd = D // blk.heads
             if half and self.USE_FUSED_ATTENTION and hd == 64:
                 # the attention itself on the fp16 tensor cores with the same hi/lo split (pnp_attention_fp16x3): unscaled output
-                a = ops.attention_fp16x3(qkv.view(B, L, 3, blk.heads, hd), inv, 1.0 / math.sqrt(hd), flag)
-                r = mm(split(a, 1.0, w_proj), w_proj[0])
+                a3 = ops.attention_fp16x3(qkv.view(B, L, 3, blk.heads, hd), inv, 1.0 / math.sqrt(hd), flag, split_hi_scale=w_proj[1])
+                r = mm(a3, w_proj[0])
             else:
                 qkv = qkv.view(B, L, 3, blk.heads, hd).permute(2, 0, 3, 1, 4)
                 a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], scale=inv * inv / math.sqrt(hd))

@@ -47,24 +47,22 @@ __device__ __forceinline__ void split2(float x0, float x1, unsigned &hi, unsigne
 // q is pre-multiplied by softmax_scale * log2(e) (the softmax runs on exp2), k and v by in_scale (a power of two: exact).
 // Done once per (image, head) instead of once per query tile inside the main kernel (7 query tiles share every K/V tile).
 __global__ void __launch_bounds__(256) attention_split_kernel(const float *__restrict__ qkv, __half *__restrict__ ws, int L, int Lp, int H,
-                                                              int B, float in_scale, float softmax_scale, int *__restrict__ flag) {
+                                                              int B, float in_scale, int *__restrict__ flag) {
     const size_t plane = (size_t)B * H * Lp * kAttD;                 // one [B,H,Lp,64] fp16 array
-    const size_t total = (size_t)B * H * Lp * (kAttD / 4) * 3;
-    const float qs = in_scale * softmax_scale * 1.4426950408889634f;
+    const size_t total = (size_t)B * H * Lp * (kAttD / 4) * 2;
     bool bad = false;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % (kAttD / 4)) * 4;
         size_t r = i / (kAttD / 4);
         const int h = (int)(r % H);                                 // (c4, h, which) fastest: consecutive threads read consecutive memory
         r /= H;
-        const int which = (int)(r % 3);                             // 0 q, 1 k, 2 v
-        r /= 3;
+        const int which = 1 + (int)(r % 2);                         // 1 k, 2 v (q is split by the main kernel)
+        r /= 2;
         const int l = (int)(r % Lp);
         const int b = (int)(r / Lp);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (l < L) v = ldg_stream4(qkv + ((((size_t)b * L + l) * 3 + which) * H + h) * kAttD + c4);
-        const float sc = which == 0 ? qs : in_scale;
-        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
         bad = bad || !(fabsf(v.x) <= 65504.f && fabsf(v.y) <= 65504.f && fabsf(v.z) <= 65504.f && fabsf(v.w) <= 65504.f);
         unsigned h01, l01, h23, l23;
         split2(v.x, v.y, h01, l01);
@@ -85,8 +83,11 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // ---- pass 2: one CTA = 64 query rows of one (image, head); K/V tiles stream through a double-buffered cp.async pipeline.
 // out [B, L, H*64] fp32.
-__global__ void __launch_bounds__(128, 2) attention_fp16x3_kernel(const __half *__restrict__ ws, float *__restrict__ out, int L, int Lp,
-                                                                  int H, int B) {
+// out [B, L, H*64] fp32 and / or out3 = its fp16 [h*hi_scale | l | h] operand split ([B*L, 3*H*64], see tf32x3.cu) for the
+// projection GEMM that follows.
+__global__ void __launch_bounds__(128, 2) attention_fp16x3_kernel(const float *__restrict__ qkv, const __half *__restrict__ ws,
+                                                                  float *__restrict__ out, __half *__restrict__ out3, int L, int Lp,
+                                                                  int H, int B, float q_scale, float hi_scale, int *__restrict__ flag) {
     extern __shared__ __align__(16) __half att_smem[];   // [2 stages][kh, kl, vh, vl][64][72]
     constexpr int kArr = kAttTile * kAttPitch;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttTile;
@@ -94,7 +95,6 @@ __global__ void __launch_bounds__(128, 2) attention_fp16x3_kernel(const __half *
     const int g = lane >> 2, tig = lane & 3;
     const size_t plane = (size_t)B * H * Lp * kAttD;
     const size_t head = ((size_t)b * H + h) * Lp * kAttD;
-    const __half *qh_g = ws + head, *ql_g = ws + plane + head;
     const __half *src[4] = {ws + 2 * plane + head, ws + 3 * plane + head, ws + 4 * plane + head, ws + 5 * plane + head};
 
     auto load_tile = [&](int stage, int k0) {   // 4 arrays x 64 rows x 128 B = 2048 16-byte pieces, 16 per thread
@@ -113,20 +113,27 @@ __global__ void __launch_bounds__(128, 2) attention_fp16x3_kernel(const __half *
     };
     load_tile(0, 0);
 
-    // ---- this warp's 16 query rows as A fragments (hi and lo)
-    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;     // < Lp: rows past L are zero in the workspace
+    // ---- this warp's 16 query rows as A fragments (hi and lo), pre-multiplied by in_scale * softmax_scale * log2(e)
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    const size_t row_stride = (size_t)3 * H * kAttD;
+    const float *qb = qkv + (size_t)b * L * row_stride + (size_t)h * kAttD;
     unsigned qh[4][4], ql[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
         const int c = 16 * ks + 2 * tig;
-        qh[ks][0] = *reinterpret_cast<const unsigned *>(qh_g + (size_t)r0 * kAttD + c);
-        qh[ks][1] = *reinterpret_cast<const unsigned *>(qh_g + (size_t)r1 * kAttD + c);
-        qh[ks][2] = *reinterpret_cast<const unsigned *>(qh_g + (size_t)r0 * kAttD + c + 8);
-        qh[ks][3] = *reinterpret_cast<const unsigned *>(qh_g + (size_t)r1 * kAttD + c + 8);
-        ql[ks][0] = *reinterpret_cast<const unsigned *>(ql_g + (size_t)r0 * kAttD + c);
-        ql[ks][1] = *reinterpret_cast<const unsigned *>(ql_g + (size_t)r1 * kAttD + c);
-        ql[ks][2] = *reinterpret_cast<const unsigned *>(ql_g + (size_t)r0 * kAttD + c + 8);
-        ql[ks][3] = *reinterpret_cast<const unsigned *>(ql_g + (size_t)r1 * kAttD + c + 8);
+        float2 v00 = make_float2(0.f, 0.f), v10 = v00, v01 = v00, v11 = v00;
+        if (r0 < L) {
+            v00 = *reinterpret_cast<const float2 *>(qb + (size_t)r0 * row_stride + c);
+            v01 = *reinterpret_cast<const float2 *>(qb + (size_t)r0 * row_stride + c + 8);
+        }
+        if (r1 < L) {
+            v10 = *reinterpret_cast<const float2 *>(qb + (size_t)r1 * row_stride + c);
+            v11 = *reinterpret_cast<const float2 *>(qb + (size_t)r1 * row_stride + c + 8);
+        }
+        split2(v00.x * q_scale, v00.y * q_scale, qh[ks][0], ql[ks][0]);
+        split2(v10.x * q_scale, v10.y * q_scale, qh[ks][1], ql[ks][1]);
+        split2(v01.x * q_scale, v01.y * q_scale, qh[ks][2], ql[ks][2]);
+        split2(v11.x * q_scale, v11.y * q_scale, qh[ks][3], ql[ks][3]);
     }
     float o_main[8][4], o_corr[8][4];
 #pragma unroll
@@ -230,17 +237,33 @@ __global__ void __launch_bounds__(128, 2) attention_fp16x3_kernel(const __half *
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-    float *ob = out + (size_t)b * L * H * kAttD + (size_t)h * kAttD;
+    const int Dm = H * kAttD;
+    bool bad = false;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-        const int c = 8 * nt + 2 * tig;
-        if (r0 < L)
-            *reinterpret_cast<float2 *>(ob + (size_t)r0 * H * kAttD + c) =
-                make_float2(fmaf(o_corr[nt][0], 1.0f / 2048.0f, o_main[nt][0]) * inv0, fmaf(o_corr[nt][1], 1.0f / 2048.0f, o_main[nt][1]) * inv0);
-        if (r1 < L)
-            *reinterpret_cast<float2 *>(ob + (size_t)r1 * H * kAttD + c) =
-                make_float2(fmaf(o_corr[nt][2], 1.0f / 2048.0f, o_main[nt][2]) * inv1, fmaf(o_corr[nt][3], 1.0f / 2048.0f, o_main[nt][3]) * inv1);
+        const int c = h * kAttD + 8 * nt + 2 * tig;
+#pragma unroll
+        for (int half_row = 0; half_row < 2; ++half_row) {
+            const int r = half_row ? r1 : r0;
+            if (r >= L) continue;
+            const float inv = half_row ? inv1 : inv0;
+            const float x0 = fmaf(o_corr[nt][2 * half_row], 1.0f / 2048.0f, o_main[nt][2 * half_row]) * inv;
+            const float x1 = fmaf(o_corr[nt][2 * half_row + 1], 1.0f / 2048.0f, o_main[nt][2 * half_row + 1]) * inv;
+            const size_t m = (size_t)b * L + r;
+            if (out) *reinterpret_cast<float2 *>(out + m * Dm + c) = make_float2(x0, x1);
+            if (out3) {   // [h * hi_scale | l | h] of the attention output, ready for the projection GEMM
+                unsigned hh, ll;
+                split2(x0, x1, hh, ll);
+                __half2 hs = __hmul2(*reinterpret_cast<__half2 *>(&hh), __float2half2_rn(hi_scale));   // a power of two: exact
+                bad = bad || !(fabsf(x0 * hi_scale) <= 65504.f && fabsf(x1 * hi_scale) <= 65504.f);
+                __half *row = out3 + m * 3 * Dm;
+                *reinterpret_cast<unsigned *>(row + c) = *reinterpret_cast<unsigned *>(&hs);
+                *reinterpret_cast<unsigned *>(row + Dm + c) = ll;
+                *reinterpret_cast<unsigned *>(row + 2 * Dm + c) = hh;
+            }
+        }
     }
+    if (bad && flag) *flag = 1;
 }
 
 }  // namespace pnp
@@ -250,13 +273,14 @@ using namespace pnp;
 extern "C" size_t pnp_attention_fp16x3_workspace_bytes(int B, int L, int H, int D) {
     if (B < 0 || L < 1 || H < 1 || D != kAttD) return 0;
     const size_t Lp = (size_t)ceil_div(L, kAttTile) * kAttTile;
-    return 6 * (size_t)B * H * Lp * kAttD * sizeof(__half);
+    return 6 * (size_t)B * H * Lp * kAttD * sizeof(__half);   // (planes 2..5 = k_hi, k_lo, v_hi, v_lo are used)
 }
 
-extern "C" int pnp_attention_fp16x3(const float *qkv, float in_scale, float softmax_scale, float *out, void *workspace,
-                                    size_t workspace_bytes, int *overflow_flag, int B, int L, int H, int D, pnp_stream_t stream) {
-    if (!qkv || !out || !workspace || B < 0 || L < 1 || H < 1 || D != kAttD || B > 65535 || H > 65535 ||
-        (reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) || (reinterpret_cast<uintptr_t>(workspace) & 15) ||
+extern "C" int pnp_attention_fp16x3(const float *qkv, float in_scale, float softmax_scale, float *out, uint16_t *out3, float out3_hi_scale,
+                                    void *workspace, size_t workspace_bytes, int *overflow_flag, int B, int L, int H, int D,
+                                    pnp_stream_t stream) {
+    if (!qkv || (!out && !out3) || (out3 && (reinterpret_cast<uintptr_t>(out3) & 3)) || !workspace || B < 0 || L < 1 || H < 1 || D != kAttD || B > 65535 || H > 65535 ||
+        (reinterpret_cast<uintptr_t>(qkv) & 15) || (out && (reinterpret_cast<uintptr_t>(out) & 7)) || (reinterpret_cast<uintptr_t>(workspace) & 15) ||
         !(in_scale > 0.f))
         return PNP_ERR_INVALID_ARGUMENT;
     if (workspace_bytes < pnp_attention_fp16x3_workspace_bytes(B, L, H, D)) return PNP_ERR_WORKSPACE;
@@ -269,10 +293,12 @@ extern "C" int pnp_attention_fp16x3(const float *qkv, float in_scale, float soft
     __half *ws = reinterpret_cast<__half *>(workspace);
     const bool timed = prof::on(kAttention, st);
     if (timed) prof::begin(kAttention, st);
-    const size_t items = (size_t)B * H * Lp * (kAttD / 4) * 3;
+    const size_t items = (size_t)B * H * Lp * (kAttD / 4) * 2;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, (size_t)kNumSMs * 16));
-    attention_split_kernel<<<grid, 256, 0, st>>>(qkv, ws, L, Lp, H, B, in_scale, softmax_scale, overflow_flag);
-    attention_fp16x3_kernel<<<dim3(Lp / kAttTile, H, B), 128, smem, st>>>(ws, out, L, Lp, H, B);
+    attention_split_kernel<<<grid, 256, 0, st>>>(qkv, ws, L, Lp, H, B, in_scale, overflow_flag);
+    attention_fp16x3_kernel<<<dim3(Lp / kAttTile, H, B), 128, smem, st>>>(qkv, ws, out, reinterpret_cast<__half *>(out3), L, Lp, H, B,
+                                                                          in_scale * softmax_scale * 1.4426950408889634f, out3_hi_scale,
+                                                                          overflow_flag);
     if (timed) prof::end(kAttention, st);
     return launch_status();
 }

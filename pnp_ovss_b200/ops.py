@@ -450,20 +450,26 @@ def layernorm_fp16_split3(x, gamma, beta, eps, residual=None, residual_scale=1.0
     return out3, out1
 
 
-def attention_fp16x3(qkv, in_scale=1.0, softmax_scale=None, flag=None):
+def attention_fp16x3(qkv, in_scale=1.0, softmax_scale=None, flag=None, split_hi_scale=None):
     """softmax(Q K^T * softmax_scale) V for qkv [B,L,3,H,64] fp32 (each value times 1/in_scale) -> [B,L,H*64] fp32
-    (pnp_attention_fp16x3: fp32-grade on the fp16 tensor cores)."""
+    (pnp_attention_fp16x3: fp32-grade on the fp16 tensor cores).  split_hi_scale: return instead the fp16 [h*s | l | h] operand
+    split of the output ([B,L,3*H*64]), written straight from the accumulators."""
     _req(qkv, torch.float32, "qkv", 5)
     B, L, three, H, D = qkv.shape
     if three != 3 or D != 64:
         raise PnpError("qkv must be [B,L,3,H,64]")
-    out = torch.empty((B, L, H * D), dtype=torch.float32, device=qkv.device)
+    out = out3 = None
+    if split_hi_scale is None:
+        out = torch.empty((B, L, H * D), dtype=torch.float32, device=qkv.device)
+    else:
+        out3 = torch.empty((B, L, 3 * H * D), dtype=torch.float16, device=qkv.device)
     lib = _lib.load()
     ws_bytes = lib.pnp_attention_fp16x3_workspace_bytes(B, L, H, D)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qkv.device)
     check(lib.pnp_attention_fp16x3(_p(qkv), float(in_scale), float(softmax_scale if softmax_scale is not None else D ** -0.5), _p(out),
-                                   _p(ws), ws_bytes, _p(flag), B, L, H, D, _stream()), "pnp_attention_fp16x3")
-    return out
+                                   _p(out3), float(split_hi_scale or 1.0), _p(ws), ws_bytes, _p(flag), B, L, H, D, _stream()),
+          "pnp_attention_fp16x3")
+    return out if out3 is None else out3
 
 
 # ----------------------------------------------------------------------------------------------- (f)

@@ -65,6 +65,7 @@ def test_algorithmic_bytes_cover_the_timed_kernel_classes():
     for n in names:
         b = bench.algorithmic_bytes(n, w, stats, 31)
         assert (b is None) == (n in bench.LATENCY_BOUND), n
+        assert bench.algorithmic_bytes(n, w, stats, 31, "3xtf32") is None or bench.algorithmic_bytes(n, w, stats, 31, "3xtf32") >= b
         if b is not None:
             assert b > 0
     # the dominant kernels' figures of DESIGN.md section 3

@@ -609,5 +609,9 @@ def test_attention_fp16x3_is_fp32_grade(dev, ops, B, L, H):
     flag = torch.zeros(1, dtype=torch.int32, device=dev)
     got_scaled = ops.attention_fp16x3((qkv * 2048.0).contiguous(), in_scale=1.0 / 2048.0, flag=flag)
     assert torch.equal(got_scaled, got) and int(flag.item()) == 0
+    # ... and the fused operand split of the output is the split kernel's, bit for bit
+    flag.zero_()
+    got3 = ops.attention_fp16x3(qkv, flag=flag, split_hi_scale=2.0)
+    assert torch.equal(got3, ops.fp16_split3(got, 1.0, 2.0, flag)) and int(flag.item()) == 0
     ops.attention_fp16x3((qkv * 1e6).contiguous(), flag=flag)            # out of fp16's range: the flag says so
     assert int(flag.item()) == 1
