@@ -567,7 +567,7 @@ def run_ours(args):
         e2e_ms, _ = timed(True, args.steps)
         per_batch_h2d = int(w["imgs"].numel() * 4 + w["guides"].size + w["gts"].size * 4)
         e2e = {"value": imgs_per_step * args.steps / (e2e_ms / 1e3), "unit": "images/s",
-               "h2d_bytes_per_step": per_batch_h2d * max(len(slots), 1), "d2h_bytes_per_step": int(hist_host[0].numel() * 8),
+               "h2d_bytes_per_step": per_batch_h2d * max(len(slots), 1) * world, "d2h_bytes_per_step": int(hist_host[0].numel() * 8) * world,
                "ms_per_step": e2e_ms / args.steps}
 
     # ---- the same steps on torch's native fp32 SIMT GEMMs, and both modes against an fp64 autograd pass
@@ -826,6 +826,20 @@ def run_reference_gpu_leg(w, dev, cores):
                                          threshold=w["threshold"], data_type=w["data_type"], mode=w["mode"], n_class=w["n_class"],
                                          coco=w["coco"], pool=pool, timings=timings, device=dev)
             sec = time.perf_counter() - t0
+        # ... and the way the reference really runs it: ONE process per GPU, post-processing image after image on one core
+        # (bounded sample: 4 images)
+        n1 = min(4, n)
+        tk1 = tok(w["captions"][:n1], padding="max_length", max_length=500)
+        t1 = {}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        torch.set_num_threads(1)
+        RA.reference_batch_confusion(model, w["imgs"][:n1].clone(), w["captions"][:n1], tk1, tok.decode, w["class_lists"][:n1], w["dataset_ids"][:n1],
+                                     list(w["gts"][:n1]), list(w["guides"][:n1]), drop_iter=w["drop_iter"], layer=w["layer"], head=w["head"],
+                                     threshold=w["threshold"], data_type=w["data_type"], mode=w["mode"], n_class=w["n_class"],
+                                     coco=w["coco"], pool=None, timings=t1, device=dev)
+        sec1 = time.perf_counter() - t0
+        torch.set_num_threads(cores)
     finally:
         if pool is not None:
             pool.close()
@@ -834,6 +848,9 @@ def run_reference_gpu_leg(w, dev, cores):
         torch.cuda.empty_cache()
     return {"value": n / sec, "unit": "images/s", "sec_per_step": sec, "images_per_step": n, "model_sec_per_step": timings.get("model_s"),
             "post_sec_per_step": timings.get("post_s"), "post_workers": workers, "cores": cores,
+            "single_process": {"value": n1 / sec1, "unit": "images/s", "images": n1, "sec": sec1, "model_sec": t1.get("model_s"),
+                               "post_sec": t1.get("post_s"),
+                               "what": "the same, as the reference runs it: one process per GPU, post-processing on one core"},
             "what": "reference-style torch-GPU model pass (12-block capture, full backward, 144 D2H per pass, native fp32) + the "
                     "reference's CPU post-processing fanned over %d worker processes (the reference uses 1)" % workers}
 

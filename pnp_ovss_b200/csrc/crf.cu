@@ -94,6 +94,28 @@ __global__ void __launch_bounds__(256) splat_kernel(LatticeView L, const float *
     }
 }
 
+// Experiment (PNP_SPLAT_ATOMIC=1, bilateral lattice only): the transposed formulation -- one thread per (pixel, chunk) reads its
+// Q row once (coalesced) and adds w * norm * Q into its d+1 vertex rows with vector float atomics (red.global.add.v4.f32).
+// No CSR, perfectly balanced warps, but the summation order -- hence the low bits of every marginal -- changes from run to
+// run, so it is NOT the default: results of the measurement in profiles/README.md.
+__global__ void __launch_bounds__(256) splat_atomic_kernel(LatticeView L, const float *__restrict__ x, float *__restrict__ values, int Cp,
+                                                           long long n_lp) {
+    const int nch = Cp >> 2;
+    const long long total = n_lp * nch;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long lp = idx / nch;
+        const int ch = (int)(idx - lp * nch);
+        float4 q = ldg_stream4(x + lp * Cp + 4 * ch);
+        const float nr = __ldg(L.norm + lp);
+        q = f4_mul(q, nr);
+        for (int j = 0; j < L.Dp1; ++j) {
+            const int o = __ldg(L.offset + lp * L.Dp1 + j) + 1;
+            const float w = __ldg(L.bary + lp * L.Dp1 + j);
+            atomicAdd(reinterpret_cast<float4 *>(values + (size_t)o * L.vp + 4 * ch), f4_mul(q, w));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ blur along one axis
 __global__ void __launch_bounds__(256) blur_axis_kernel(LatticeView L, const float *__restrict__ old_v, float *__restrict__ new_v, int axis,
                                                         int Cp) {
@@ -697,7 +719,17 @@ static const float *run_splat_blur(const LatticeView &L, const float *x, float *
     const int gx = std::max(1, grid_for((long long)(L.M + 1) * nch, 256, mult_blur()) / div);
     const int id_splat = L.shared ? kSplatSpatial : kSplatBilateral;
     const int id_blur = L.shared ? kBlurAxisSpatial : kBlurAxisBilateral;
-    PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx_splat, gy), 256, 0, st>>>(L, x, va, Cp, normalized));
+    static const int atomic_splat = env_mult("PNP_SPLAT_ATOMIC", 2) == 1;
+    if (atomic_splat && !L.shared && normalized) {   // experiment: pixel-order vector-atomic splat (non-deterministic sums)
+        const bool timed = prof::on(id_splat, st);
+        if (timed) prof::begin(id_splat, st);
+        cudaMemsetAsync(va, 0, (size_t)(L.M + 1) * L.vp * sizeof(float), st);
+        const long long n_lp = (long long)B * L.N;
+        splat_atomic_kernel<<<grid_for(n_lp * nch, 256, 16), 256, 0, st>>>(L, x, va, Cp, n_lp);
+        if (timed) prof::end(id_splat, st);
+    } else {
+        PNP_LAUNCH(id_splat, st, splat_kernel<<<dim3(gx_splat, gy), 256, 0, st>>>(L, x, va, Cp, normalized));
+    }
     float *src = va, *dst = vb;
     // Two axes per launch halve the HBM traffic of the blur but re-gather the first axis at both neighbours; measured on
     // B200 that pays up to ~340-byte rows (21 ch: 0.187 vs 0.232 ms, 81 ch @448: 23.6 vs 27.5 ms per pass) and loses with

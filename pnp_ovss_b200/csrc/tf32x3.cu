@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) gelu_split3_kernel(const float *__restric
 // Optional residual: x = x + res * res_scale (+ res_bias) is formed first and written back to x_out (the running hidden state),
 // so the residual add, the LayerNorm and the operand split are one pass.
 template <int kChunks, bool kHalf>
-__global__ void __launch_bounds__(256) layernorm_split3_kernel(const float *__restrict__ x, const float *__restrict__ res, float res_scale,
+__global__ void __launch_bounds__(256, kChunks <= 8 ? 3 : 1) layernorm_split3_kernel(const float *__restrict__ x, const float *__restrict__ res, float res_scale,
                                                                const float *__restrict__ res_bias, float *__restrict__ x_out,
                                                                const float *__restrict__ gamma, const float *__restrict__ beta,
                                                                float eps, typename Split3<kHalf>::out_t *__restrict__ out3,

@@ -84,10 +84,34 @@ def run_xattn(dev):
     return err
 
 
+def run_model(dev):
+    """A small BLIP-shaped model (head dimension 64) through the trimmed GradCAM pass in the shipped GEMM mode (3xFP16: fused
+    operand kernels, the fp16x3 attention kernel, tensor-core text side, CUDA graphs) against torch's plain fp32 pass."""
+    from pnp_ovss_b200.blip_itm import BlipITM
+    tok = synth.SyntheticWordPieceTokenizer()
+    caps = ["A picture of cat aeroplane", "A picture of dog"]
+    tokens = tok(caps, padding="max_length", max_length=500).to(dev)
+    torch.manual_seed(3)
+    m = BlipITM(img_size=96, tokenizer=tok, hidden=128, layers=3, heads=2, inter=256, vit_dim=128, vit_depth=3, vit_heads=2, max_pos=64).eval()
+    with torch.no_grad():
+        for p_ in m.parameters():
+            p_.mul_(2.0)
+    m = m.to(dev).requires_grad_(False)
+    imgs = torch.randn(2, 3, 96, 96, generator=torch.Generator().manual_seed(1)).to(dev)
+    ref, _ = m.gradcam(imgs, caps, tokens, layer=1, head=1)
+    m.gemm_precision = "3xfp16"
+    got, _ = m.gradcam(imgs, caps, tokens, layer=1, head=1)
+    again, _ = m.gradcam(imgs, caps, tokens, layer=1, head=1)         # second call: replayed from the captured graphs
+    m.check_fp16_overflow()
+    rel = float((got - ref).abs().max() / ref.abs().max())
+    assert rel <= 1e-3 and torch.equal(got, again), "3xFP16 GradCAM differs from the fp32 pass by %g of its max" % rel
+    return rel
+
+
 def run(dev):
-    """smoke(): the fused softmax/GradCAM kernels on the reference's capture, then one DropOut + blur + CRF batch on the GPU
-    against the oracle."""
-    report = {"xattn_softmax_max_abs_err": run_xattn(dev)}
+    """smoke(): the fused softmax/GradCAM kernels on the reference's capture, a small model pass in the shipped GEMM mode, then
+    one DropOut + blur + CRF batch on the GPU against the oracle."""
+    report = {"xattn_softmax_max_abs_err": run_xattn(dev), "model_3xfp16_vs_fp32_rel": run_model(dev)}
     for mode in ("blur", "blur+crf"):
         g0, gagg = run_gpu("voc_r4", mode, dev)
         o0, oagg = run_oracle("voc_r4", mode)
