@@ -15,7 +15,7 @@
  *   - one host thread per process, one process per GPU (DRV:1439 mp.spawn).  Process-global state is limited to: the
  *     in-situ profiler (pnp_profile_*, off by default), the per-kernel "allow > 48 KB of dynamic shared memory" function
  *     attribute (idempotent), and tuning environment variables read once (PNP_GRID_MULT_*, PNP_BLUR_FUSE*, PNP_UPDATE_*,
- *     PNP_VALUE_PITCH: experiment switches, unset in production).  No data is cached between calls.
+ *     PNP_VALUE_PITCH, PNP_SPLAT_ATOMIC, PNP_ATT_VARIANT: experiment switches, unset in production).  No data is cached between calls.
  *   - exception to "returns immediately": pnp_lattice_finish synchronises the stream (it reads the vertex count back).
  */
 #ifndef PNP_OVSS_B200_H

@@ -13,6 +13,7 @@
 // head), O written once.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -28,19 +29,31 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const unsigned (&a)[4],
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void ldmatrix_x4(unsigned &r0, unsigned &r1, unsigned &r2, unsigned &r3, const __half *row_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"((unsigned)__cvta_generic_to_shared(row_ptr)));
+}
+
+__device__ __forceinline__ void ldmatrix_x4_trans(unsigned &r0, unsigned &r1, unsigned &r2, unsigned &r3, const __half *row_ptr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"((unsigned)__cvta_generic_to_shared(row_ptr)));
+}
+
 __device__ __forceinline__ void ldmatrix_x2_trans(unsigned &r0, unsigned &r1, const __half *row_ptr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
                  : "=r"(r0), "=r"(r1)
                  : "r"((unsigned)__cvta_generic_to_shared(row_ptr)));
 }
 
-// (x0, x1) -> packed half2 of the hi parts and of the 2^11-scaled lo parts
+// (x0, x1) -> packed half2 of the hi parts and of the 2^11-scaled lo parts (packed cvt.rn.f16x2.f32 conversions)
 __device__ __forceinline__ void split2(float x0, float x1, unsigned &hi, unsigned &lo) {
-    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-    const __half l0 = __float2half_rn((x0 - __half2float(h0)) * 2048.0f), l1 = __float2half_rn((x1 - __half2float(h1)) * 2048.0f);
-    __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-    hi = *reinterpret_cast<unsigned *>(&hh);
-    lo = *reinterpret_cast<unsigned *>(&ll);
+    const __half2 hh = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+    hi = *reinterpret_cast<const unsigned *>(&hh);
+    lo = *reinterpret_cast<const unsigned *>(&ll);
 }
 
 // ---- pass 1: fp32 q, k, v -> fp16 (hi, lo) pairs, [3, 2, B, H, Lp, 64] with Lp = L rounded up to the tile (rows past L zero).
@@ -85,6 +98,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // out [B, L, H*64] fp32.
 // out [B, L, H*64] fp32 and / or out3 = its fp16 [h*hi_scale | l | h] operand split ([B*L, 3*H*64], see tf32x3.cu) for the
 // projection GEMM that follows.
+template <bool KX4, bool VX4>
 __global__ void __launch_bounds__(128, 2) attention_fp16x3_kernel(const float *__restrict__ qkv, const __half *__restrict__ ws,
                                                                   float *__restrict__ out, __half *__restrict__ out3, int L, int Lp,
                                                                   int H, int B, float q_scale, float hi_scale, int *__restrict__ flag) {
@@ -161,29 +175,52 @@ __global__ void __launch_bounds__(128, 2) attention_fp16x3_kernel(const float *_
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
             for (int i = 0; i < 4; ++i) s_main[nt][i] = s_corr[nt][i] = 0.f;
+        if (KX4) {
+            // B fragments of K^T through ldmatrix.x4 over the row-major [key][dim] tile: matrices (keys 8nt.., dims 16ks..+7),
+            // (same keys, dims +8) = b0, b1 of k-step ks, then the same pair for k-step ks+1; lane l supplies row (l & 7) of matrix l >> 3
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
+            for (int kp = 0; kp < 2; ++kp) {           // k-steps 2kp, 2kp+1
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                const __half *krow_h = s_kh + (8 * nt + g) * kAttPitch + 2 * tig + 16 * ks;
-                const __half *krow_l = s_kl + (8 * nt + g) * kAttPitch + 2 * tig + 16 * ks;
-                const unsigned bh0 = *reinterpret_cast<const unsigned *>(krow_h), bh1 = *reinterpret_cast<const unsigned *>(krow_h + 8);
-                const unsigned bl0 = *reinterpret_cast<const unsigned *>(krow_l), bl1 = *reinterpret_cast<const unsigned *>(krow_l + 8);
-                mma_16816(s_main[nt], qh[ks], bh0, bh1);
-                mma_16816(s_corr[nt], ql[ks], bh0, bh1);
-                mma_16816(s_corr[nt], qh[ks], bl0, bl1);
+                for (int nt = 0; nt < 8; ++nt) {
+                    const int off = (8 * nt + (lane & 7)) * kAttPitch + 32 * kp + 8 * (lane >> 3);
+                    unsigned h0, h1, h2, h3, l0_, l1_, l2_, l3_;
+                    ldmatrix_x4(h0, h1, h2, h3, s_kh + off);
+                    ldmatrix_x4(l0_, l1_, l2_, l3_, s_kl + off);
+                    mma_16816(s_main[nt], qh[2 * kp], h0, h1);
+                    mma_16816(s_corr[nt], ql[2 * kp], h0, h1);
+                    mma_16816(s_corr[nt], qh[2 * kp], l0_, l1_);
+                    mma_16816(s_main[nt], qh[2 * kp + 1], h2, h3);
+                    mma_16816(s_corr[nt], ql[2 * kp + 1], h2, h3);
+                    mma_16816(s_corr[nt], qh[2 * kp + 1], l2_, l3_);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const __half *krow_h = s_kh + (8 * nt + g) * kAttPitch + 2 * tig + 16 * ks;
+                    const __half *krow_l = s_kl + (8 * nt + g) * kAttPitch + 2 * tig + 16 * ks;
+                    const unsigned bh0 = *reinterpret_cast<const unsigned *>(krow_h), bh1 = *reinterpret_cast<const unsigned *>(krow_h + 8);
+                    const unsigned bl0 = *reinterpret_cast<const unsigned *>(krow_l), bl1 = *reinterpret_cast<const unsigned *>(krow_l + 8);
+                    mma_16816(s_main[nt], qh[ks], bh0, bh1);
+                    mma_16816(s_corr[nt], ql[ks], bh0, bh1);
+                    mma_16816(s_corr[nt], qh[ks], bl0, bl1);
+                }
             }
         }
         // ---- online softmax in the exp2 domain (fp32)
         float mx0 = -INFINITY, mx1 = -INFINITY;
+        const bool tail = k0 + kAttTile > L;   // only the last tile holds keys past L (uniform branch)
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-            const int key = k0 + 8 * nt + 2 * tig;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float s = fmaf(s_corr[nt][i], 1.0f / 2048.0f, s_main[nt][i]);
-                if (key + (i & 1) >= L) s = -INFINITY;
-                s_main[nt][i] = s;
+            for (int i = 0; i < 4; ++i) s_main[nt][i] = fmaf(s_corr[nt][i], 1.0f / 2048.0f, s_main[nt][i]);
+            if (tail) {
+                const int key = k0 + 8 * nt + 2 * tig;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (key + (i & 1) >= L) s_main[nt][i] = -INFINITY;
             }
             mx0 = fmaxf(mx0, fmaxf(s_main[nt][0], s_main[nt][1]));
             mx1 = fmaxf(mx1, fmaxf(s_main[nt][2], s_main[nt][3]));
@@ -219,15 +256,33 @@ __global__ void __launch_bounds__(128, 2) attention_fp16x3_kernel(const float *_
             split2(s_main[2 * ks + 1][0], s_main[2 * ks + 1][1], ph[2], pl[2]);
             split2(s_main[2 * ks + 1][2], s_main[2 * ks + 1][3], ph[3], pl[3]);
             // B fragments of V[keys 16ks.., dims 8nt..]: ldmatrix.trans over the row-major [key][dim] tile; lanes 0-15 give the rows
-            const int vrow = 16 * ks + (lane & 15);
+            if (VX4) {
+                // x4.trans: lanes 0-15 give the 16 key rows at dims 8nt.. (b0, b1 of n-tile nt), lanes 16-31 the same rows at dims
+                // 8(nt+1).. (b0, b1 of n-tile nt+1)
+                const int voff = (16 * ks + (lane & 15)) * kAttPitch + 8 * (lane >> 4);
 #pragma unroll
-            for (int nt = 0; nt < 8; ++nt) {
-                unsigned vh0, vh1, vl0, vl1;
-                ldmatrix_x2_trans(vh0, vh1, s_vh + vrow * kAttPitch + 8 * nt);
-                ldmatrix_x2_trans(vl0, vl1, s_vl + vrow * kAttPitch + 8 * nt);
-                mma_16816(o_main[nt], ph, vh0, vh1);
-                mma_16816(o_corr[nt], pl, vh0, vh1);
-                mma_16816(o_corr[nt], ph, vl0, vl1);
+                for (int nt = 0; nt < 8; nt += 2) {
+                    unsigned vh0, vh1, vh2, vh3, vl0, vl1, vl2, vl3;
+                    ldmatrix_x4_trans(vh0, vh1, vh2, vh3, s_vh + voff + 8 * nt);
+                    ldmatrix_x4_trans(vl0, vl1, vl2, vl3, s_vl + voff + 8 * nt);
+                    mma_16816(o_main[nt], ph, vh0, vh1);
+                    mma_16816(o_corr[nt], pl, vh0, vh1);
+                    mma_16816(o_corr[nt], ph, vl0, vl1);
+                    mma_16816(o_main[nt + 1], ph, vh2, vh3);
+                    mma_16816(o_corr[nt + 1], pl, vh2, vh3);
+                    mma_16816(o_corr[nt + 1], ph, vl2, vl3);
+                }
+            } else {
+                const int vrow = 16 * ks + (lane & 15);
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    unsigned vh0, vh1, vl0, vl1;
+                    ldmatrix_x2_trans(vh0, vh1, s_vh + vrow * kAttPitch + 8 * nt);
+                    ldmatrix_x2_trans(vl0, vl1, s_vl + vrow * kAttPitch + 8 * nt);
+                    mma_16816(o_main[nt], ph, vh0, vh1);
+                    mma_16816(o_corr[nt], pl, vh0, vh1);
+                    mma_16816(o_corr[nt], ph, vl0, vl1);
+                }
             }
         }
         __syncthreads();   // everyone is done with this stage before the next iteration's prefetch overwrites the other one's successor
@@ -288,17 +343,32 @@ extern "C" int pnp_attention_fp16x3(const float *qkv, float in_scale, float soft
     cudaStream_t st = as_stream(stream);
     const int Lp = ceil_div(L, kAttTile) * kAttTile;
     const size_t smem = 2 * 4 * (size_t)kAttTile * kAttPitch * sizeof(__half);   // 73 728 B: two CTAs per SM
-    cudaError_t e = cudaFuncSetAttribute(attention_fp16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_err(e);
+    // fragment loads: bit 0 = K through ldmatrix.x4 (else quad LDS.32), bit 1 = V through ldmatrix.x4.trans (else x2.trans).  All four
+    // run within 1.5 % of each other (0.353-0.359 ms per call at 35 x 16 x 442, profiles/experiments/r2_attention_variants.py): the
+    // kernel is bound by the mma pipe and its latency at 2 CTAs per SM, not by fragment loads.  Default 2 (229 registers).
+    static const int variant = getenv("PNP_ATT_VARIANT") ? atoi(getenv("PNP_ATT_VARIANT")) : 2;
     __half *ws = reinterpret_cast<__half *>(workspace);
     const bool timed = prof::on(kAttention, st);
     if (timed) prof::begin(kAttention, st);
     const size_t items = (size_t)B * H * Lp * (kAttD / 4) * 2;
     const int grid = (int)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, (size_t)kNumSMs * 16));
     attention_split_kernel<<<grid, 256, 0, st>>>(qkv, ws, L, Lp, H, B, in_scale, overflow_flag);
-    attention_fp16x3_kernel<<<dim3(Lp / kAttTile, H, B), 128, smem, st>>>(qkv, ws, out, reinterpret_cast<__half *>(out3), L, Lp, H, B,
-                                                                          in_scale * softmax_scale * 1.4426950408889634f, out3_hi_scale,
-                                                                          overflow_flag);
+    const dim3 grid_main(Lp / kAttTile, H, B);
+    const float q_scale = in_scale * softmax_scale * 1.4426950408889634f;
+    __half *o3 = reinterpret_cast<__half *>(out3);
+#define PNP_ATT(KX, VX)                                                                                                       \
+    do {                                                                                                                      \
+        cudaError_t e = cudaFuncSetAttribute(attention_fp16x3_kernel<KX, VX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e != cudaSuccess) return cuda_err(e);                                                                             \
+        attention_fp16x3_kernel<KX, VX><<<grid_main, 128, smem, st>>>(qkv, ws, out, o3, L, Lp, H, B, q_scale, out3_hi_scale, overflow_flag); \
+    } while (0)
+    switch (variant & 3) {
+        case 1: PNP_ATT(true, false); break;
+        case 2: PNP_ATT(false, true); break;
+        case 3: PNP_ATT(true, true); break;
+        default: PNP_ATT(false, false); break;
+    }
+#undef PNP_ATT
     if (timed) prof::end(kAttention, st);
     return launch_status();
 }
