@@ -321,6 +321,10 @@ __global__ void __launch_bounds__(128, 2) attention_fp16x3_kernel(const float *_
     if (bad && flag) *flag = 1;
 }
 
+// attention_tc5.cu: the same contraction on tcgen05.mma / tensor memory (the default main kernel)
+int launch_attention_tc5(const float *qkv, const __half *ws, float *out, __half *out3, int L, int Lp, int H, int B, float q_scale,
+                         float hi_scale, int *flag, cudaStream_t st);
+
 }  // namespace pnp
 
 using namespace pnp;
@@ -356,6 +360,13 @@ extern "C" int pnp_attention_fp16x3(const float *qkv, float in_scale, float soft
     const dim3 grid_main(Lp / kAttTile, H, B);
     const float q_scale = in_scale * softmax_scale * 1.4426950408889634f;
     __half *o3 = reinterpret_cast<__half *>(out3);
+    // main kernel: tcgen05.mma with TMEM accumulators (attention_tc5.cu) unless PNP_ATT_TCGEN05=0 asks for the mma.sync one below
+    static const int use_tc5 = getenv("PNP_ATT_TCGEN05") ? atoi(getenv("PNP_ATT_TCGEN05")) : 1;
+    if (use_tc5) {
+        const int rc = launch_attention_tc5(qkv, ws, out, o3, L, Lp, H, B, q_scale, out3_hi_scale, overflow_flag, st);
+        if (timed) prof::end(kAttention, st);
+        return rc;
+    }
 #define PNP_ATT(KX, VX)                                                                                                       \
     do {                                                                                                                      \
         cudaError_t e = cudaFuncSetAttribute(attention_fp16x3_kernel<KX, VX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

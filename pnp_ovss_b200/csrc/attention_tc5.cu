@@ -1,0 +1,366 @@
+// attention_tc5.cu -- the encoder self-attention of attention.cu on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// tensor memory).  Same arithmetic contract: every fp32 operand is split exactly into x = h + l 2^-11 (fp16 pairs) and each
+// product is  a_h b_h + 2^-11 (a_l b_h + a_h b_l)  with fp32 accumulation, main term and corrections in separate accumulators;
+// fp32 online softmax in the exp2 domain; VIT:93-119.
+//
+// One CTA = 128 query rows of one (image, head) = the 128 lanes of tensor memory; thread t owns row t.  Keys stream in tiles of 64.
+// Per tile:  S = Q K^T   : 12 tcgen05.mma (M 128, N 64, K 16) from shared memory into TMEM columns [0,64) main, [64,128) corr
+//            softmax     : every thread reads its row of S with tcgen05.ld, p = exp2(s - m), writes P as fp16 (hi, lo) to shared memory
+//            O_t = P V   : 12 tcgen05.mma into TMEM columns [128,192) main, [192,256) corr (fresh per tile)
+//            O += O_t    : every thread reads its row of O_t and folds it into 64 fp32 registers with the online-softmax rescale
+// Operands sit in shared memory in the un-swizzled canonical core-matrix layouts (8 rows x 16 bytes = 128 contiguous bytes):
+// Q, K and P K-major; V MN-major, i.e. its row-major [key][dim] 16-byte pieces are only re-tiled, never transposed.
+// 256 TMEM columns and 112 KB of shared memory per CTA: two CTAs per SM, one's softmax under the other's MMAs.
+// Inside a CTA the tensor pipe runs ahead of the threads: S_{j+1} is issued as soon as every thread has read S_j (K tiles are
+// double-buffered), and O_{j-1} is folded into the registers one tile late, so neither MMA group is waited for right after its issue.
+// K and V tiles are fp16 (hi, lo) pairs written once per (image, head) by attention_split_kernel (attention.cu) and copied with
+// cp.async as soon as the MMAs reading the buffer they replace have committed.
+#include <cuda_fp16.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace pnp {
+namespace tc5 {
+
+constexpr int BM = 128;            // query rows per CTA = TMEM lanes
+constexpr int BN = 64;             // keys per tile
+constexpr int D = 64;              // head dimension
+constexpr uint32_t LBO = 128;      // bytes between core matrices along K (adjacent)
+constexpr uint32_t SBO = 1024;     // bytes between 8-row groups along M/N (8 K-chunks of a 64-wide tile)
+constexpr uint32_t OFF_QH = 0, OFF_QL = 16384, OFF_K = 32768 /* 2 stages x (hi 8 KB, lo 8 KB) */, OFF_VH = 65536, OFF_VL = 73728,
+                   OFF_PH = 81920, OFF_PL = 98304, OFF_BAR = 114688, SMEM_BYTES = OFF_BAR + 32;
+constexpr uint32_t TM_S_MAIN = 0, TM_S_CORR = 64, TM_O_MAIN = 128, TM_O_CORR = 192, TM_COLS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle: start >> 4 | LBO >> 4 at 16 | SBO >> 4 at 32 | version 1 at 46
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor, kind::f16: D fp32 (bit 4), A/B fp16, A K-major, B major at bit 16, N >> 3 at 17, M >> 4 at 24
+constexpr uint32_t kIdescS = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdescO = (1u << 4) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 26); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (done) return;
+    }
+    __trap();   // an MMA group that never commits is a bug: fail the launch instead of hanging the GPU
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 consecutive 32-bit columns of this thread's TMEM lane (no wait: several loads are put in flight before tmem_ld_wait)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void st_shared8(uint32_t addr, unsigned a, unsigned b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void split2(float x0, float x1, unsigned &hi, unsigned &lo) {
+    const __half2 hh = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(hh);
+    const __half2 ll = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+    hi = *reinterpret_cast<const unsigned *>(&hh);
+    lo = *reinterpret_cast<const unsigned *>(&ll);
+}
+__device__ __forceinline__ void st_shared16(uint32_t addr, unsigned a, unsigned b, unsigned c, unsigned d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ws: the workspace of attention_split_kernel, [6][B,H,Lp,64] fp16 planes (2 k_hi, 3 k_lo, 4 v_hi, 5 v_lo), Lp a multiple of 64.
+__global__ void __launch_bounds__(BM, 2) attention_tc5_kernel(const float *__restrict__ qkv, const __half *__restrict__ ws,
+                                                              float *__restrict__ out, __half *__restrict__ out3, int L, int Lp, int H, int B,
+                                                              float q_scale, float hi_scale, int *__restrict__ flag) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int t = threadIdx.x, warp = t >> 5;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
+    const uint32_t bar_s = sbase + OFF_BAR, bar_o = sbase + OFF_BAR + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 16);
+
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_o), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+
+    // ---- K / V tile copies: 512 16-byte pieces per array, 4 per thread; piece (key, c = dim / 8)
+    const size_t plane = (size_t)B * H * Lp * D;
+    const __half *head = ws + ((size_t)b * H + h) * Lp * D;
+    const int n_tiles = Lp / BN;
+    auto load_k = [&](int tile) {   // into stage tile & 1
+        const uint32_t stage = sbase + OFF_K + (uint32_t)(tile & 1) * 16384;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = t + BM * i, key = idx >> 3, c = idx & 7;
+            const uint32_t dst = (uint32_t)(key >> 3) * SBO + (uint32_t)c * LBO + (uint32_t)(key & 7) * 16;   // K-major: rows = keys
+            const __half *src = head + (size_t)(tile * BN + key) * D + c * 8;
+            cp_async16(stage + dst, src + 2 * plane);
+            cp_async16(stage + 8192 + dst, src + 3 * plane);
+        }
+    };
+    auto load_v = [&](int tile) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = t + BM * i, key = idx >> 3, c = idx & 7;
+            const uint32_t dst = (uint32_t)c * SBO + (uint32_t)(key >> 3) * LBO + (uint32_t)(key & 7) * 16;   // MN-major: 8 dims contiguous
+            const __half *src = head + (size_t)(tile * BN + key) * D + c * 8;
+            cp_async16(sbase + OFF_VH + dst, src + 4 * plane);
+            cp_async16(sbase + OFF_VL + dst, src + 5 * plane);
+        }
+    };
+    auto issue_s = [&](int tile) {   // S = Q K_tile^T : main = Qh Kh, corr = Ql Kh + Qh Kl
+        const uint32_t kh = sbase + OFF_K + (uint32_t)(tile & 1) * 16384, kl = kh + 8192;
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < D / 16; ++s) umma(tmem_slot[0] + TM_S_MAIN, make_desc(sbase + OFF_QH + 256 * s), make_desc(kh + 256 * s), kIdescS, s > 0);
+#pragma unroll
+        for (int s = 0; s < D / 16; ++s) umma(tmem_slot[0] + TM_S_CORR, make_desc(sbase + OFF_QL + 256 * s), make_desc(kh + 256 * s), kIdescS, s > 0);
+#pragma unroll
+        for (int s = 0; s < D / 16; ++s) umma(tmem_slot[0] + TM_S_CORR, make_desc(sbase + OFF_QH + 256 * s), make_desc(kl + 256 * s), kIdescS, 1);
+        umma_commit(bar_s);
+    };
+    load_k(0);
+    if (n_tiles > 1) load_k(1);
+    load_v(0);
+    cp_async_commit();
+
+    // ---- the CTA's 128 query rows, pre-multiplied by in_scale * softmax_scale * log2(e), as K-major (hi, lo) rows; 16 threads read
+    // one row's 256 bytes (coalesced), every thread converts one float4 per step
+    {
+        const float *qb = qkv + (size_t)b * L * (size_t)(3 * H * D) + (size_t)h * D;
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int idx = t + BM * i, row = idx >> 4, f = idx & 15;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q0 + row < L) a = __ldg(reinterpret_cast<const float4 *>(qb + (size_t)(q0 + row) * (size_t)(3 * H * D) + 4 * f));
+            unsigned h0, h1, l0, l1;
+            split2(a.x * q_scale, a.y * q_scale, h0, l0);
+            split2(a.z * q_scale, a.w * q_scale, h1, l1);
+            const uint32_t off = (uint32_t)(row >> 3) * SBO + (uint32_t)(f >> 1) * LBO + (uint32_t)(row & 7) * 16 + (uint32_t)(f & 1) * 8;
+            st_shared8(sbase + OFF_QH + off, h0, h1);
+            st_shared8(sbase + OFF_QL + off, l0, l1);
+        }
+    }
+    cp_async_wait0();
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    if (t == 0) issue_s(0);
+
+    float o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+    const uint32_t p_row = (uint32_t)(t >> 3) * SBO + (uint32_t)(t & 7) * 16;
+
+    // O = alpha O + O_t for the tile whose P V group was committed last
+    auto fold_o = [&](float alpha) {
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t a[32], cr[32];
+            tmem_ld32(lane_addr + TM_O_MAIN + c0, a);
+            tmem_ld32(lane_addr + TM_O_CORR + c0, cr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                o[c0 + i] = fmaf(o[c0 + i], alpha, fmaf(__uint_as_float(cr[i]), 1.0f / 2048.0f, __uint_as_float(a[i])));
+        }
+    };
+
+    for (int j = 0; j < n_tiles; ++j) {
+        const int k0 = j * BN;
+        // ---- S_j is ready (issued one tile ago); its K stage is free for tile j + 2
+        mbar_wait(bar_s, (uint32_t)(j & 1));
+        tc_fence_after();
+        if (j + 2 < n_tiles) load_k(j + 2);
+        float s[BN];
+        {
+            uint32_t a0[32], c0[32], a1[32], c1[32];
+            tmem_ld32(lane_addr + TM_S_MAIN, a0);
+            tmem_ld32(lane_addr + TM_S_CORR, c0);
+            tmem_ld32(lane_addr + TM_S_MAIN + 32, a1);
+            tmem_ld32(lane_addr + TM_S_CORR + 32, c1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                s[i] = fmaf(__uint_as_float(c0[i]), 1.0f / 2048.0f, __uint_as_float(a0[i]));
+                s[32 + i] = fmaf(__uint_as_float(c1[i]), 1.0f / 2048.0f, __uint_as_float(a1[i]));
+            }
+        }
+        // ---- every thread holds its row of S_j: the tensor pipe starts on S_{j+1} (K_{j+1} landed before the last P V issue)
+        tc_fence_before();
+        __syncthreads();
+        if (t == 0 && j + 1 < n_tiles) issue_s(j + 1);
+
+        // ---- fold O_{j-1} (its MMAs ran under the reads above); P and V buffers are free again
+        if (j > 0) {
+            mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
+            tc_fence_after();
+            fold_o(alpha_prev);
+            load_v(j);
+        }
+        cp_async_commit();
+
+        // ---- online softmax on this thread's row
+        if (k0 + BN > L) {   // only the last tile holds keys past L
+#pragma unroll
+            for (int i = 0; i < BN; ++i)
+                if (k0 + i >= L) s[i] = -INFINITY;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int i = 1; i < BN; ++i) mx = fmaxf(mx, s[i]);
+        const float mn = fmaxf(m, mx);       // finite: every tile holds at least one key < L
+        alpha_prev = ex2_approx(m - mn);     // m = -inf on the first tile: 0, and o = l = 0 there
+        m = mn;
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < BN / 8; ++c) {
+            unsigned ph[4], pl[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float p0 = ex2_approx(s[8 * c + 2 * i] - mn), p1 = ex2_approx(s[8 * c + 2 * i + 1] - mn);
+                sum += p0 + p1;
+                split2(p0, p1, ph[i], pl[i]);
+            }
+            st_shared16(sbase + OFF_PH + p_row + c * LBO, ph[0], ph[1], ph[2], ph[3]);
+            st_shared16(sbase + OFF_PL + p_row + c * LBO, pl[0], pl[1], pl[2], pl[3]);
+        }
+        l = l * alpha_prev + sum;
+
+        // ---- O_t = P V_j : main = Ph Vh, corr = Pl Vh + Ph Vl
+        cp_async_wait0();          // V_j (and K_{j+2}) have landed
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (t == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int s2 = 0; s2 < BN / 16; ++s2)
+                umma(tmem + TM_O_MAIN, make_desc(sbase + OFF_PH + 256 * s2), make_desc(sbase + OFF_VH + 256 * s2), kIdescO, s2 > 0);
+#pragma unroll
+            for (int s2 = 0; s2 < BN / 16; ++s2)
+                umma(tmem + TM_O_CORR, make_desc(sbase + OFF_PL + 256 * s2), make_desc(sbase + OFF_VH + 256 * s2), kIdescO, s2 > 0);
+#pragma unroll
+            for (int s2 = 0; s2 < BN / 16; ++s2)
+                umma(tmem + TM_O_CORR, make_desc(sbase + OFF_PH + 256 * s2), make_desc(sbase + OFF_VL + 256 * s2), kIdescO, 1);
+            umma_commit(bar_o);
+        }
+    }
+    mbar_wait(bar_o, (uint32_t)((n_tiles - 1) & 1));
+    tc_fence_after();
+    fold_o(alpha_prev);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
+
+    // ---- normalise and store this thread's row
+    const int r = q0 + t;
+    if (r >= L) return;
+    const float inv = 1.0f / l;
+    const int Dm = H * D;
+    const size_t mrow = (size_t)b * L + r;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] *= inv;
+    if (out) {
+        float *dst = out + mrow * Dm + (size_t)h * D;
+#pragma unroll
+        for (int i = 0; i < D; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+    }
+    if (out3) {   // [h * hi_scale | l | h] of the attention output, ready for the projection GEMM
+        __half *row = out3 + mrow * 3 * Dm + (size_t)h * D;
+        const __half2 hs2 = __float2half2_rn(hi_scale);
+#pragma unroll
+        for (int i = 0; i < D; i += 8) {
+            unsigned hh[4], ll[4], sc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                split2(o[i + 2 * k], o[i + 2 * k + 1], hh[k], ll[k]);
+                const __half2 hsv = __hmul2(*reinterpret_cast<__half2 *>(&hh[k]), hs2);   // a power of two: exact
+                sc[k] = *reinterpret_cast<const unsigned *>(&hsv);
+                bad = bad || !(fabsf(o[i + 2 * k] * hi_scale) <= 65504.f && fabsf(o[i + 2 * k + 1] * hi_scale) <= 65504.f);
+            }
+            *reinterpret_cast<uint4 *>(row + i) = make_uint4(sc[0], sc[1], sc[2], sc[3]);
+            *reinterpret_cast<uint4 *>(row + Dm + i) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+            *reinterpret_cast<uint4 *>(row + 2 * Dm + i) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        }
+    }
+    if (bad && flag) *flag = 1;
+}
+
+}  // namespace tc5
+
+// launched by pnp_attention_fp16x3 (attention.cu) after the K/V split pass
+int launch_attention_tc5(const float *qkv, const __half *ws, float *out, __half *out3, int L, int Lp, int H, int B, float q_scale,
+                         float hi_scale, int *flag, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc5::attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5::SMEM_BYTES);
+        if (e != cudaSuccess) return cuda_err(e);
+        configured = true;
+    }
+    const dim3 grid(ceil_div(L, tc5::BM), H, B);
+    tc5::attention_tc5_kernel<<<grid, tc5::BM, tc5::SMEM_BYTES, st>>>(qkv, ws, out, out3, L, Lp, H, B, q_scale, hi_scale, flag);
+    return launch_status();
+}
+
+}  // namespace pnp
