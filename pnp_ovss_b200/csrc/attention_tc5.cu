@@ -27,10 +27,13 @@ namespace tc5 {
 constexpr int BM = 128;            // query rows per CTA = TMEM lanes
 constexpr int BN = 64;             // keys per tile
 constexpr int D = 64;              // head dimension
+constexpr int NT = 256;            // threads: two per query row
+constexpr int HC = 32;             // columns (keys of S, dims of O) per thread
 constexpr uint32_t LBO = 128;      // bytes between core matrices along K (adjacent)
 constexpr uint32_t SBO = 1024;     // bytes between 8-row groups along M/N (8 K-chunks of a 64-wide tile)
 constexpr uint32_t OFF_QH = 0, OFF_QL = 16384, OFF_K = 32768 /* 2 stages x (hi 8 KB, lo 8 KB) */, OFF_VH = 65536, OFF_VL = 73728,
-                   OFF_PH = 81920, OFF_PL = 98304, OFF_BAR = 114688, SMEM_BYTES = OFF_BAR + 32;
+                   OFF_PH = 81920, OFF_PL = 98304, OFF_BAR = 114688, OFF_XCH = OFF_BAR + 32, SMEM_BYTES = OFF_XCH + 512;
+static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
 constexpr uint32_t TM_S_MAIN = 0, TM_S_CORR = 64, TM_O_MAIN = 128, TM_O_CORR = 192, TM_COLS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,15 +121,22 @@ __device__ __forceinline__ void st_shared16(uint32_t addr, unsigned a, unsigned 
 }
 
 // ws: the workspace of attention_split_kernel, [6][B,H,Lp,64] fp16 planes (2 k_hi, 3 k_lo, 4 v_hi, 5 v_lo), Lp a multiple of 64.
-__global__ void __launch_bounds__(BM, 2) attention_tc5_kernel(const float *__restrict__ qkv, const __half *__restrict__ ws,
+// 256 threads: thread t works on query row t & 127 (TMEM lane) and on the column half t >> 7 of S (keys) and of O (dims); the two
+// threads of a row exchange their partial row maximum through shared memory once per tile and their row sums once at the end.
+__global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__restrict__ qkv, const __half *__restrict__ ws,
                                                               float *__restrict__ out, __half *__restrict__ out3, int L, int Lp, int H, int B,
                                                               float q_scale, float hi_scale, int *__restrict__ flag) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const int t = threadIdx.x, warp = t >> 5;
+    const int row = t & (BM - 1), hh = t >> 7;            // TMEM lane / column half
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
     const uint32_t bar_s = sbase + OFF_BAR, bar_o = sbase + OFF_BAR + 8;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 16);
+    // [256] partial row maxima, rounded up to bf16: both threads of a row must subtract the SAME bound, and any bound >= the
+    // maximum is exact for a softmax; 16 bits keep two CTAs per SM inside the 228 KB
+    unsigned short *xch = reinterpret_cast<unsigned short *>(smem + OFF_XCH);
+    float *xch_l = reinterpret_cast<float *>(smem + OFF_K);   // [256] row sums (after the last S group the K stages are free)
 
     if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1) : "memory");
@@ -138,15 +148,15 @@ __global__ void __launch_bounds__(BM, 2) attention_tc5_kernel(const float *__res
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
 
-    // ---- K / V tile copies: 512 16-byte pieces per array, 4 per thread; piece (key, c = dim / 8)
+    // ---- K / V tile copies: 512 16-byte pieces per array, 2 per thread; piece (key, c = dim / 8)
     const size_t plane = (size_t)B * H * Lp * D;
     const __half *head = ws + ((size_t)b * H + h) * Lp * D;
     const int n_tiles = Lp / BN;
     auto load_k = [&](int tile) {   // into stage tile & 1
         const uint32_t stage = sbase + OFF_K + (uint32_t)(tile & 1) * 16384;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = t + BM * i, key = idx >> 3, c = idx & 7;
+        for (int i = 0; i < 2; ++i) {
+            const int idx = t + NT * i, key = idx >> 3, c = idx & 7;
             const uint32_t dst = (uint32_t)(key >> 3) * SBO + (uint32_t)c * LBO + (uint32_t)(key & 7) * 16;   // K-major: rows = keys
             const __half *src = head + (size_t)(tile * BN + key) * D + c * 8;
             cp_async16(stage + dst, src + 2 * plane);
@@ -155,23 +165,27 @@ __global__ void __launch_bounds__(BM, 2) attention_tc5_kernel(const float *__res
     };
     auto load_v = [&](int tile) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = t + BM * i, key = idx >> 3, c = idx & 7;
+        for (int i = 0; i < 2; ++i) {
+            const int idx = t + NT * i, key = idx >> 3, c = idx & 7;
             const uint32_t dst = (uint32_t)c * SBO + (uint32_t)(key >> 3) * LBO + (uint32_t)(key & 7) * 16;   // MN-major: 8 dims contiguous
             const __half *src = head + (size_t)(tile * BN + key) * D + c * 8;
             cp_async16(sbase + OFF_VH + dst, src + 4 * plane);
             cp_async16(sbase + OFF_VL + dst, src + 5 * plane);
         }
     };
-    auto issue_s = [&](int tile) {   // S = Q K_tile^T : main = Qh Kh, corr = Ql Kh + Qh Kl
-        const uint32_t kh = sbase + OFF_K + (uint32_t)(tile & 1) * 16384, kl = kh + 8192;
+    // descriptors of the first k-step of every operand; k-step s is 256 bytes further: + 16 in the start-address field
+    const uint64_t d_qh = make_desc(sbase + OFF_QH), d_ql = make_desc(sbase + OFF_QL), d_ph = make_desc(sbase + OFF_PH),
+                   d_pl = make_desc(sbase + OFF_PL), d_vh = make_desc(sbase + OFF_VH), d_vl = make_desc(sbase + OFF_VL),
+                   d_k0 = make_desc(sbase + OFF_K);
+    auto issue_s = [&](int tile, uint32_t tm) {   // S = Q K_tile^T : main = Qh Kh, corr = Ql Kh + Qh Kl
+        const uint64_t d_kh = d_k0 + (uint64_t)((tile & 1) * (16384 >> 4)), d_kl = d_kh + (8192 >> 4);
         tc_fence_after();
 #pragma unroll
-        for (int s = 0; s < D / 16; ++s) umma(tmem_slot[0] + TM_S_MAIN, make_desc(sbase + OFF_QH + 256 * s), make_desc(kh + 256 * s), kIdescS, s > 0);
+        for (int s = 0; s < D / 16; ++s) umma(tm + TM_S_MAIN, d_qh + 16 * s, d_kh + 16 * s, kIdescS, s > 0);
 #pragma unroll
-        for (int s = 0; s < D / 16; ++s) umma(tmem_slot[0] + TM_S_CORR, make_desc(sbase + OFF_QL + 256 * s), make_desc(kh + 256 * s), kIdescS, s > 0);
+        for (int s = 0; s < D / 16; ++s) umma(tm + TM_S_CORR, d_ql + 16 * s, d_kh + 16 * s, kIdescS, s > 0);
 #pragma unroll
-        for (int s = 0; s < D / 16; ++s) umma(tmem_slot[0] + TM_S_CORR, make_desc(sbase + OFF_QH + 256 * s), make_desc(kl + 256 * s), kIdescS, 1);
+        for (int s = 0; s < D / 16; ++s) umma(tm + TM_S_CORR, d_qh + 16 * s, d_kl + 16 * s, kIdescS, 1);
         umma_commit(bar_s);
     };
     load_k(0);
@@ -180,18 +194,23 @@ __global__ void __launch_bounds__(BM, 2) attention_tc5_kernel(const float *__res
     cp_async_commit();
 
     // ---- the CTA's 128 query rows, pre-multiplied by in_scale * softmax_scale * log2(e), as K-major (hi, lo) rows; 16 threads read
-    // one row's 256 bytes (coalesced), every thread converts one float4 per step
+    // one row's 256 bytes (coalesced); all eight loads of a thread are in flight before the first conversion
     {
         const float *qb = qkv + (size_t)b * L * (size_t)(3 * H * D) + (size_t)h * D;
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int idx = t + BM * i, row = idx >> 4, f = idx & 15;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (q0 + row < L) a = __ldg(reinterpret_cast<const float4 *>(qb + (size_t)(q0 + row) * (size_t)(3 * H * D) + 4 * f));
+        float4 a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = t + NT * i, r = idx >> 4, f = idx & 15;
+            a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q0 + r < L) a[i] = __ldg(reinterpret_cast<const float4 *>(qb + (size_t)(q0 + r) * (size_t)(3 * H * D) + 4 * f));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = t + NT * i, r = idx >> 4, f = idx & 15;
             unsigned h0, h1, l0, l1;
-            split2(a.x * q_scale, a.y * q_scale, h0, l0);
-            split2(a.z * q_scale, a.w * q_scale, h1, l1);
-            const uint32_t off = (uint32_t)(row >> 3) * SBO + (uint32_t)(f >> 1) * LBO + (uint32_t)(row & 7) * 16 + (uint32_t)(f & 1) * 8;
+            split2(a[i].x * q_scale, a[i].y * q_scale, h0, l0);
+            split2(a[i].z * q_scale, a[i].w * q_scale, h1, l1);
+            const uint32_t off = (uint32_t)(r >> 3) * SBO + (uint32_t)(f >> 1) * LBO + (uint32_t)(r & 7) * 16 + (uint32_t)(f & 1) * 8;
             st_shared8(sbase + OFF_QH + off, h0, h1);
             st_shared8(sbase + OFF_QL + off, l0, l1);
         }
@@ -202,53 +221,67 @@ __global__ void __launch_bounds__(BM, 2) attention_tc5_kernel(const float *__res
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    if (t == 0) issue_s(0);
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(hh * HC);
+    if (t == 0) issue_s(0, tmem);
 
-    float o[D];
+    float o[HC];
 #pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    for (int i = 0; i < HC; ++i) o[i] = 0.f;
     float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
-    const uint32_t p_row = (uint32_t)(t >> 3) * SBO + (uint32_t)(t & 7) * 16;
+    const uint32_t p_row = (uint32_t)(row >> 3) * SBO + (uint32_t)(row & 7) * 16 + (uint32_t)(hh * (HC / 8)) * LBO;
 
-    // O = alpha O + O_t for the tile whose P V group was committed last
+    // O = alpha O + O_t (this thread's 32 dims) for the tile whose P V group was committed last
     auto fold_o = [&](float alpha) {
 #pragma unroll
-        for (int c0 = 0; c0 < D; c0 += 32) {
-            uint32_t a[32], cr[32];
-            tmem_ld32(lane_addr + TM_O_MAIN + c0, a);
-            tmem_ld32(lane_addr + TM_O_CORR + c0, cr);
+        for (int c0 = 0; c0 < HC; c0 += 16) {
+            float a[16], cr[16];
+            tmem_ld16(lane_addr + TM_O_MAIN + c0, a);
+            tmem_ld16(lane_addr + TM_O_CORR + c0, cr);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-                o[c0 + i] = fmaf(o[c0 + i], alpha, fmaf(__uint_as_float(cr[i]), 1.0f / 2048.0f, __uint_as_float(a[i])));
+            for (int i = 0; i < 16; ++i) o[c0 + i] = fmaf(o[c0 + i], alpha, fmaf(cr[i], 1.0f / 2048.0f, a[i]));
         }
     };
 
     for (int j = 0; j < n_tiles; ++j) {
-        const int k0 = j * BN;
+        const int k0 = j * BN + hh * HC;     // first key of this thread's half of the tile
         // ---- S_j is ready (issued one tile ago); its K stage is free for tile j + 2
         mbar_wait(bar_s, (uint32_t)(j & 1));
         tc_fence_after();
         if (j + 2 < n_tiles) load_k(j + 2);
-        float s[BN];
+        float s[HC];
         {
-            uint32_t a0[32], c0[32], a1[32], c1[32];
-            tmem_ld32(lane_addr + TM_S_MAIN, a0);
-            tmem_ld32(lane_addr + TM_S_CORR, c0);
-            tmem_ld32(lane_addr + TM_S_MAIN + 32, a1);
-            tmem_ld32(lane_addr + TM_S_CORR + 32, c1);
+            float a0[16], c0[16], a1[16], c1[16];
+            tmem_ld16(lane_addr + TM_S_MAIN, a0);
+            tmem_ld16(lane_addr + TM_S_CORR, c0);
+            tmem_ld16(lane_addr + TM_S_MAIN + 16, a1);
+            tmem_ld16(lane_addr + TM_S_CORR + 16, c1);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                s[i] = fmaf(__uint_as_float(c0[i]), 1.0f / 2048.0f, __uint_as_float(a0[i]));
-                s[32 + i] = fmaf(__uint_as_float(c1[i]), 1.0f / 2048.0f, __uint_as_float(a1[i]));
+            for (int i = 0; i < 16; ++i) {
+                s[i] = fmaf(c0[i], 1.0f / 2048.0f, a0[i]);
+                s[16 + i] = fmaf(c1[i], 1.0f / 2048.0f, a1[i]);
             }
         }
-        // ---- every thread holds its row of S_j: the tensor pipe starts on S_{j+1} (K_{j+1} landed before the last P V issue)
+        if (k0 + HC > L) {   // only the last tile holds keys past L
+#pragma unroll
+            for (int i = 0; i < HC; ++i)
+                if (k0 + i >= L) s[i] = -INFINITY;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int i = 1; i < HC; ++i) mx = fmaxf(mx, s[i]);
+        {
+            const unsigned u = __float_as_uint(mx);
+            const unsigned up = (u & 0x80000000u) ? (u & 0xFFFF0000u) : ((u + 0xFFFFu) & 0xFFFF0000u);   // towards +inf
+            mx = __uint_as_float(up);
+            xch[t] = (unsigned short)(up >> 16);
+        }
+        // ---- every thread holds its part of S_j: the tensor pipe starts on S_{j+1} (K_{j+1} landed before the last P V issue)
         tc_fence_before();
         __syncthreads();
-        if (t == 0 && j + 1 < n_tiles) issue_s(j + 1);
+        if (t == 0 && j + 1 < n_tiles) issue_s(j + 1, tmem);
+        mx = fmaxf(mx, __uint_as_float((unsigned)xch[t ^ BM] << 16));   // the other half of the row (written before the barrier above)
 
         // ---- fold O_{j-1} (its MMAs ran under the reads above); P and V buffers are free again
         if (j > 0) {
@@ -259,21 +292,13 @@ __global__ void __launch_bounds__(BM, 2) attention_tc5_kernel(const float *__res
         }
         cp_async_commit();
 
-        // ---- online softmax on this thread's row
-        if (k0 + BN > L) {   // only the last tile holds keys past L
-#pragma unroll
-            for (int i = 0; i < BN; ++i)
-                if (k0 + i >= L) s[i] = -INFINITY;
-        }
-        float mx = s[0];
-#pragma unroll
-        for (int i = 1; i < BN; ++i) mx = fmaxf(mx, s[i]);
+        // ---- online softmax on this thread's half row
         const float mn = fmaxf(m, mx);       // finite: every tile holds at least one key < L
         alpha_prev = ex2_approx(m - mn);     // m = -inf on the first tile: 0, and o = l = 0 there
         m = mn;
         float sum = 0.f;
 #pragma unroll
-        for (int c = 0; c < BN / 8; ++c) {
+        for (int c = 0; c < HC / 8; ++c) {
             unsigned ph[4], pl[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -294,54 +319,75 @@ __global__ void __launch_bounds__(BM, 2) attention_tc5_kernel(const float *__res
         if (t == 0) {
             tc_fence_after();
 #pragma unroll
-            for (int s2 = 0; s2 < BN / 16; ++s2)
-                umma(tmem + TM_O_MAIN, make_desc(sbase + OFF_PH + 256 * s2), make_desc(sbase + OFF_VH + 256 * s2), kIdescO, s2 > 0);
+            for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_MAIN, d_ph + 16 * s2, d_vh + 16 * s2, kIdescO, s2 > 0);
 #pragma unroll
-            for (int s2 = 0; s2 < BN / 16; ++s2)
-                umma(tmem + TM_O_CORR, make_desc(sbase + OFF_PL + 256 * s2), make_desc(sbase + OFF_VH + 256 * s2), kIdescO, s2 > 0);
+            for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_CORR, d_pl + 16 * s2, d_vh + 16 * s2, kIdescO, s2 > 0);
 #pragma unroll
-            for (int s2 = 0; s2 < BN / 16; ++s2)
-                umma(tmem + TM_O_CORR, make_desc(sbase + OFF_PH + 256 * s2), make_desc(sbase + OFF_VL + 256 * s2), kIdescO, 1);
+            for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_CORR, d_ph + 16 * s2, d_vl + 16 * s2, kIdescO, 1);
             umma_commit(bar_o);
         }
     }
     mbar_wait(bar_o, (uint32_t)((n_tiles - 1) & 1));
     tc_fence_after();
     fold_o(alpha_prev);
+    xch_l[t] = l;
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
 
-    // ---- normalise and store this thread's row
-    const int r = q0 + t;
-    if (r >= L) return;
-    const float inv = 1.0f / l;
+    // ---- normalise; the rows go through shared memory (the V and P buffers are free) so that the global stores are whole
+    // 256-byte (fp32) / 128-byte (fp16) row segments.  16-byte pieces are XOR-swizzled by the row: conflict-free both ways.
+    const float inv = 1.0f / (l + xch_l[t ^ BM]);
     const int Dm = H * D;
-    const size_t mrow = (size_t)b * L + r;
     bool bad = false;
 #pragma unroll
-    for (int i = 0; i < D; ++i) o[i] *= inv;
+    for (int i = 0; i < HC; ++i) o[i] *= inv;
+    const uint32_t stage = sbase + OFF_VH;
     if (out) {
-        float *dst = out + mrow * Dm + (size_t)h * D;
 #pragma unroll
-        for (int i = 0; i < D; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+        for (int c = 0; c < HC / 4; ++c) {   // fp32 [128][16 pieces]
+            const int piece = hh * (HC / 4) + c;
+            st_shared16(stage + (uint32_t)row * 256 + (uint32_t)((piece ^ (row & 7)) * 16), __float_as_uint(o[4 * c]), __float_as_uint(o[4 * c + 1]),
+                        __float_as_uint(o[4 * c + 2]), __float_as_uint(o[4 * c + 3]));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = t + NT * i, r = idx >> 4, piece = idx & 15;
+            if (q0 + r < L) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(smem + OFF_VH + r * 256 + ((piece ^ (r & 7)) * 16));
+                *reinterpret_cast<uint4 *>(out + ((size_t)b * L + q0 + r) * Dm + (size_t)h * D + 4 * piece) = v;
+            }
+        }
+        if (out3) __syncthreads();
     }
-    if (out3) {   // [h * hi_scale | l | h] of the attention output, ready for the projection GEMM
-        __half *row = out3 + mrow * 3 * Dm + (size_t)h * D;
+    if (out3) {   // [h * hi_scale | l | h] of the attention output, ready for the projection GEMM: three fp16 [128][8 pieces] arrays
         const __half2 hs2 = __float2half2_rn(hi_scale);
 #pragma unroll
-        for (int i = 0; i < D; i += 8) {
-            unsigned hh[4], ll[4], sc[4];
+        for (int c = 0; c < HC / 8; ++c) {
+            unsigned hv[4], lv[4], sc[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                split2(o[i + 2 * k], o[i + 2 * k + 1], hh[k], ll[k]);
-                const __half2 hsv = __hmul2(*reinterpret_cast<__half2 *>(&hh[k]), hs2);   // a power of two: exact
+                const float x0 = o[8 * c + 2 * k], x1 = o[8 * c + 2 * k + 1];
+                split2(x0, x1, hv[k], lv[k]);
+                const __half2 hsv = __hmul2(*reinterpret_cast<__half2 *>(&hv[k]), hs2);   // a power of two: exact
                 sc[k] = *reinterpret_cast<const unsigned *>(&hsv);
-                bad = bad || !(fabsf(o[i + 2 * k] * hi_scale) <= 65504.f && fabsf(o[i + 2 * k + 1] * hi_scale) <= 65504.f);
+                bad = bad || !(fabsf(x0 * hi_scale) <= 65504.f && fabsf(x1 * hi_scale) <= 65504.f);
             }
-            *reinterpret_cast<uint4 *>(row + i) = make_uint4(sc[0], sc[1], sc[2], sc[3]);
-            *reinterpret_cast<uint4 *>(row + Dm + i) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-            *reinterpret_cast<uint4 *>(row + 2 * Dm + i) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            const int piece = hh * (HC / 8) + c;
+            const uint32_t off = (uint32_t)row * 128 + (uint32_t)((piece ^ (row & 7)) * 16);
+            st_shared16(stage + off, sc[0], sc[1], sc[2], sc[3]);
+            st_shared16(stage + 16384 + off, lv[0], lv[1], lv[2], lv[3]);
+            st_shared16(stage + 32768 + off, hv[0], hv[1], hv[2], hv[3]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const int idx = t + NT * i, arr = idx >> 10, r = (idx >> 3) & (BM - 1), piece = idx & 7;
+            if (q0 + r < L) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(smem + OFF_VH + arr * 16384 + r * 128 + ((piece ^ (r & 7)) * 16));
+                *reinterpret_cast<uint4 *>(out3 + ((size_t)b * L + q0 + r) * 3 * Dm + (size_t)arr * Dm + (size_t)h * D + 8 * piece) = v;
+            }
         }
     }
     if (bad && flag) *flag = 1;
@@ -359,7 +405,7 @@ int launch_attention_tc5(const float *qkv, const __half *ws, float *out, __half 
         configured = true;
     }
     const dim3 grid(ceil_div(L, tc5::BM), H, B);
-    tc5::attention_tc5_kernel<<<grid, tc5::BM, tc5::SMEM_BYTES, st>>>(qkv, ws, out, out3, L, Lp, H, B, q_scale, hi_scale, flag);
+    tc5::attention_tc5_kernel<<<grid, tc5::NT, tc5::SMEM_BYTES, st>>>(qkv, ws, out, out3, L, Lp, H, B, q_scale, hi_scale, flag);
     return launch_status();
 }
 
