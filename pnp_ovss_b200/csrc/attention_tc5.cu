@@ -24,15 +24,23 @@
 namespace pnp {
 namespace tc5 {
 
+#ifdef PNP_ATT_TRACE   // debugging build only (profiles/experiments/att_trace.sh): per-phase clock stamps of two threads of one CTA
+__device__ long long g_trace[2][16][12];
+#define TR(k) do { if (trace_on) g_trace[trace_who][j < 16 ? j : 15][k] = clock64(); } while (0)
+#else
+#define TR(k) do { } while (0)
+#endif
+
 constexpr int BM = 128;            // query rows per CTA = TMEM lanes
 constexpr int BN = 64;             // keys per tile
 constexpr int D = 64;              // head dimension
 constexpr int NT = 256;            // threads: two per query row
+constexpr int NS = NT;
 constexpr int HC = 32;             // columns (keys of S, dims of O) per thread
 constexpr uint32_t LBO = 128;      // bytes between core matrices along K (adjacent)
 constexpr uint32_t SBO = 1024;     // bytes between 8-row groups along M/N (8 K-chunks of a 64-wide tile)
 constexpr uint32_t OFF_QH = 0, OFF_QL = 16384, OFF_K = 32768 /* 2 stages x (hi 8 KB, lo 8 KB) */, OFF_VH = 65536, OFF_VL = 73728,
-                   OFF_PH = 81920, OFF_PL = 98304, OFF_BAR = 114688, OFF_XCH = OFF_BAR + 32, SMEM_BYTES = OFF_XCH + 512;
+                   OFF_PH = 81920, OFF_PL = 98304, OFF_BAR = 114688, OFF_XCH = OFF_BAR + 64, SMEM_BYTES = OFF_XCH + 512;
 static_assert(2 * (SMEM_BYTES + 1024) <= 233472, "two CTAs per SM");
 constexpr uint32_t TM_S_MAIN = 0, TM_S_CORR = 64, TM_O_MAIN = 128, TM_O_CORR = 192, TM_COLS = 256;
 
@@ -44,6 +52,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 // instruction descriptor, kind::f16: D fp32 (bit 4), A/B fp16, A K-major, B major at bit 16, N >> 3 at 17, M >> 4 at 24
 constexpr uint32_t kIdescS = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdescS2 = (1u << 4) | ((uint32_t)(2 * BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);             // N = 128: hi and lo stacked
+constexpr uint32_t kIdescO2 = (1u << 4) | (1u << 16) | ((uint32_t)(2 * D >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+static_assert(TM_S_CORR == TM_S_MAIN + BN && TM_O_CORR == TM_O_MAIN + D && OFF_VL == OFF_VH + 8192, "stacked-N MMAs need adjacent halves");
 constexpr uint32_t kIdescO = (1u << 4) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -64,6 +75,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (done) return;
     }
     __trap();   // an MMA group that never commits is a bug: fail the launch instead of hanging the GPU
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -123,6 +140,8 @@ __device__ __forceinline__ void st_shared16(uint32_t addr, unsigned a, unsigned 
 // ws: the workspace of attention_split_kernel, [6][B,H,Lp,64] fp16 planes (2 k_hi, 3 k_lo, 4 v_hi, 5 v_lo), Lp a multiple of 64.
 // 256 threads: thread t works on query row t & 127 (TMEM lane) and on the column half t >> 7 of S (keys) and of O (dims); the two
 // threads of a row exchange their partial row maximum through shared memory once per tile and their row sums once at the end.
+// Thread 0 also issues every tcgen05.mma.  (A ninth warp that only issues was measured: 288 threads leave 96 registers per thread
+// and the softmax code then spills -- 0.31 against 0.28 ms per call.)
 __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__restrict__ qkv, const __half *__restrict__ ws,
                                                               float *__restrict__ out, __half *__restrict__ out3, int L, int Lp, int H, int B,
                                                               float q_scale, float hi_scale, int *__restrict__ flag) {
@@ -131,16 +150,21 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
     const int t = threadIdx.x, warp = t >> 5;
     const int row = t & (BM - 1), hh = t >> 7;            // TMEM lane / column half
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
-    const uint32_t bar_s = sbase + OFF_BAR, bar_o = sbase + OFF_BAR + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 16);
+    // bar_s / bar_o: an MMA group has finished (tcgen05.commit).  bar_s_free: every thread has read its part of S_j (S_{j+1} may
+    // overwrite it).  bar_p_full: every thread has written its part of P_j, folded O_{j-1} and seen its copies land (P V_j may be
+    // issued).  Only the issuing thread waits for the last two: the CTA has no block-wide barrier inside the loop.
+    const uint32_t bar_s = sbase + OFF_BAR, bar_o = sbase + OFF_BAR + 8, bar_s_free = sbase + OFF_BAR + 16, bar_p_full = sbase + OFF_BAR + 24;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 32);
     // [256] partial row maxima, rounded up to bf16: both threads of a row must subtract the SAME bound, and any bound >= the
     // maximum is exact for a softmax; 16 bits keep two CTAs per SM inside the 228 KB
     unsigned short *xch = reinterpret_cast<unsigned short *>(smem + OFF_XCH);
     float *xch_l = reinterpret_cast<float *>(smem + OFF_K);   // [256] row sums (after the last S group the K stages are free)
 
     if (t == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_o), "r"(1) : "memory");
+        mbar_init(bar_s, 1);
+        mbar_init(bar_o, 1);
+        mbar_init(bar_s_free, NS);
+        mbar_init(bar_p_full, NS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -156,7 +180,7 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
         const uint32_t stage = sbase + OFF_K + (uint32_t)(tile & 1) * 16384;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int idx = t + NT * i, key = idx >> 3, c = idx & 7;
+            const int idx = t + NS * i, key = idx >> 3, c = idx & 7;
             const uint32_t dst = (uint32_t)(key >> 3) * SBO + (uint32_t)c * LBO + (uint32_t)(key & 7) * 16;   // K-major: rows = keys
             const __half *src = head + (size_t)(tile * BN + key) * D + c * 8;
             cp_async16(stage + dst, src + 2 * plane);
@@ -166,7 +190,7 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
     auto load_v = [&](int tile) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int idx = t + NT * i, key = idx >> 3, c = idx & 7;
+            const int idx = t + NS * i, key = idx >> 3, c = idx & 7;
             const uint32_t dst = (uint32_t)c * SBO + (uint32_t)(key >> 3) * LBO + (uint32_t)(key & 7) * 16;   // MN-major: 8 dims contiguous
             const __half *src = head + (size_t)(tile * BN + key) * D + c * 8;
             cp_async16(sbase + OFF_VH + dst, src + 4 * plane);
@@ -180,12 +204,13 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
     auto issue_s = [&](int tile, uint32_t tm) {   // S = Q K_tile^T : main = Qh Kh, corr = Ql Kh + Qh Kl
         const uint64_t d_kh = d_k0 + (uint64_t)((tile & 1) * (16384 >> 4)), d_kl = d_kh + (8192 >> 4);
         tc_fence_after();
+        // B = [Kh ; Kl] stacked along N (the lo stage follows the hi stage: 8 more 8-row groups at the same SBO): one N = 128 MMA
+        // per k-step gives Qh Kh in columns [0,64) and Qh Kl in [64,128); Ql Kh is added to the second half.  An MMA whose A
+        // operand comes from shared memory costs the same for N = 64 and N = 128 (the 4 KB A read dominates): 8 MMAs, not 12.
 #pragma unroll
-        for (int s = 0; s < D / 16; ++s) umma(tm + TM_S_MAIN, d_qh + 16 * s, d_kh + 16 * s, kIdescS, s > 0);
+        for (int s = 0; s < D / 16; ++s) umma(tm + TM_S_MAIN, d_qh + 16 * s, d_kh + 16 * s, kIdescS2, s > 0);
 #pragma unroll
-        for (int s = 0; s < D / 16; ++s) umma(tm + TM_S_CORR, d_ql + 16 * s, d_kh + 16 * s, kIdescS, s > 0);
-#pragma unroll
-        for (int s = 0; s < D / 16; ++s) umma(tm + TM_S_CORR, d_qh + 16 * s, d_kl + 16 * s, kIdescS, 1);
+        for (int s = 0; s < D / 16; ++s) umma(tm + TM_S_CORR, d_ql + 16 * s, d_kh + 16 * s, kIdescS, 1);
         umma_commit(bar_s);
     };
     load_k(0);
@@ -200,13 +225,13 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
         float4 a[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int idx = t + NT * i, r = idx >> 4, f = idx & 15;
+            const int idx = t + NS * i, r = idx >> 4, f = idx & 15;
             a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (q0 + r < L) a[i] = __ldg(reinterpret_cast<const float4 *>(qb + (size_t)(q0 + r) * (size_t)(3 * H * D) + 4 * f));
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int idx = t + NT * i, r = idx >> 4, f = idx & 15;
+            const int idx = t + NS * i, r = idx >> 4, f = idx & 15;
             unsigned h0, h1, l0, l1;
             split2(a[i].x * q_scale, a[i].y * q_scale, h0, l0);
             split2(a[i].z * q_scale, a[i].w * q_scale, h1, l1);
@@ -221,9 +246,13 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(hh * HC);
     if (t == 0) issue_s(0, tmem);
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(hh * HC);
 
+#ifdef PNP_ATT_TRACE
+    const bool trace_on = blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 17 && (t == 0 || t == 64);
+    const int trace_who = t == 0 ? 0 : 1;
+#endif
     float o[HC];
 #pragma unroll
     for (int i = 0; i < HC; ++i) o[i] = 0.f;
@@ -246,8 +275,10 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
     for (int j = 0; j < n_tiles; ++j) {
         const int k0 = j * BN + hh * HC;     // first key of this thread's half of the tile
         // ---- S_j is ready (issued one tile ago); its K stage is free for tile j + 2
+        TR(0);
         mbar_wait(bar_s, (uint32_t)(j & 1));
         tc_fence_after();
+        TR(1);
         if (j + 2 < n_tiles) load_k(j + 2);
         float s[HC];
         {
@@ -257,6 +288,7 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
             tmem_ld16(lane_addr + TM_S_MAIN + 16, a1);
             tmem_ld16(lane_addr + TM_S_CORR + 16, c1);
             tmem_ld_wait();
+            TR(2);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 s[i] = fmaf(c0[i], 1.0f / 2048.0f, a0[i]);
@@ -277,20 +309,31 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
             mx = __uint_as_float(up);
             xch[t] = (unsigned short)(up >> 16);
         }
-        // ---- every thread holds its part of S_j: the tensor pipe starts on S_{j+1} (K_{j+1} landed before the last P V issue)
+        // the two warps that share these 32 rows meet at a named barrier (ids 1..4, 64 threads) and read each other's bound
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
+        mx = fmaxf(mx, __uint_as_float((unsigned)xch[t ^ BM] << 16));
+        TR(3);
+        // ---- this thread is done with S_j (and with its partner's xch slot: the slot is rewritten only after S_{j+1} has been
+        // committed, which needs this arrival).  The tensor pipe starts on S_{j+1} once all 256 have arrived.
         tc_fence_before();
-        __syncthreads();
-        if (t == 0 && j + 1 < n_tiles) issue_s(j + 1, tmem);
-        mx = fmaxf(mx, __uint_as_float((unsigned)xch[t ^ BM] << 16));   // the other half of the row (written before the barrier above)
+        mbar_arrive(bar_s_free);
+        if (t == 0 && j + 1 < n_tiles) {
+            mbar_wait(bar_s_free, (uint32_t)(j & 1));
+            TR(10);
+            issue_s(j + 1, tmem);
+        }
+        TR(4);
 
         // ---- fold O_{j-1} (its MMAs ran under the reads above); P and V buffers are free again
         if (j > 0) {
             mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
             tc_fence_after();
+            TR(5);
             fold_o(alpha_prev);
             load_v(j);
         }
         cp_async_commit();
+        TR(6);
 
         // ---- online softmax on this thread's half row
         const float mn = fmaxf(m, mx);       // finite: every tile holds at least one key < L
@@ -310,22 +353,25 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
             st_shared16(sbase + OFF_PL + p_row + c * LBO, pl[0], pl[1], pl[2], pl[3]);
         }
         l = l * alpha_prev + sum;
+        TR(7);
 
         // ---- O_t = P V_j : main = Ph Vh, corr = Pl Vh + Ph Vl
-        cp_async_wait0();          // V_j (and K_{j+2}) have landed
+        cp_async_wait0();          // this thread's pieces of V_j (and K_{j+2}) have landed
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
+        mbar_arrive(bar_p_full);
+        TR(8);
         if (t == 0) {
+            mbar_wait(bar_p_full, (uint32_t)(j & 1));
+            TR(11);
             tc_fence_after();
 #pragma unroll
-            for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_MAIN, d_ph + 16 * s2, d_vh + 16 * s2, kIdescO, s2 > 0);
+            for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_MAIN, d_ph + 16 * s2, d_vh + 16 * s2, kIdescO2, s2 > 0);   // B = [Vh | Vl]
 #pragma unroll
-            for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_CORR, d_pl + 16 * s2, d_vh + 16 * s2, kIdescO, s2 > 0);
-#pragma unroll
-            for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_CORR, d_ph + 16 * s2, d_vl + 16 * s2, kIdescO, 1);
+            for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_CORR, d_pl + 16 * s2, d_vh + 16 * s2, kIdescO, 1);
             umma_commit(bar_o);
         }
+        TR(9);
     }
     mbar_wait(bar_o, (uint32_t)((n_tiles - 1) & 1));
     tc_fence_after();
@@ -350,16 +396,16 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
             st_shared16(stage + (uint32_t)row * 256 + (uint32_t)((piece ^ (row & 7)) * 16), __float_as_uint(o[4 * c]), __float_as_uint(o[4 * c + 1]),
                         __float_as_uint(o[4 * c + 2]), __float_as_uint(o[4 * c + 3]));
         }
-        __syncthreads();
+        asm volatile("bar.sync 5, %0;" ::"n"(NS) : "memory");
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int idx = t + NT * i, r = idx >> 4, piece = idx & 15;
+            const int idx = t + NS * i, r = idx >> 4, piece = idx & 15;
             if (q0 + r < L) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(smem + OFF_VH + r * 256 + ((piece ^ (r & 7)) * 16));
                 *reinterpret_cast<uint4 *>(out + ((size_t)b * L + q0 + r) * Dm + (size_t)h * D + 4 * piece) = v;
             }
         }
-        if (out3) __syncthreads();
+        if (out3) asm volatile("bar.sync 5, %0;" ::"n"(NS) : "memory");
     }
     if (out3) {   // [h * hi_scale | l | h] of the attention output, ready for the projection GEMM: three fp16 [128][8 pieces] arrays
         const __half2 hs2 = __float2half2_rn(hi_scale);
@@ -380,10 +426,10 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
             st_shared16(stage + 16384 + off, lv[0], lv[1], lv[2], lv[3]);
             st_shared16(stage + 32768 + off, hv[0], hv[1], hv[2], hv[3]);
         }
-        __syncthreads();
+        asm volatile("bar.sync 5, %0;" ::"n"(NS) : "memory");
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
-            const int idx = t + NT * i, arr = idx >> 10, r = (idx >> 3) & (BM - 1), piece = idx & 7;
+            const int idx = t + NS * i, arr = idx >> 10, r = (idx >> 3) & (BM - 1), piece = idx & 7;
             if (q0 + r < L) {
                 const uint4 v = *reinterpret_cast<const uint4 *>(smem + OFF_VH + arr * 16384 + r * 128 + ((piece ^ (r & 7)) * 16));
                 *reinterpret_cast<uint4 *>(out3 + ((size_t)b * L + q0 + r) * 3 * Dm + (size_t)arr * Dm + (size_t)h * D + 8 * piece) = v;
@@ -394,6 +440,12 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
 }
 
 }  // namespace tc5
+
+#ifdef PNP_ATT_TRACE
+extern "C" int pnp_debug_attention_trace(long long *host_out) {
+    return cuda_err(cudaMemcpyFromSymbol(host_out, tc5::g_trace, sizeof(tc5::g_trace)));
+}
+#endif
 
 // launched by pnp_attention_fp16x3 (attention.cu) after the K/V split pass
 int launch_attention_tc5(const float *qkv, const __half *ws, float *out, __half *out3, int L, int Lp, int H, int B, float q_scale,

@@ -21,7 +21,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 }
 
 __global__ void __launch_bounds__(128) probe_kernel(const __half *__restrict__ A, const __half *__restrict__ B, float *__restrict__ D,
-                                                    int b_mn_major, int a_var, int b_var, int *__restrict__ err) {
+                                                    int b_mn_major, int a_var, int b_var, int a_tmem, int *__restrict__ err) {
     __shared__ __align__(128) __half sA[M * K];
     __shared__ __align__(128) __half sB[N * K];
     __shared__ __align__(8) uint64_t bar;
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half *__restrict__ A
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(64));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("fence.proxy.async.shared::cta;");
@@ -54,6 +54,24 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half *__restrict__ A
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base_s;
+    if (a_tmem) {   // A row t as packed fp16 pairs in TMEM columns [64, 96): column c = elements (2c, 2c+1), low half first
+        uint32_t r[32];
+        for (int c = 0; c < 32; ++c) {
+            const unsigned short lo = __half_as_ushort(A[t * K + 2 * c]), hi = __half_as_ushort(A[t * K + 2 * c + 1]);
+            r[c] = (uint32_t)lo | ((uint32_t)hi << 16);
+        }
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + 64;
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31};"
+            ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+              "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+              "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+              "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+    }
     if (t == 0) {
         // idesc: c_format F32 (1 << 4), a/b F16, a K-major, b major bit 16, N >> 3 at 17, M >> 4 at 24
         const uint32_t idesc = (1u << 4) | ((uint32_t)(b_mn_major ? 1 : 0) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -62,6 +80,11 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half *__restrict__ A
             const uint64_t da = a_var ? make_desc(a_addr, SBO, LBO) : make_desc(a_addr, LBO, SBO);
             const uint64_t db = b_var ? make_desc(b_addr, SBO, LBO) : make_desc(b_addr, LBO, SBO);
             const uint32_t acc = s > 0;
+            if (a_tmem) {
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem),
+                             "r"(tmem + 64 + 8 * s), "l"(db), "r"(idesc), "r"(acc));
+                continue;
+            }
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
                          "l"(da), "l"(db), "r"(idesc), "r"(acc));
         }
@@ -93,7 +116,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __half *__restrict__ A
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
 }
 
 int main() {
@@ -112,11 +135,12 @@ int main() {
     cudaMalloc(&dA, M * K * 2); cudaMalloc(&dB, N * K * 2); cudaMalloc(&dD, M * N * 4); cudaMalloc(&dErr, 4);
     cudaMemcpy(dA, hA.data(), M * K * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hB.data(), N * K * 2, cudaMemcpyHostToDevice);
+    for (int a_tm = 0; a_tm < 2; ++a_tm)
     for (int b_mn = 0; b_mn < 2; ++b_mn)
-        for (int av = 0; av < 2; ++av)
-            for (int bv = 0; bv < 2; ++bv) {
+        for (int av = 0; av < 1; ++av)
+            for (int bv = 0; bv < 1; ++bv) {
                 cudaMemset(dD, 0, M * N * 4); cudaMemset(dErr, 0, 4);
-                probe_kernel<<<1, 128>>>(dA, dB, dD, b_mn, av, bv, dErr);
+                probe_kernel<<<1, 128>>>(dA, dB, dD, b_mn, av, bv, a_tm, dErr);
                 cudaError_t e = cudaDeviceSynchronize();
                 int herr = 0;
                 if (e == cudaSuccess) {
@@ -125,7 +149,7 @@ int main() {
                 }
                 double mx = 0;
                 for (int i = 0; i < M * N; ++i) mx = fmax(mx, fabs((double)out[i] - ref[i]));
-                printf("B %s-major  a_var %d  b_var %d : cuda %s  timeout %d  max|err| %.3e\n", b_mn ? "MN" : "K", av, bv, cudaGetErrorString(e),
+                printf("A in %s  B %s-major  a_var %d  b_var %d : cuda %s  timeout %d  max|err| %.3e\n", a_tm ? "TMEM" : "smem", b_mn ? "MN" : "K", av, bv, cudaGetErrorString(e),
                        herr, mx);
                 if (e != cudaSuccess) { printf("sticky error, stopping\n"); return 1; }
             }
