@@ -61,20 +61,16 @@ __device__ __forceinline__ void split2(float x0, float x1, unsigned &hi, unsigne
 // Done once per (image, head) instead of once per query tile inside the main kernel (7 query tiles share every K/V tile).
 __global__ void __launch_bounds__(256) attention_split_kernel(const float *__restrict__ qkv, __half *__restrict__ ws, int L, int Lp, int H,
                                                               int B, float in_scale, int *__restrict__ flag) {
+    // grid = (Lp, B): one CTA per token row; its k and v parts are 2 x H x 64 contiguous floats of qkv.  No per-item divisions.
     const size_t plane = (size_t)B * H * Lp * kAttD;                 // one [B,H,Lp,64] fp16 array
-    const size_t total = (size_t)B * H * Lp * (kAttD / 4) * 2;
+    const int l = blockIdx.x, b = blockIdx.y;
+    const int per_which = H * (kAttD / 4);                           // float4 pieces of the k (or v) part of one row
     bool bad = false;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % (kAttD / 4)) * 4;
-        size_t r = i / (kAttD / 4);
-        const int h = (int)(r % H);                                 // (c4, h, which) fastest: consecutive threads read consecutive memory
-        r /= H;
-        const int which = 1 + (int)(r % 2);                         // 1 k, 2 v (q is split by the main kernel)
-        r /= 2;
-        const int l = (int)(r % Lp);
-        const int b = (int)(r / Lp);
+    for (int i = threadIdx.x; i < 2 * per_which; i += blockDim.x) {
+        const int which = 1 + (i >= per_which), j = i - (which - 1) * per_which;   // 1 k, 2 v (q is split by the main kernel)
+        const int h = j >> 4, c4 = (j & 15) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (l < L) v = ldg_stream4(qkv + ((((size_t)b * L + l) * 3 + which) * H + h) * kAttD + c4);
+        if (l < L) v = ldg_stream4(qkv + (((size_t)b * L + l) * 3 + which) * H * kAttD + 4 * j);
         v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
         bad = bad || !(fabsf(v.x) <= 65504.f && fabsf(v.y) <= 65504.f && fabsf(v.z) <= 65504.f && fabsf(v.w) <= 65504.f);
         unsigned h01, l01, h23, l23;
@@ -354,14 +350,13 @@ extern "C" int pnp_attention_fp16x3(const float *qkv, float in_scale, float soft
     __half *ws = reinterpret_cast<__half *>(workspace);
     const bool timed = prof::on(kAttention, st);
     if (timed) prof::begin(kAttention, st);
-    const size_t items = (size_t)B * H * Lp * (kAttD / 4) * 2;
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, (size_t)kNumSMs * 16));
-    attention_split_kernel<<<grid, 256, 0, st>>>(qkv, ws, L, Lp, H, B, in_scale, overflow_flag);
+    attention_split_kernel<<<dim3(Lp, B), 256, 0, st>>>(qkv, ws, L, Lp, H, B, in_scale, overflow_flag);
     const dim3 grid_main(Lp / kAttTile, H, B);
     const float q_scale = in_scale * softmax_scale * 1.4426950408889634f;
     __half *o3 = reinterpret_cast<__half *>(out3);
     // main kernel: tcgen05.mma with TMEM accumulators (attention_tc5.cu) unless PNP_ATT_TCGEN05=0 asks for the mma.sync one below
-    static const int use_tc5 = getenv("PNP_ATT_TCGEN05") ? atoi(getenv("PNP_ATT_TCGEN05")) : 1;
+    const char *env_tc5 = getenv("PNP_ATT_TCGEN05");   // read per call: tests compare the two kernels in one process
+    const int use_tc5 = env_tc5 ? atoi(env_tc5) : 1;
     if (use_tc5) {
         const int rc = launch_attention_tc5(qkv, ws, out, o3, L, Lp, H, B, q_scale, out3_hi_scale, overflow_flag, st);
         if (timed) prof::end(kAttention, st);
