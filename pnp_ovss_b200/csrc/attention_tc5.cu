@@ -24,18 +24,12 @@
 namespace pnp {
 namespace tc5 {
 
-#ifdef PNP_ATT_TRACE   // debugging build only (profiles/experiments/att_trace.sh): per-phase clock stamps of two threads of one CTA
-__device__ long long g_trace[2][16][12];
-#define TR(k) do { if (trace_on) g_trace[trace_who][j < 16 ? j : 15][k] = clock64(); } while (0)
-#else
-#define TR(k) do { } while (0)
-#endif
 
 constexpr int BM = 128;            // query rows per CTA = TMEM lanes
 constexpr int BN = 64;             // keys per tile
 constexpr int D = 64;              // head dimension
-constexpr int NT = 256;            // threads: two per query row
-constexpr int NS = NT;
+constexpr int NS = 256;            // softmax threads: two per query row
+constexpr int NT = NS + 32;        // + the warp whose lane 0 issues every tcgen05.mma
 constexpr int HC = 32;             // columns (keys of S, dims of O) per thread
 constexpr uint32_t LBO = 128;      // bytes between core matrices along K (adjacent)
 constexpr uint32_t SBO = 1024;     // bytes between 8-row groups along M/N (8 K-chunks of a 64-wide tile)
@@ -137,28 +131,39 @@ __device__ __forceinline__ void st_shared16(uint32_t addr, unsigned a, unsigned 
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// 16 consecutive 32-bit columns of this thread's TMEM lane, store
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::"r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+                 "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])),
+                 "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr float kRescaleThreshold = 8.0f;   // O and l are rescaled only when a row's maximum has grown by more than 2^8 (exp2 domain)
+
 // ws: the workspace of attention_split_kernel, [6][B,H,Lp,64] fp16 planes (2 k_hi, 3 k_lo, 4 v_hi, 5 v_lo), Lp a multiple of 64.
-// 256 threads: thread t works on query row t & 127 (TMEM lane) and on the column half t >> 7 of S (keys) and of O (dims); the two
-// threads of a row exchange their partial row maximum through shared memory once per tile and their row sums once at the end.
-// Thread 0 also issues every tcgen05.mma.  (A ninth warp that only issues was measured: 288 threads leave 96 registers per thread
-// and the softmax code then spills -- 0.31 against 0.28 ms per call.)
+// 288 threads.  Warps 0-7 (softmax): thread t works on query row t & 127 (TMEM lane) and on the column half t >> 7 of S (keys) and
+// of O (dims); the two threads of a row exchange their partial row maximum through shared memory once per tile and their row sums
+// once at the end; they also copy the K / V tiles (cp.async).  Warp 8: lane 0 issues every tcgen05.mma (an issue blocks for ~100
+// cycles per MMA -- measured, profiles/experiments/probe_umma_timing.cu -- so it must not sit in a softmax thread's instruction stream).
+// O accumulates in tensor memory over all key tiles (the MMAs of tile j add to it).  The softmax subtracts a reference m_used that is
+// refreshed -- and O, l rescaled through tcgen05.ld / tcgen05.st -- only when the row maximum has outgrown it by more than 2^8: p stays
+// below 256, which fp16 (hi, lo) pairs hold as exactly as values below 1, and the result is the same softmax (any common shift is).
+// Hand-offs are mbarriers only: s_full / o_full (tcgen05.commit: an MMA group has finished), s_free (all 256 softmax threads have
+// read S_j), p_full (all 256 have written their part of P_j, finished any rescale of O and seen their copies land).
 __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__restrict__ qkv, const __half *__restrict__ ws,
                                                               float *__restrict__ out, __half *__restrict__ out3, int L, int Lp, int H, int B,
                                                               float q_scale, float hi_scale, int *__restrict__ flag) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
-    const int t = threadIdx.x, warp = t >> 5;
-    const int row = t & (BM - 1), hh = t >> 7;            // TMEM lane / column half
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
-    // bar_s / bar_o: an MMA group has finished (tcgen05.commit).  bar_s_free: every thread has read its part of S_j (S_{j+1} may
-    // overwrite it).  bar_p_full: every thread has written its part of P_j, folded O_{j-1} and seen its copies land (P V_j may be
-    // issued).  Only the issuing thread waits for the last two: the CTA has no block-wide barrier inside the loop.
     const uint32_t bar_s = sbase + OFF_BAR, bar_o = sbase + OFF_BAR + 8, bar_s_free = sbase + OFF_BAR + 16, bar_p_full = sbase + OFF_BAR + 24;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 32);
-    // [256] partial row maxima, rounded up to bf16: both threads of a row must subtract the SAME bound, and any bound >= the
-    // maximum is exact for a softmax; 16 bits keep two CTAs per SM inside the 228 KB
-    unsigned short *xch = reinterpret_cast<unsigned short *>(smem + OFF_XCH);
-    float *xch_l = reinterpret_cast<float *>(smem + OFF_K);   // [256] row sums (after the last S group the K stages are free)
+    const int n_tiles = Lp / BN;
 
     if (t == 0) {
         mbar_init(bar_s, 1);
@@ -167,15 +172,66 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
         mbar_init(bar_p_full, NS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == NS / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
 
+    if (warp == NS / 32) {
+        // ================================================================ MMA warp: lane 0 issues, the others wait at the end
+        tc_fence_before();
+        __syncthreads();                 // Q, K_0, K_1, V_0 are staged, TMEM is allocated, the barriers are initialised
+        tc_fence_after();
+        const uint32_t tmem = *tmem_slot;
+        if (lane == 0) {
+            // descriptors of the first k-step of every operand; k-step s is 256 bytes further: + 16 in the start-address field
+            const uint64_t d_qh = make_desc(sbase + OFF_QH), d_ql = make_desc(sbase + OFF_QL), d_ph = make_desc(sbase + OFF_PH),
+                           d_pl = make_desc(sbase + OFF_PL), d_vh = make_desc(sbase + OFF_VH), d_k0 = make_desc(sbase + OFF_K);
+            auto issue_s = [&](int tile) {   // S = Q K_tile^T : main = Qh Kh, corr = Ql Kh + Qh Kl
+                const uint64_t d_kh = d_k0 + (uint64_t)((tile & 1) * (16384 >> 4));
+                // B = [Kh ; Kl] stacked along N (the lo stage follows the hi stage: 8 more 8-row groups at the same SBO): one N = 128
+                // MMA per k-step gives Qh Kh in columns [0,64) and Qh Kl in [64,128); Ql Kh is added to the second half.  An MMA
+                // costs ~100 cycles for N = 64 and N = 128 alike: 8 MMAs, not 12.
+#pragma unroll
+                for (int s = 0; s < D / 16; ++s) umma(tmem + TM_S_MAIN, d_qh + 16 * s, d_kh + 16 * s, kIdescS2, s > 0);
+#pragma unroll
+                for (int s = 0; s < D / 16; ++s) umma(tmem + TM_S_CORR, d_ql + 16 * s, d_kh + 16 * s, kIdescS, 1);
+                umma_commit(bar_s);
+            };
+            issue_s(0);
+            for (int j = 0; j < n_tiles; ++j) {
+                const uint32_t par = (uint32_t)(j & 1);
+                if (j + 1 < n_tiles) {       // S_{j+1} once all 256 have read S_j (K_{j+1} landed before they arrived at p_full(j-1))
+                    mbar_wait(bar_s_free, par);
+                    tc_fence_after();
+                    issue_s(j + 1);
+                }
+                mbar_wait(bar_p_full, par);  // P_j and V_j are in shared memory, O has been rescaled where it had to be
+                tc_fence_after();
+#pragma unroll
+                for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_MAIN, d_ph + 16 * s2, d_vh + 16 * s2, kIdescO2, (j | s2) > 0);   // B = [Vh | Vl]
+#pragma unroll
+                for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_CORR, d_pl + 16 * s2, d_vh + 16 * s2, kIdescO, 1);
+                umma_commit(bar_o);
+            }
+        }
+        __syncwarp();
+        tc_fence_before();
+        __syncthreads();                 // the softmax warps have read the final O (which also means: every MMA has completed)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
+        return;
+    }
+
+    // ==================================================================== softmax warps
+    const int row = t & (BM - 1), hh = t >> 7;            // TMEM lane / column half
+    // [256] partial row maxima, rounded up to bf16: both threads of a row must subtract the SAME bound, and any bound >= the
+    // maximum is exact for a softmax; 16 bits keep two CTAs per SM inside the 228 KB
+    unsigned short *xch = reinterpret_cast<unsigned short *>(smem + OFF_XCH);
+    float *xch_l = reinterpret_cast<float *>(smem + OFF_K);   // [256] row sums (after the last S group the K stages are free)
+
     // ---- K / V tile copies: 512 16-byte pieces per array, 2 per thread; piece (key, c = dim / 8)
     const size_t plane = (size_t)B * H * Lp * D;
     const __half *head = ws + ((size_t)b * H + h) * Lp * D;
-    const int n_tiles = Lp / BN;
     auto load_k = [&](int tile) {   // into stage tile & 1
         const uint32_t stage = sbase + OFF_K + (uint32_t)(tile & 1) * 16384;
 #pragma unroll
@@ -196,22 +252,6 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
             cp_async16(sbase + OFF_VH + dst, src + 4 * plane);
             cp_async16(sbase + OFF_VL + dst, src + 5 * plane);
         }
-    };
-    // descriptors of the first k-step of every operand; k-step s is 256 bytes further: + 16 in the start-address field
-    const uint64_t d_qh = make_desc(sbase + OFF_QH), d_ql = make_desc(sbase + OFF_QL), d_ph = make_desc(sbase + OFF_PH),
-                   d_pl = make_desc(sbase + OFF_PL), d_vh = make_desc(sbase + OFF_VH), d_vl = make_desc(sbase + OFF_VL),
-                   d_k0 = make_desc(sbase + OFF_K);
-    auto issue_s = [&](int tile, uint32_t tm) {   // S = Q K_tile^T : main = Qh Kh, corr = Ql Kh + Qh Kl
-        const uint64_t d_kh = d_k0 + (uint64_t)((tile & 1) * (16384 >> 4)), d_kl = d_kh + (8192 >> 4);
-        tc_fence_after();
-        // B = [Kh ; Kl] stacked along N (the lo stage follows the hi stage: 8 more 8-row groups at the same SBO): one N = 128 MMA
-        // per k-step gives Qh Kh in columns [0,64) and Qh Kl in [64,128); Ql Kh is added to the second half.  An MMA whose A
-        // operand comes from shared memory costs the same for N = 64 and N = 128 (the 4 KB A read dominates): 8 MMAs, not 12.
-#pragma unroll
-        for (int s = 0; s < D / 16; ++s) umma(tm + TM_S_MAIN, d_qh + 16 * s, d_kh + 16 * s, kIdescS2, s > 0);
-#pragma unroll
-        for (int s = 0; s < D / 16; ++s) umma(tm + TM_S_CORR, d_ql + 16 * s, d_kh + 16 * s, kIdescS, 1);
-        umma_commit(bar_s);
     };
     load_k(0);
     if (n_tiles > 1) load_k(1);
@@ -246,39 +286,16 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    if (t == 0) issue_s(0, tmem);
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(hh * HC);
 
-#ifdef PNP_ATT_TRACE
-    const bool trace_on = blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 17 && (t == 0 || t == 64);
-    const int trace_who = t == 0 ? 0 : 1;
-#endif
-    float o[HC];
-#pragma unroll
-    for (int i = 0; i < HC; ++i) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f, alpha_prev = 1.f;
+    float m_used = -INFINITY, l = 0.f;
     const uint32_t p_row = (uint32_t)(row >> 3) * SBO + (uint32_t)(row & 7) * 16 + (uint32_t)(hh * (HC / 8)) * LBO;
-
-    // O = alpha O + O_t (this thread's 32 dims) for the tile whose P V group was committed last
-    auto fold_o = [&](float alpha) {
-#pragma unroll
-        for (int c0 = 0; c0 < HC; c0 += 16) {
-            float a[16], cr[16];
-            tmem_ld16(lane_addr + TM_O_MAIN + c0, a);
-            tmem_ld16(lane_addr + TM_O_CORR + c0, cr);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[c0 + i] = fmaf(o[c0 + i], alpha, fmaf(cr[i], 1.0f / 2048.0f, a[i]));
-        }
-    };
 
     for (int j = 0; j < n_tiles; ++j) {
         const int k0 = j * BN + hh * HC;     // first key of this thread's half of the tile
         // ---- S_j is ready (issued one tile ago); its K stage is free for tile j + 2
-        TR(0);
         mbar_wait(bar_s, (uint32_t)(j & 1));
         tc_fence_after();
-        TR(1);
         if (j + 2 < n_tiles) load_k(j + 2);
         float s[HC];
         {
@@ -288,7 +305,6 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
             tmem_ld16(lane_addr + TM_S_MAIN + 16, a1);
             tmem_ld16(lane_addr + TM_S_CORR + 16, c1);
             tmem_ld_wait();
-            TR(2);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 s[i] = fmaf(c0[i], 1.0f / 2048.0f, a0[i]);
@@ -312,74 +328,77 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
         // the two warps that share these 32 rows meet at a named barrier (ids 1..4, 64 threads) and read each other's bound
         asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
         mx = fmaxf(mx, __uint_as_float((unsigned)xch[t ^ BM] << 16));
-        TR(3);
         // ---- this thread is done with S_j (and with its partner's xch slot: the slot is rewritten only after S_{j+1} has been
         // committed, which needs this arrival).  The tensor pipe starts on S_{j+1} once all 256 have arrived.
         tc_fence_before();
         mbar_arrive(bar_s_free);
-        if (t == 0 && j + 1 < n_tiles) {
-            mbar_wait(bar_s_free, (uint32_t)(j & 1));
-            TR(10);
-            issue_s(j + 1, tmem);
-        }
-        TR(4);
 
-        // ---- fold O_{j-1} (its MMAs ran under the reads above); P and V buffers are free again
+        // ---- P V_{j-1} has committed: the P and V buffers are free, and O may be rescaled
         if (j > 0) {
             mbar_wait(bar_o, (uint32_t)((j - 1) & 1));
             tc_fence_after();
-            TR(5);
-            fold_o(alpha_prev);
             load_v(j);
         }
         cp_async_commit();
-        TR(6);
+        // a row whose maximum has outgrown its reference by more than 2^8 gets a new reference; O (in TMEM) and l follow.  Both
+        // threads of a row see the same mx and take the same decision for their column halves; the branch is uniform per warp
+        // because tcgen05.ld / st are warp-wide.  Tile 0 only sets the reference (O is still empty).
+        const bool grow = mx > m_used + kRescaleThreshold;   // also true on tile 0 (m_used = -inf)
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+            const float alpha = grow ? ex2_approx(m_used - mx) : 1.0f;
+#pragma unroll
+            for (int c0 = 0; c0 < HC; c0 += 16) {
+                float a[16], cr[16];
+                tmem_ld16(lane_addr + TM_O_MAIN + c0, a);
+                tmem_ld16(lane_addr + TM_O_CORR + c0, cr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { a[i] *= alpha; cr[i] *= alpha; }
+                tmem_st16(lane_addr + TM_O_MAIN + c0, a);
+                tmem_st16(lane_addr + TM_O_CORR + c0, cr);
+            }
+            tmem_st_wait();
+            l *= alpha;
+        }
+        if (grow) m_used = mx;
 
-        // ---- online softmax on this thread's half row
-        const float mn = fmaxf(m, mx);       // finite: every tile holds at least one key < L
-        alpha_prev = ex2_approx(m - mn);     // m = -inf on the first tile: 0, and o = l = 0 there
-        m = mn;
+        // ---- p = exp2(s - m_used) as fp16 (hi, lo) pairs, K-major rows of P
         float sum = 0.f;
 #pragma unroll
         for (int c = 0; c < HC / 8; ++c) {
             unsigned ph[4], pl[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float p0 = ex2_approx(s[8 * c + 2 * i] - mn), p1 = ex2_approx(s[8 * c + 2 * i + 1] - mn);
+                const float p0 = ex2_approx(s[8 * c + 2 * i] - m_used), p1 = ex2_approx(s[8 * c + 2 * i + 1] - m_used);
                 sum += p0 + p1;
                 split2(p0, p1, ph[i], pl[i]);
             }
             st_shared16(sbase + OFF_PH + p_row + c * LBO, ph[0], ph[1], ph[2], ph[3]);
             st_shared16(sbase + OFF_PL + p_row + c * LBO, pl[0], pl[1], pl[2], pl[3]);
         }
-        l = l * alpha_prev + sum;
-        TR(7);
+        l += sum;
 
-        // ---- O_t = P V_j : main = Ph Vh, corr = Pl Vh + Ph Vl
+        // ---- P V_j may be issued once all 256 are here
         cp_async_wait0();          // this thread's pieces of V_j (and K_{j+2}) have landed
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(bar_p_full);
-        TR(8);
-        if (t == 0) {
-            mbar_wait(bar_p_full, (uint32_t)(j & 1));
-            TR(11);
-            tc_fence_after();
-#pragma unroll
-            for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_MAIN, d_ph + 16 * s2, d_vh + 16 * s2, kIdescO2, s2 > 0);   // B = [Vh | Vl]
-#pragma unroll
-            for (int s2 = 0; s2 < BN / 16; ++s2) umma(tmem + TM_O_CORR, d_pl + 16 * s2, d_vh + 16 * s2, kIdescO, 1);
-            umma_commit(bar_o);
-        }
-        TR(9);
     }
     mbar_wait(bar_o, (uint32_t)((n_tiles - 1) & 1));
     tc_fence_after();
-    fold_o(alpha_prev);
+    float o[HC];
+#pragma unroll
+    for (int c0 = 0; c0 < HC; c0 += 16) {
+        float a[16], cr[16];
+        tmem_ld16(lane_addr + TM_O_MAIN + c0, a);
+        tmem_ld16(lane_addr + TM_O_CORR + c0, cr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c0 + i] = fmaf(cr[i], 1.0f / 2048.0f, a[i]);
+    }
     xch_l[t] = l;
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
 
     // ---- normalise; the rows go through shared memory (the V and P buffers are free) so that the global stores are whole
     // 256-byte (fp32) / 128-byte (fp16) row segments.  16-byte pieces are XOR-swizzled by the row: conflict-free both ways.
@@ -441,11 +460,6 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
 
 }  // namespace tc5
 
-#ifdef PNP_ATT_TRACE
-extern "C" int pnp_debug_attention_trace(long long *host_out) {
-    return cuda_err(cudaMemcpyFromSymbol(host_out, tc5::g_trace, sizeof(tc5::g_trace)));
-}
-#endif
 
 // launched by pnp_attention_fp16x3 (attention.cu) after the K/V split pass
 int launch_attention_tc5(const float *qkv, const __half *ws, float *out, __half *out3, int L, int Lp, int H, int B, float q_scale,
