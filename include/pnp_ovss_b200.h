@@ -134,6 +134,16 @@ size_t pnp_lowrank_blur_workspace_bytes(int B, int C, int P, int H, int W, doubl
 int pnp_lowrank_blur_unary(const float *class_maps, float *unary, int32_t *labels, float *maps_out, float *minmax_out,
                            void *workspace, size_t workspace_bytes, int B, int C, int P, int H, int W, float threshold,
                            int rescale, int with_background, double sigma, pnp_stream_t stream);
+/* The same over a batch whose images have DIFFERENT class counts (DRV:340-347: every image brings its own caption classes):
+ * class_maps is padded to C classes, image b really has n_classes[b] <= C of them (device int32 [B]; NULL = all C).  The channels
+ * an image does not have are dead: value -inf in maps_out, never the argmax, and unary +inf -- as are the padding channels up to
+ * Cp -- so a mean-field inference over all Cp channels (pnp_crf_inference with C = Cp) keeps their Q at exactly 0 and every
+ * real channel gets bit for bit what a per-image run with the exact class count gives.  Scale_0_1's one-class quirk
+ * (DRV:1079-1080) is applied per image. */
+int pnp_lowrank_blur_unary_padded(const float *class_maps, const int32_t *n_classes, float *unary, int32_t *labels,
+                                  float *maps_out, float *minmax_out, void *workspace, size_t workspace_bytes, int B, int C,
+                                  int P, int H, int W, float threshold, int rescale, int with_background, double sigma,
+                                  pnp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * (e) dense-CRF mean-field inference on permutohedral lattices; replaces the pydensecrf calls of

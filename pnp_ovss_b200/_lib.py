@@ -45,6 +45,8 @@ SIGNATURES = {
     "pnp_lowrank_blur_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_double, c_int]),
     "pnp_lowrank_blur_unary": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
                                        c_int, c_float, c_int, c_int, c_double, c_void_p]),
+    "pnp_lowrank_blur_unary_padded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_int,
+                                              c_int, c_int, c_float, c_int, c_int, c_double, c_void_p]),
     "pnp_lattice_storage_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pnp_lattice_build_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pnp_lattice_init": (c_int, [_LP, c_void_p, c_size_t, c_int, c_int, c_int, c_int]),

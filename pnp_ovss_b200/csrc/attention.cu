@@ -364,7 +364,7 @@ extern "C" int pnp_attention_fp16x3(const float *qkv, float in_scale, float soft
     }
 #define PNP_ATT(KX, VX)                                                                                                       \
     do {                                                                                                                      \
-        cudaError_t e = cudaFuncSetAttribute(attention_fp16x3_kernel<KX, VX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaError_t e = allow_smem(attention_fp16x3_kernel<KX, VX>, smem); \
         if (e != cudaSuccess) return cuda_err(e);                                                                             \
         attention_fp16x3_kernel<KX, VX><<<grid_main, 128, smem, st>>>(qkv, ws, out, o3, L, Lp, H, B, q_scale, out3_hi_scale, overflow_flag); \
     } while (0)

@@ -464,12 +464,8 @@ __global__ void __launch_bounds__(NT, 2) attention_tc5_kernel(const float *__res
 // launched by pnp_attention_fp16x3 (attention.cu) after the K/V split pass
 int launch_attention_tc5(const float *qkv, const __half *ws, float *out, __half *out3, int L, int Lp, int H, int B, float q_scale,
                          float hi_scale, int *flag, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc5::attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc5::SMEM_BYTES);
-        if (e != cudaSuccess) return cuda_err(e);
-        configured = true;
-    }
+    const cudaError_t e = allow_smem(tc5::attention_tc5_kernel, tc5::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_err(e);
     const dim3 grid(ceil_div(L, tc5::BM), H, B);
     tc5::attention_tc5_kernel<<<grid, tc5::NT, tc5::SMEM_BYTES, st>>>(qkv, ws, out, out3, L, Lp, H, B, q_scale, hi_scale, flag);
     return launch_status();

@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <mutex>
+#include <unordered_set>
 
 #include "../../include/pnp_ovss_b200.h"
 
@@ -20,6 +22,27 @@ static inline int launch_status() { return cuda_err(cudaGetLastError()); }
 static inline cudaStream_t as_stream(pnp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- opt-in to more than 48 KB of dynamic shared memory: granted ONCE per kernel, at the device maximum (the attribute only bounds
+// what a launch may ask for; it is process-wide state, so setting it per launch to that launch's size races between host threads)
+constexpr int kMaxOptinSmemBytes = 232448;   // B200: 227 KB per CTA
+inline cudaError_t allow_smem_ptr(const void *kernel) {
+    static std::mutex mu;
+    static std::unordered_set<const void *> granted;
+    std::lock_guard<std::mutex> lock(mu);
+    if (granted.count(kernel)) return cudaSuccess;
+    cudaFuncAttributes attr;
+    cudaError_t e = cudaFuncGetAttributes(&attr, kernel);     // static + dynamic share the 227 KB
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxOptinSmemBytes - (int)attr.sharedSizeBytes);
+    if (e == cudaSuccess) granted.insert(kernel);
+    return e;
+}
+template <typename K>
+inline cudaError_t allow_smem(K kernel, size_t bytes) {
+    if (bytes > (size_t)kMaxOptinSmemBytes) return cudaErrorInvalidValue;
+    return allow_smem_ptr(reinterpret_cast<const void *>(kernel));
+}
 
 // ---- streaming 128-bit global accesses (read-once / write-once data: keep L1 clean) ----
 __device__ __forceinline__ float4 ldg_stream4(const float *p) {

@@ -174,8 +174,7 @@ extern "C" int pnp_confusion_accumulate(const int32_t *labels, const float *gt, 
     unsigned long long *h = reinterpret_cast<unsigned long long *>(hist);
     if (smem <= 200 * 1024) {
         if (smem > 48 * 1024) {
-            cudaError_t e = vec ? cudaFuncSetAttribute(confusion_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                : cudaFuncSetAttribute(confusion_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = vec ? allow_smem(confusion_kernel<true, true>, smem) : allow_smem(confusion_kernel<true, false>, smem);
             if (e != cudaSuccess) return cuda_err(e);
             grid = (int)std::max<long long>(1, std::min<long long>((long long)kNumSMs, (items + 511) / 512));
         }

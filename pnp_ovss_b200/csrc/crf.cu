@@ -904,7 +904,7 @@ extern "C" int pnp_crf_unary_from_maps(const float *maps, const float *minmax, f
         return launch_status();
     }
     size_t smem = unary_smem(Cp);
-    cudaError_t e = cudaFuncSetAttribute(unary_from_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_smem(unary_from_maps_kernel, smem);
     if (e != cudaSuccess) return cuda_err(e);
     PNP_LAUNCH(kCrfUnary, st, unary_from_maps_kernel<<<dim3(ceil_div(N, kUnaryPix), B), kUnaryPix, smem, st>>>(maps, minmax, unary, C, Cp, N));
     return launch_status();

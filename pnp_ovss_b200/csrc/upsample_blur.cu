@@ -23,13 +23,18 @@ constexpr int kMaxP2 = 1024;
 // K1: per (b,c): min-max threshold of the PxP map; optional min/max of its upsampled image (for Scale_0_1)
 __global__ void __launch_bounds__(256) threshold_prep_kernel(const float *__restrict__ class_maps, float *__restrict__ masked,
                                                              float *__restrict__ scale_params, int C, int P, int H, int W,
-                                                             float threshold, int rescale) {
+                                                             float threshold, int rescale, const int32_t *__restrict__ n_classes) {
     __shared__ float s_grid[kMaxP2];
     __shared__ float s_red[2][8];
     __shared__ float s_mm[2];
     const int c = blockIdx.x, b = blockIdx.y;
     const int PP = P * P;
     const long long base = ((long long)b * C + c) * PP;
+    if (n_classes) {   // a batch padded to C classes: image b has n_classes[b] of them (and is rescaled only with more than one)
+        const int Cb = n_classes[b];
+        if (c >= Cb) return;
+        rescale = rescale && Cb > 1;
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     float mn = INFINITY, mx = -INFINITY;
@@ -101,9 +106,11 @@ __global__ void __launch_bounds__(256) threshold_prep_kernel(const float *__rest
 template <int VEC, bool kBgOnly = false>
 __global__ void __launch_bounds__(256) upsample_write_kernel(const float *__restrict__ masked, const float *__restrict__ scale_params,
                                                              float *__restrict__ out, int C, int P, int H, int W, int rescale,
-                                                             int with_background) {
+                                                             int with_background, const int32_t *__restrict__ n_classes = nullptr) {
     const int b = blockIdx.y;
     const int PP = P * P;
+    const int Cb = n_classes ? n_classes[b] : C;          // classes image b really has (the batch is padded to C)
+    if (n_classes) rescale = rescale && Cb > 1;
     const int Wq = W / VEC;
     const long long N = (long long)H * W;
     const int Cout = C + (with_background ? 1 : 0);
@@ -130,7 +137,7 @@ __global__ void __launch_bounds__(256) upsample_write_kernel(const float *__rest
         bool vnan[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { vmax[v] = -INFINITY; vnan[v] = false; }
-        for (int c = 0; c < C; ++c) {
+        for (int c = 0; c < Cb; ++c) {
             if (kBgOnly) {
                 // background = (no NaN) && (max over classes == 0): a pixel is decided (not background) as soon as one class
                 // is positive or NaN, and dense maps decide every pixel within the first few classes
@@ -537,8 +544,10 @@ template <int PPAD>
 __global__ void __launch_bounds__(512) lowrank_minmax_kernel(const float *__restrict__ masked, const float *__restrict__ Ay,
                                                              const float *__restrict__ AxT, float *__restrict__ T,
                                                              float *__restrict__ norm, float *__restrict__ minmax_out, int C, int P,
-                                                             int H, int W, int rows_chunk, int out_channel_offset, int out_channels) {
+                                                             int H, int W, int rows_chunk, int out_channel_offset, int out_channels,
+                                                             const int32_t *__restrict__ n_classes) {
     extern __shared__ __align__(16) float lr_smem[];
+    if (n_classes && (int)blockIdx.x >= n_classes[blockIdx.y]) return;   // a class this image does not have
     float *s_m = lr_smem;                   // [PPAD][PPAD] the thresholded grid, zero padded
     float *s_T = lr_smem + PPAD * PPAD;     // [rows_chunk][PPAD]
     __shared__ float s_red[2][16];
@@ -613,9 +622,12 @@ __global__ void __launch_bounds__(128) lowrank_unary_kernel(const float *__restr
                                                             const float *__restrict__ norm, const float *__restrict__ bg_blur,
                                                             const float *__restrict__ bg_minmax, float *__restrict__ unary,
                                                             int32_t *__restrict__ labels, float *__restrict__ maps_out, int C, int H,
-                                                            int W, int with_bg, int Cp) {
+                                                            int W, int with_bg, int Cp, const int32_t *__restrict__ n_classes) {
     extern __shared__ __align__(16) float lr_smem[];
     const int TP = blockDim.x;
+    // a batch padded to C classes: the channels image b does not have are dead -- value -inf (never the maximum, exp = 0 in the
+    // softmax) and unary +inf (Q = 0 in every mean-field iteration, so they add exact zeros to every sum)
+    const int Cb = n_classes ? n_classes[blockIdx.z] : C;
     const int Cc = C + with_bg;
     const int pitch = Cp + 1;                    // odd: thread-per-row accesses hit 32 different banks
     float *s_T = lr_smem;                        // [C][PPAD] row y of every channel's T
@@ -626,12 +638,12 @@ __global__ void __launch_bounds__(128) lowrank_unary_kernel(const float *__restr
     const size_t N = (size_t)H * W;
     {   // T rows of all channels: C segments of PPAD contiguous floats, copied as float4
         const int q_per = PPAD / 4;
-        for (int e = threadIdx.x; e < C * q_per; e += TP) {
+        for (int e = threadIdx.x; e < Cb * q_per; e += TP) {
             const int c = e / q_per, q = e - c * q_per;
             reinterpret_cast<float4 *>(s_T)[e] = __ldg(reinterpret_cast<const float4 *>(T + (((size_t)b * C + c) * H + y) * PPAD) + q);
         }
     }
-    for (int e = threadIdx.x; e < C; e += TP) s_norm[e] = __ldg(reinterpret_cast<const float2 *>(norm) + (size_t)b * C + e);
+    for (int e = threadIdx.x; e < Cb; e += TP) s_norm[e] = __ldg(reinterpret_cast<const float2 *>(norm) + (size_t)b * C + e);
     __syncthreads();
     float *row = s_tile + threadIdx.x * pitch;
     if (x < W) {
@@ -646,8 +658,9 @@ __global__ void __launch_bounds__(128) lowrank_unary_kernel(const float *__restr
             mxv = fmaxf(mxv, v);
         }
         float *rc = row + with_bg;
+        for (int c = Cb; c < C; ++c) rc[c] = -INFINITY;
 #pragma unroll 2
-        for (int c = 0; c < C; ++c) {
+        for (int c = 0; c < Cb; ++c) {
             const float yv = lr_dot<PPAD>(s_T + c * PPAD, ax);
             const float2 nm = s_norm[c];
             const float v = __fmul_rn(__fsub_rn(yv, nm.x), nm.y);   // (y - min) / (max - min), DRV:1151-1152
@@ -675,11 +688,12 @@ __global__ void __launch_bounds__(128) lowrank_unary_kernel(const float *__restr
             for (int c = 0; c < Cc; ++c) sum += __expf(row[c] - mxv);
             const bool has_nan = sum != sum;
             const float shift = __logf(sum) + mxv;
-            for (int c = 0; c < Cc; ++c) {
+            for (int c = 0; c < Cb + with_bg; ++c) {
                 const float u = fminf(fmaxf(shift - row[c], 0.f), kUnaryClipHi);
                 row[c] = has_nan ? __int_as_float(0x7fc00000) : u;
             }
-            for (int c = Cc; c < Cp; ++c) row[c] = 0.f;
+            for (int c = Cb + with_bg; c < Cc; ++c) row[c] = INFINITY;
+            for (int c = Cc; c < Cp; ++c) row[c] = n_classes ? INFINITY : 0.f;   // padded-batch mode: the CRF runs over all Cp channels
         }
     }
     if (!unary) return;
@@ -722,7 +736,7 @@ extern "C" int pnp_threshold_upsample(const float *class_maps, float *out, void 
     cudaStream_t st = as_stream(stream);
     float *masked = reinterpret_cast<float *>(workspace);
     float *params = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align_up((size_t)B * C * P * P * sizeof(float), 256));
-    PNP_LAUNCH(kThresholdPrep, st, threshold_prep_kernel<<<dim3(C, B), 256, 0, st>>>(class_maps, masked, params, C, P, H, W, threshold, rescale));
+    PNP_LAUNCH(kThresholdPrep, st, threshold_prep_kernel<<<dim3(C, B), 256, 0, st>>>(class_maps, masked, params, C, P, H, W, threshold, rescale, nullptr));
     int rc = launch_status();
     if (rc != PNP_OK) return rc;
     const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
@@ -791,12 +805,6 @@ extern "C" size_t pnp_gaussian_blur_workspace_bytes(int n_maps, int H, int W, do
 }
 
 namespace {
-// one-time opt-in to > 48 KB of dynamic shared memory per kernel (a function attribute, not data: set once per process)
-template <typename K>
-inline cudaError_t allow_smem(K kernel, size_t bytes) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-}
-
 // enqueue prologue (weights + key reset) + pass V + pass H + key decode (+ normalisation)
 int blur_impl(const float *in, float *out, float *minmax, float *weights, unsigned *keys, float *tmp, const BlurPlan &p, int n_maps,
               int H, int W, double sigma, int normalize, cudaStream_t st) {
@@ -891,7 +899,7 @@ bool make_lowrank_plan(int B, int C, int P, int H, int W, double sigma, int with
 
 template <int PPAD>
 int launch_lowrank(const LowrankPlan &p, char *ws, float *unary, int32_t *labels, float *maps_out, float *minmax_out, int B, int C,
-                   int P, int H, int W, int with_background, cudaStream_t st) {
+                   int P, int H, int W, int with_background, const int32_t *n_classes, cudaStream_t st) {
     const float *masked = reinterpret_cast<const float *>(ws + p.off_masked);
     const float *Ay = reinterpret_cast<const float *>(ws + p.off_ay), *AxT = reinterpret_cast<const float *>(ws + p.off_axt);
     float *T = reinterpret_cast<float *>(ws + p.off_T), *norm = reinterpret_cast<float *>(ws + p.off_norm);
@@ -901,11 +909,11 @@ int launch_lowrank(const LowrankPlan &p, char *ws, float *unary, int32_t *labels
     e = allow_smem(lowrank_unary_kernel<PPAD>, p.smem_b);
     if (e != cudaSuccess) return cuda_err(e);
     PNP_LAUNCH(kLowrankBlur, st, (lowrank_minmax_kernel<PPAD><<<dim3(C, B), p.threads_a, p.smem_a, st>>>(
-        masked, Ay, AxT, T, norm, minmax_out, C, P, H, W, p.rows_chunk, with_background ? 1 : 0, Cc)));
+        masked, Ay, AxT, T, norm, minmax_out, C, P, H, W, p.rows_chunk, with_background ? 1 : 0, Cc, n_classes)));
     PNP_LAUNCH(kLowrankUnary, st, (lowrank_unary_kernel<PPAD><<<dim3(ceil_div(W, p.tile_pix), H, B), p.tile_pix, p.smem_b, st>>>(
         T, AxT, norm, with_background ? reinterpret_cast<const float *>(ws + p.off_bgblur) : nullptr,
         with_background ? reinterpret_cast<const float *>(ws + p.off_bgmm) : nullptr, unary, labels, maps_out, C, H, W,
-        with_background ? 1 : 0, Cp)));
+        with_background ? 1 : 0, Cp, n_classes)));
     return launch_status();
 }
 }  // namespace
@@ -918,6 +926,14 @@ extern "C" size_t pnp_lowrank_blur_workspace_bytes(int B, int C, int P, int H, i
 extern "C" int pnp_lowrank_blur_unary(const float *class_maps, float *unary, int32_t *labels, float *maps_out, float *minmax_out,
                                       void *workspace, size_t workspace_bytes, int B, int C, int P, int H, int W, float threshold,
                                       int rescale, int with_background, double sigma, pnp_stream_t stream) {
+    return pnp_lowrank_blur_unary_padded(class_maps, nullptr, unary, labels, maps_out, minmax_out, workspace, workspace_bytes, B, C, P, H, W,
+                                         threshold, rescale, with_background, sigma, stream);
+}
+
+extern "C" int pnp_lowrank_blur_unary_padded(const float *class_maps, const int32_t *n_classes, float *unary, int32_t *labels,
+                                             float *maps_out, float *minmax_out, void *workspace, size_t workspace_bytes, int B, int C,
+                                             int P, int H, int W, float threshold, int rescale, int with_background, double sigma,
+                                             pnp_stream_t stream) {
     LowrankPlan p;
     if (!class_maps || !workspace || (!unary && !labels && !maps_out) || B > 65535 || H > 65535 ||
         !make_lowrank_plan(B, C, P, H, W, sigma, with_background, p))
@@ -929,11 +945,11 @@ extern "C" int pnp_lowrank_blur_unary(const float *class_maps, float *unary, int
     float *masked = reinterpret_cast<float *>(ws + p.off_masked), *params = reinterpret_cast<float *>(ws + p.off_params);
     // Scale_0_1 only matters for the background test (it cancels in every class channel, see above); with ONE class the
     // reference's rescale silently does not happen (DRV:1079-1080), as in pnp_threshold_upsample
-    const int bg_rescale = (rescale && with_background && C > 1) ? 1 : 0;
+    const int bg_rescale = (rescale && with_background && (n_classes || C > 1)) ? 1 : 0;   // per image in the kernels when n_classes is given
     char *bws = ws + p.off_blur_ws;
     lowrank_operator_kernel<<<ceil_div(H + W, 128), 128, (2 * p.blur.lw + 1) * sizeof(double), st>>>(
         reinterpret_cast<float *>(ws + p.off_ay), reinterpret_cast<float *>(ws + p.off_axt), H, W, P, p.PPAD, p.blur.lw, sigma);
-    PNP_LAUNCH(kThresholdPrep, st, threshold_prep_kernel<<<dim3(C, B), 256, 0, st>>>(class_maps, masked, params, C, P, H, W, threshold, bg_rescale));
+    PNP_LAUNCH(kThresholdPrep, st, threshold_prep_kernel<<<dim3(C, B), 256, 0, st>>>(class_maps, masked, params, C, P, H, W, threshold, bg_rescale, n_classes));
     int rc = launch_status();
     if (rc != PNP_OK) return rc;
     if (with_background) {
@@ -942,9 +958,9 @@ extern "C" int pnp_lowrank_blur_unary(const float *class_maps, float *unary, int
         const int per = vec ? H * (W / 4) : H * W;
         const int gx = std::max(1, std::min(ceil_div(per, 256), ceil_div(kNumSMs * 8, B)));
         if (vec)
-            PNP_LAUNCH(kUpsampleWrite, st, (upsample_write_kernel<4, true><<<dim3(gx, B), 256, 0, st>>>(masked, params, bg, C, P, H, W, bg_rescale, 1)));
+            PNP_LAUNCH(kUpsampleWrite, st, (upsample_write_kernel<4, true><<<dim3(gx, B), 256, 0, st>>>(masked, params, bg, C, P, H, W, bg_rescale, 1, n_classes)));
         else
-            PNP_LAUNCH(kUpsampleWrite, st, (upsample_write_kernel<1, true><<<dim3(gx, B), 256, 0, st>>>(masked, params, bg, C, P, H, W, bg_rescale, 1)));
+            PNP_LAUNCH(kUpsampleWrite, st, (upsample_write_kernel<1, true><<<dim3(gx, B), 256, 0, st>>>(masked, params, bg, C, P, H, W, bg_rescale, 1, n_classes)));
         const bool timed = prof::on(kBackgroundBlur, st);
         if (timed) prof::begin(kBackgroundBlur, st);
         rc = blur_impl(bg, reinterpret_cast<float *>(ws + p.off_bgblur), reinterpret_cast<float *>(ws + p.off_bgmm),
@@ -960,8 +976,8 @@ extern "C" int pnp_lowrank_blur_unary(const float *class_maps, float *unary, int
         }
     }
     switch (p.PPAD) {
-        case 24: return launch_lowrank<24>(p, ws, unary, labels, maps_out, minmax_out, B, C, P, H, W, with_background, st);
-        case 28: return launch_lowrank<28>(p, ws, unary, labels, maps_out, minmax_out, B, C, P, H, W, with_background, st);
-        default: return launch_lowrank<32>(p, ws, unary, labels, maps_out, minmax_out, B, C, P, H, W, with_background, st);
+        case 24: return launch_lowrank<24>(p, ws, unary, labels, maps_out, minmax_out, B, C, P, H, W, with_background, n_classes, st);
+        case 28: return launch_lowrank<28>(p, ws, unary, labels, maps_out, minmax_out, B, C, P, H, W, with_background, n_classes, st);
+        default: return launch_lowrank<32>(p, ws, unary, labels, maps_out, minmax_out, B, C, P, H, W, with_background, n_classes, st);
     }
 }

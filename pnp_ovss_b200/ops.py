@@ -155,14 +155,21 @@ def gaussian_blur(maps, sigma, normalize=True):
     return out, minmax
 
 
-def lowrank_blur_unary(class_maps, H, W, threshold, rescale, with_background, sigma, unary=True, labels=False, maps=False, minmax=False):
+def lowrank_blur_unary(class_maps, H, W, threshold, rescale, with_background, sigma, unary=True, labels=False, maps=False, minmax=False,
+                       n_classes=None):
     """Fused threshold -> upsample -> background -> blur -> min-max -> {CRF unary | argmax labels | maps} for class_maps
     [B,C,P,P] (pnp_lowrank_blur_unary).  Returns a dict with the requested outputs: "unary" [B,N,Cp], "labels" int32 [B,N],
-    "maps" [B,C',H,W], "minmax" [B*C',2]."""
+    "maps" [B,C',H,W], "minmax" [B*C',2].
+    n_classes: int32 [B] CUDA tensor for a batch PADDED to C classes (pnp_lowrank_blur_unary_padded): image b has n_classes[b] <= C
+    classes; its other channels, and the padding up to Cp, come out dead (unary +inf), ready for crf_inference(C = Cp)."""
     _req(class_maps, torch.float32, "class_maps", 4)
     B, C, P, P2 = class_maps.shape
     if P != P2:
         raise PnpError("class_maps must be [B,C,P,P]")
+    if n_classes is not None:
+        _req(n_classes, torch.int32, "n_classes", 1)
+        if n_classes.shape[0] != B:
+            raise PnpError("n_classes must be [B]")
     lib = _lib.load()
     ws_bytes = lib.pnp_lowrank_blur_workspace_bytes(B, C, P, int(H), int(W), float(sigma), int(bool(with_background)))
     if ws_bytes == 0:
@@ -182,9 +189,10 @@ def lowrank_blur_unary(class_maps, H, W, threshold, rescale, with_background, si
         out["minmax"] = torch.empty((B * Cc, 2), dtype=torch.float32, device=dev)
     if not (unary or labels or maps):
         raise PnpError("nothing to compute")
-    check(lib.pnp_lowrank_blur_unary(_p(class_maps), _p(out.get("unary")), _p(out.get("labels")), _p(out.get("maps")), _p(out.get("minmax")),
-                                     _p(ws), ws_bytes, B, C, P, int(H), int(W), float(threshold), int(bool(rescale)),
-                                     int(bool(with_background)), float(sigma), _stream()), "pnp_lowrank_blur_unary")
+    check(lib.pnp_lowrank_blur_unary_padded(_p(class_maps), _p(n_classes), _p(out.get("unary")), _p(out.get("labels")), _p(out.get("maps")),
+                                            _p(out.get("minmax")), _p(ws), ws_bytes, B, C, P, int(H), int(W), float(threshold),
+                                            int(bool(rescale)), int(bool(with_background)), float(sigma), _stream()),
+          "pnp_lowrank_blur_unary_padded")
     return out
 
 
@@ -235,8 +243,9 @@ class LatticeHandle:
         }
 
 
-def build_lattice(H, W, sxy, rgb=None, srgb=None, device=None):
-    """Spatial lattice (rgb None; shared by every image of a batch) or bilateral lattice over rgb uint8 [B,H,W,3]."""
+def build_lattice_begin(H, W, sxy, rgb=None, srgb=None, device=None):
+    """Enqueue the build of a spatial lattice (rgb None; shared by every image of a batch) or of a bilateral lattice over rgb uint8
+    [B,H,W,3] on the current stream (pnp_lattice_build, asynchronous).  Returns (handle, workspace) for build_lattice_finish."""
     lib = _lib.load()
     sx, sy = (sxy, sxy) if not isinstance(sxy, (tuple, list)) else sxy
     if rgb is None:
@@ -257,9 +266,20 @@ def build_lattice(H, W, sxy, rgb=None, srgb=None, device=None):
     ws_base = (ws.data_ptr() + 255) // 256 * 256
     check(lib.pnp_lattice_build(ctypes.byref(s), _p(rgb), int(H), int(W), float(sx), float(sy), float(sr), float(sg), float(sb),
                                 ctypes.c_void_p(ws_base), ws_bytes, _stream()), "pnp_lattice_build")
-    check(lib.pnp_lattice_finish(ctypes.byref(s), _stream()), "pnp_lattice_finish")
+    return lat, ws
+
+
+def build_lattice_finish(lat, ws):
+    """Second half of a build (pnp_lattice_finish: waits for the stream the build was enqueued on -- call it under that stream --
+    and reads the vertex count back).  Several builds enqueued on different streams overlap when their finishes come afterwards."""
+    check(_lib.load().pnp_lattice_finish(ctypes.byref(lat.struct), _stream()), "pnp_lattice_finish")
     del ws
     return lat
+
+
+def build_lattice(H, W, sxy, rgb=None, srgb=None, device=None):
+    """Spatial lattice (rgb None; shared by every image of a batch) or bilateral lattice over rgb uint8 [B,H,W,3]."""
+    return build_lattice_finish(*build_lattice_begin(H, W, sxy, rgb=rgb, srgb=srgb, device=device))
 
 
 def _lattice_array(lattices):

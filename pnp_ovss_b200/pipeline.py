@@ -15,6 +15,16 @@ SAVE_LEN = 10      # DRV:643
 # direct kernels (full-resolution upsample, tap-by-tap blur of every channel, separate unary): ~10x slower, same results to
 # 5e-6 on the maps; kept because its summation order is the one the bit-exact golden confusion matrices were recorded with.
 USE_LOWRANK_BLUR = True
+# Ragged batches (real datasets: every image has its own class list and ground-truth size).  Images are bucketed by
+# (padded channel count Cp, background rule, H, W): inside a bucket the class counts may differ -- the fused (d) group takes them
+# per image (pnp_lowrank_blur_unary_padded) and the channels an image lacks are dead in the CRF (Q = 0 exactly), so every image
+# gets bit for bit what a batch of its own would give.  Buckets are independent launch chains of small kernels: they are spread
+# round-robin over BUCKET_STREAMS CUDA streams, and all bilateral lattice builds are enqueued before the first one is waited for.
+PAD_CLASSES_IN_BUCKETS = True
+BUCKET_STREAMS = 4
+# A bucket of one small image is ~150 kernel launches whose device time is shorter than the host time to issue them: the buckets
+# of a ragged batch are therefore ALSO issued from BUCKET_STREAMS host threads (one per stream; the C-ABI calls release the GIL).
+BUCKET_THREADS = True
 
 
 # ---------------------------------------------------------------------------------------------- (c) loop
@@ -82,12 +92,14 @@ def segment_tensors(token_ids, decode, class_lists, dev):
     return _SEG_TABLES[key]
 
 
-def merge_tokens_batch(gradcam, token_ids, decode, class_lists, segs=None):
+def merge_tokens_batch(gradcam, token_ids, decode, class_lists, segs=None, padded=False):
     """gradcam [B,T-1,P,P]; token_ids [B,>=T] host ints; returns a list of per-image [C_b,P,P] CUDA tensors
-    (one pnp_token_merge launch over the batch, padded to the largest C)."""
+    (one pnp_token_merge launch over the batch, padded to the largest C), or with padded=True the [B,Cmax,P,P] tensor itself."""
     if segs is None:
         segs = segment_tensors(token_ids, decode, class_lists, gradcam.device)
     maps = ops.token_merge(gradcam.contiguous(), segs[0], segs[1], segs[2], row_offset=3, max_end=segs[3] if len(segs) > 3 else None)
+    if padded:
+        return maps
     return [maps[b, :len(class_lists[b])] for b in range(gradcam.shape[0])]
 
 
@@ -97,20 +109,23 @@ class SpatialLatticeCache:
     have many ground-truth sizes, so the cache is a small LRU (a 336x336 spatial lattice is about 11 MB)."""
 
     def __init__(self, max_entries=32):
+        import threading
         from collections import OrderedDict
         self._cache = OrderedDict()
         self._max = max_entries
+        self._lock = threading.Lock()     # bucket threads look shapes up concurrently
 
     def get(self, H, W, sxy, device):
         sx, sy = (sxy, sxy) if not isinstance(sxy, (tuple, list)) else sxy
         key = (int(H), int(W), float(sx), float(sy), str(device))
-        if key in self._cache:
-            self._cache.move_to_end(key)
-        else:
-            self._cache[key] = ops.build_lattice(H, W, (sx, sy), device=device)
-            while len(self._cache) > self._max:
-                self._cache.popitem(last=False)
-        return self._cache[key]
+        with self._lock:
+            if key in self._cache:
+                self._cache.move_to_end(key)
+            else:
+                self._cache[key] = ops.build_lattice(H, W, (sx, sy), device=device)
+                while len(self._cache) > self._max:
+                    self._cache.popitem(last=False)
+            return self._cache[key]
 
 
 _SPATIAL = SpatialLatticeCache()
@@ -125,10 +140,12 @@ def _mark(stats, name):
 
 
 def postprocess_batch(class_maps, guides, gts, luts, hist, *, threshold, rescale, with_background, mode, n_class,
-                      crf=None, bad_count=None, return_labels=False, stats=None, bilateral=None):
+                      crf=None, bad_count=None, return_labels=False, stats=None, bilateral=None, n_classes=None):
     """class_maps [B,C,P,P] -> labels -> hist (accumulated in place).  guides uint8 [B,H,W,3]; gts float32 [B,H,W];
     luts int32 [B,C'] (composed relabel tables).  mode: the --postprocess string ('', 'blur', 'crf', 'blur+crf').
-    bilateral: a lattice already built over `guides` (the two reference passes of one batch share it)."""
+    bilateral: a lattice already built over `guides` (the two reference passes of one batch share it).
+    n_classes: int32 [B] CUDA tensor when the images have different class counts (class_maps padded to the largest; blurred modes
+    only); luts then has Cp columns and the CRF runs over all Cp channels (the dead ones stay at Q = 0)."""
     B, C = class_maps.shape[:2]
     P_grid = class_maps.shape[-1]
     H, W = gts.shape[1:]
@@ -139,10 +156,14 @@ def postprocess_batch(class_maps, guides, gts, luts, hist, *, threshold, rescale
     p.update(crf or {})
     Cc = C + (1 if with_background else 0)
     labels = U = None
+    if n_classes is not None and not (use_blur and P_grid <= 32 and USE_LOWRANK_BLUR):
+        raise PnpError("per-image class counts need the fused low-rank (d) group (a blurred mode, P <= 32)")
     if use_blur and P_grid <= 32 and USE_LOWRANK_BLUR:
         # blurred maps: the whole (d) group as one fused low-rank launch group that emits the CRF unary (or the labels) directly
         out = ops.lowrank_blur_unary(class_maps.contiguous(), H, W, threshold, rescale, with_background, BLUR_SCALE * max(H, W),
-                                     unary=use_crf, labels=not use_crf)
+                                     unary=use_crf, labels=not use_crf, n_classes=n_classes)
+        if n_classes is not None:
+            Cc = ops.crf_pad_channels(Cc)    # every padded channel takes part; the ones an image lacks carry unary +inf
         U, labels = out.get("unary"), out.get("labels")
         _mark(stats, "upsample+blur+unary")
     else:
@@ -182,6 +203,54 @@ def _as_device_batch(items, members, dtype, dev):
 
 
 _SIDE_STREAMS = {}
+_BUCKET_STREAMS = {}
+
+
+def _bucket_streams(dev, n):
+    key = (dev.type, dev.index)
+    pool = _BUCKET_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
+
+_BUCKET_POOL = {}
+
+
+def _run_on_streams(dev, pool, jobs):
+    """jobs[i]() under stream pool[i % len(pool)]: from one host thread per stream when BUCKET_THREADS (launch-bound chains issue
+    in parallel), else in order from the calling thread.  Returns the results in order; the first exception is re-raised."""
+    if not pool:
+        return [job() for job in jobs]
+
+    def under(i, job):
+        torch.cuda.set_device(dev)
+        with torch.cuda.stream(pool[i % len(pool)]):
+            return job()
+
+    if not BUCKET_THREADS or len(jobs) < 2:
+        return [under(i, job) for i, job in enumerate(jobs)]
+    from concurrent.futures import ThreadPoolExecutor
+    n = len(pool)
+    if n not in _BUCKET_POOL:
+        _BUCKET_POOL[n] = ThreadPoolExecutor(max_workers=n, thread_name_prefix="pnp-bucket")
+
+    def lane(k):   # one thread walks the jobs of one stream in order
+        return [(i, under(i, jobs[i])) for i in range(k, len(jobs), n)]
+
+    out = [None] * len(jobs)
+    for fut in [_BUCKET_POOL[n].submit(lane, k) for k in range(n)]:
+        for i, r in fut.result():
+            out[i] = r
+    return out
+
+
+class _null_context:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
 
 
 def _side_stream(dev):
@@ -231,16 +300,29 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
     _mark(stats, "start")
 
     # everything that depends on the inputs only: buckets, device copies, relabel LUTs, token segment tables
+    use_blur = bool(mode) and "blur" in mode
+    pad_classes = PAD_CLASSES_IN_BUCKETS and use_blur and patch_num <= 32 and USE_LOWRANK_BLUR
     buckets = {}
     for b in range(B):
         C = len(class_lists[b])
         with_bg = host.add_background_rule(data_type, C)
-        buckets.setdefault((C, with_bg, tuple(gts[b].shape)), []).append(b)
-    inputs = {}
+        # with padded classes a bucket holds every class count that pads to the same Cp; else the exact count is part of the key
+        ckey = ops.crf_pad_channels(C + (1 if with_bg else 0)) if pad_classes else C
+        buckets.setdefault((ckey, with_bg, tuple(gts[b].shape)), []).append(b)
+    inputs, ncls = {}, {}
     for key, members in buckets.items():
         with_bg = key[1]
+        counts = [len(class_lists[b]) for b in members]
+        ragged_c = pad_classes and len(set(counts)) > 1
+        width = key[0] if ragged_c else counts[0] + (1 if with_bg else 0)     # LUT columns: Cp when the CRF runs over all of them
+        lut_rows = []
+        for b in members:
+            row = list(host.relabel_lut(dataset_ids[b], with_bg))
+            lut_rows.append(row + [0] * (width - len(row)))                    # dead channels are never the argmax
         inputs[key] = (_as_device_batch(gts, members, torch.float32, dev), _as_device_batch(guides, members, torch.uint8, dev),
-                       torch.tensor([host.relabel_lut(dataset_ids[b], with_bg) for b in members], dtype=torch.int32, device=dev))
+                       torch.tensor(lut_rows, dtype=torch.int32, device=dev))
+        ncls[key] = (torch.tensor(counts, dtype=torch.int32, device=dev), max(counts)) if ragged_c else (None, counts[0])
+    n_streams = min(int(BUCKET_STREAMS), len(buckets)) if (len(buckets) > 1 and not timed_stages and dev.type == "cuda") else 0
     segs = segment_tensors(token_ids, decode, class_lists, dev)
     hists = {}
     if round0_scored:
@@ -252,26 +334,60 @@ def batch_confusion(gradcam_fn, imgs, token_ids, decode, class_lists, dataset_id
     lattices = {}
     ev_lattices = None
 
+    def bucket_streams():
+        """The streams the buckets of a ragged batch are spread over (empty: everything on the current stream).  They start
+        after everything already enqueued on the current stream."""
+        if not n_streams:
+            return []
+        cur = torch.cuda.current_stream(dev)
+        pool = _bucket_streams(dev, n_streams)
+        for st in pool:
+            st.wait_stream(cur)
+        return pool
+
+    def join_streams(pool):
+        if not pool:
+            return
+        cur = torch.cuda.current_stream(dev)
+        for st in pool:
+            cur.wait_stream(st)
+
     def build_lattices():  # one bilateral lattice per bucket, shared by both passes (the guide images are the same)
         if use_crf:
-            for key in buckets:
-                lattices[key] = ops.build_lattice(key[2][0], key[2][1], crf_p["bi_xy_std"], rgb=inputs[key][1], srgb=crf_p["bi_rgb_std"])
+            keys = list(buckets)
+            for key in keys:
                 _SPATIAL.get(key[2][0], key[2][1], crf_p["pos_xy_std"], dev)
+            pool = bucket_streams()
+            # every build is enqueued before the first one is waited for (pnp_lattice_finish reads the vertex count back)
+            begun = _run_on_streams(dev, pool, [lambda key=key: ops.build_lattice_begin(key[2][0], key[2][1], crf_p["bi_xy_std"], rgb=inputs[key][1],
+                                                                                        srgb=crf_p["bi_rgb_std"]) for key in keys])
+            done = _run_on_streams(dev, pool, [lambda lw=lw: ops.build_lattice_finish(*lw) for lw in begun])
+            lattices.update(zip(keys, done))
+            join_streams(pool)
             _mark(stats, "lattice")
 
     def run_pass(name, gmaps, rescale):
-        merged = merge_tokens_batch(gmaps, token_ids, decode, class_lists, segs)
+        merged = merge_tokens_batch(gmaps, token_ids, decode, class_lists, segs, padded=True)
         _mark(stats, "merge")
-        for key, members in buckets.items():
+        pool = bucket_streams()
+
+        def one_bucket(key, members):
             gt, gd, lut = inputs[key]
-            cm = torch.stack([merged[b] for b in members]).contiguous()
-            pred = postprocess_batch(cm, gd, gt, lut, hists[name], threshold=threshold, rescale=rescale, with_background=key[1],
+            n_cls, c_max = ncls[key]
+            if len(members) == B and c_max == merged.shape[1]:
+                cm = merged
+            else:
+                cm = merged[torch.as_tensor(members, device=dev), :c_max].contiguous()
+            return postprocess_batch(cm, gd, gt, lut, hists[name], threshold=threshold, rescale=rescale, with_background=key[1],
                                      mode=mode, n_class=n_class, crf=crf, bad_count=bad, stats=stats, bilateral=lattices.get(key),
-                                     return_labels=labels_out is not None)
-            if labels_out is not None:
-                if len(buckets) != 1:
-                    raise PnpError("labels_out needs a uniform batch (one bucket)")
-                labels_out[name] = pred
+                                     return_labels=labels_out is not None, n_classes=n_cls)
+
+        if labels_out is not None and len(buckets) != 1:
+            raise PnpError("labels_out needs a uniform batch (one bucket)")
+        preds = _run_on_streams(dev, pool, [lambda key=key, members=members: one_bucket(key, members) for key, members in buckets.items()])
+        if labels_out is not None:
+            labels_out[name] = preds[0]
+        join_streams(pool)
 
     def side_prologue():
         """First use of the side stream for this batch: inputs visible, lattices built (under the running model pass)."""

@@ -52,15 +52,25 @@ def make(ops_module):
             x = torch.cat([(x.max(1, keepdim=True)[0] == 0).float(), x], 1)
         return x.contiguous()
 
-    def lowrank_blur_unary(class_maps, H, W, threshold, rescale, with_background, sigma, unary=True, labels=False, maps=False, minmax=False):
+    def crf_pad_channels(C):
+        return (C + 3) // 4 * 4
+
+    def lowrank_blur_unary(class_maps, H, W, threshold, rescale, with_background, sigma, unary=True, labels=False, maps=False, minmax=False,
+                           n_classes=None):
         log("lowrank_blur_unary")
         x = threshold_upsample(class_maps, H, W, threshold, rescale, with_background)
         ns.calls.pop()
         B, Cc = x.shape[:2]
+        if n_classes is not None:   # the channels an image lacks are dead
+            assert n_classes.dtype == torch.int32 and n_classes.shape == (B,)
+            for b in range(B):
+                x[b, int(n_classes[b]) + (1 if with_background else 0):] = -float("inf")
         out = {}
         if unary:
             out["unary"] = crf_unary_from_maps(x.view(B, Cc, H * W))
             ns.calls.pop()
+            if n_classes is not None:
+                out["unary"][:, :, Cc:] = float("inf")
         if labels:
             out["labels"] = x.view(B, Cc, H * W).argmax(1).to(torch.int32)
         if maps:
@@ -83,6 +93,13 @@ def make(ops_module):
     def build_lattice(H, W, sxy, rgb=None, srgb=None, device=None):
         log("build_lattice")
         return _Lattice(H * W // 4)
+
+    def build_lattice_begin(H, W, sxy, rgb=None, srgb=None, device=None):
+        log("build_lattice")
+        return _Lattice(H * W // 4), None
+
+    def build_lattice_finish(lat, ws):
+        return lat
 
     def crf_inference(lattices, weights, unary, C, n_iter, want_labels=True, scratch=None):
         log("crf_inference")

@@ -490,3 +490,96 @@ def test_schedules_give_identical_matrices(dev):
     for o in outs[1:]:
         assert all(torch.equal(a, b) for a, b in zip(outs[0], o))
     assert int(outs[0][1].sum()) == sum(int(((g >= 0) & (g < c["n_class"])).sum()) for g in c["gts"])
+
+
+# ------------------------------------------------------------------------------------------------ ragged class counts / buckets
+def _ragged_case(dev, counts, H, W, P=21, n_class=21):
+    from pnp_ovss_b200 import synthetic as synth
+    items = []
+    for b, C in enumerate(counts):
+        items.append(dict(maps=synth.saliency_maps(100 + b, C, P).unsqueeze(0).to(dev),
+                          guide=torch.from_numpy(synth.guide_image(200 + b, H, W)[None]).to(dev),
+                          gt=torch.from_numpy(synth.gt_labels(300 + b, H, W, n_class)[None]).to(dev),
+                          lut=torch.arange(1, C + 2, dtype=torch.int32, device=dev)[None] % n_class))
+    return items
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,rescale", [("blur+crf", True), ("blur+crf", False), ("blur", True)])
+def test_padded_class_counts_equal_per_image_runs(dev, ops, mode, rescale):
+    """Images with 1, 2 or 3 classes (+ background: 2-4 channels, all padding to Cp = 4) in ONE launch group with per-image class
+    counts (pnp_lowrank_blur_unary_padded + a CRF over all Cp channels, the dead ones at unary +inf) against one run per image with
+    its exact channel count: the unary of every real channel, the label maps and the confusion matrix are identical bit for bit,
+    including Scale_0_1's one-class quirk (DRV:1079-1080), which is per image."""
+    from pnp_ovss_b200 import pipeline
+    counts, H, W, n = [1, 2, 3, 1, 3, 2], 96, 80, 21
+    items = _ragged_case(dev, counts, H, W, n_class=n)
+    common = dict(threshold=0.15, rescale=rescale, with_background=True, mode=mode, n_class=n, return_labels=True)
+    hist_each = torch.zeros((n, n), dtype=torch.int64, device=dev)
+    preds = [pipeline.postprocess_batch(it["maps"], it["guide"], it["gt"], it["lut"], hist_each, **common) for it in items]
+    Cmax = max(counts)
+    maps = torch.zeros((len(counts), Cmax, 21, 21), device=dev)
+    lut = torch.zeros((len(counts), 4), dtype=torch.int32, device=dev)
+    for b, it in enumerate(items):
+        maps[b, :counts[b]] = it["maps"][0]
+        maps[b, counts[b]:] = float("nan")                      # whatever sits in the padding must not matter
+        lut[b, :counts[b] + 1] = it["lut"][0]
+    hist_pad = torch.zeros((n, n), dtype=torch.int64, device=dev)
+    pred = pipeline.postprocess_batch(maps, torch.cat([it["guide"] for it in items]), torch.cat([it["gt"] for it in items]), lut, hist_pad,
+                                      n_classes=torch.tensor(counts, dtype=torch.int32, device=dev), **common)
+    assert torch.equal(hist_pad, hist_each) and int(hist_pad.sum()) > 0
+    for b in range(len(counts)):
+        assert torch.equal(pred[b], preds[b][0])
+    # kernel level: unary of the real channels identical, dead channels +inf, maps of dead channels -inf
+    out = ops.lowrank_blur_unary(maps, H, W, 0.15, rescale, True, pipeline.BLUR_SCALE * max(H, W), unary=True, maps=True,
+                                 n_classes=torch.tensor(counts, dtype=torch.int32, device=dev))
+    for b, it in enumerate(items):
+        ref = ops.lowrank_blur_unary(it["maps"], H, W, 0.15, rescale, True, pipeline.BLUR_SCALE * max(H, W), unary=True, maps=True)
+        Cc = counts[b] + 1
+        assert torch.equal(out["unary"][b, :, :Cc].isnan(), ref["unary"][0, :, :Cc].isnan())
+        assert torch.equal(out["unary"][b, :, :Cc].nan_to_num(7.0), ref["unary"][0, :, :Cc].nan_to_num(7.0))
+        assert bool((out["unary"][b, :, Cc:] == float("inf")).all())
+        assert torch.equal(out["maps"][b, :Cc].nan_to_num(7.0), ref["maps"][0].nan_to_num(7.0))
+        if Cc < Cmax + 1:
+            assert bool((out["maps"][b, Cc:] == float("-inf")).all())
+
+
+@pytest.mark.gpu
+def test_ragged_batch_through_bucket_streams_equals_single_stream(dev):
+    """batch_confusion over a batch of several ground-truth sizes and class counts: buckets keyed by (Cp, background, H, W), spread over
+    BUCKET_STREAMS CUDA streams with the lattice builds overlapped, give exactly the matrices of the exact-count buckets on one stream."""
+    import synth
+    from pnp_ovss_b200 import pipeline
+    tok = synth.SyntheticWordPieceTokenizer()
+    names = ["aeroplane", "bicycle", "bird", "boat", "motorbike", "television"]
+    B, S, n = 10, 96, 21
+    shapes = [(64, 80), (64, 80), (80, 64), (64, 80), (72, 72), (80, 64), (64, 80), (72, 72), (64, 80), (80, 64)]
+    class_lists = [names[:1 + (b * 7) % 4] for b in range(B)]
+    caps = ["A picture of " + " ".join(c) for c in class_lists]
+    tokens = tok(caps, padding="max_length", max_length=500)
+    T = max(len(tok.encode(c)) for c in caps)
+    P = S // 16
+    fn = synth.SynthGradcamFn(3, B, T, P)
+    rows = tokens.attention_mask[:, 1:T].float()
+    gts = [synth.gt_labels(10 + b, *shapes[b], n) for b in range(B)]
+    guides = [synth.guide_image(20 + b, *shapes[b]) for b in range(B)]
+    ids = [[1 + names.index(c) for c in cl] for cl in class_lists]
+
+    def run():
+        fn.calls = 0                                   # the stand-in model counts its passes
+        imgs = torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(0)).to(dev)
+        return pipeline.batch_confusion(lambda x: fn(x.cpu(), rows).to(dev), imgs, tokens.input_ids.tolist(), tok.decode, class_lists, ids, gts, guides,
+                                        drop_iter=2, patch_num=P, threshold=0.15, data_type="voc", mode="blur+crf", n_class=n)
+
+    h0, hall, _ = run()
+    torch.cuda.synchronize()
+    old = (pipeline.PAD_CLASSES_IN_BUCKETS, pipeline.BUCKET_STREAMS)
+    pipeline.PAD_CLASSES_IN_BUCKETS, pipeline.BUCKET_STREAMS = False, 1
+    try:
+        h0_ref, hall_ref, _ = run()
+    finally:
+        pipeline.PAD_CLASSES_IN_BUCKETS, pipeline.BUCKET_STREAMS = old
+    torch.cuda.synchronize()
+    valid = sum(int(((g >= 0) & (g < n)).sum()) for g in gts)
+    assert int(h0.sum()) == valid == int(hall.sum())
+    assert torch.equal(h0, h0_ref) and torch.equal(hall, hall_ref)

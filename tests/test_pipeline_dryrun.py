@@ -70,10 +70,25 @@ def test_ragged_batch_is_bucketed_and_segment_tables_are_cached(pipe):
     kw = dict(drop_iter=2, patch_num=b["P"], threshold=0.15, data_type="voc", mode="blur+crf", n_class=21, overlap=False)
     h0, hall, _ = pipeline.batch_confusion(*args, **kw)
     assert int(h0.sum()) == b["valid"] == int(hall.sum())
-    n_buckets = len({len(c) for c in b["class_lists"]})
-    assert stub.calls.count("crf_inference") == 2 * n_buckets
-    with pytest.raises(pipeline.PnpError):            # label maps of a ragged batch have no single shape
-        pipeline.batch_confusion(*args, labels_out={}, **kw)
+    # class counts that pad to the same CRF channel count share a bucket (the fused (d) group takes them per image) ...
+    from pnp_ovss_b200 import host
+    keys = {((len(c) + int(host.add_background_rule("voc", len(c))) + 3) // 4 * 4, tuple(g.shape)) for c, g in zip(b["class_lists"], b["gts"])}
+    assert stub.calls.count("crf_inference") == 2 * len(keys) < 2 * len({len(c) for c in b["class_lists"]})
+    # ... and with that switched off every class count is a bucket of its own, with the same matrices
+    stub.calls.clear()
+    pipeline.PAD_CLASSES_IN_BUCKETS = False
+    try:
+        h0_exact, hall_exact, _ = pipeline.batch_confusion(*args, **kw)
+    finally:
+        pipeline.PAD_CLASSES_IN_BUCKETS = True
+    assert stub.calls.count("crf_inference") == 2 * len({(len(c), tuple(g.shape)) for c, g in zip(b["class_lists"], b["gts"])})
+    assert int(h0_exact.sum()) == b["valid"] == int(hall_exact.sum())
+    pipeline.PAD_CLASSES_IN_BUCKETS = False
+    try:
+        with pytest.raises(pipeline.PnpError):        # label maps of a batch that falls into several buckets have no single shape
+            pipeline.batch_confusion(*args, labels_out={}, **kw)
+    finally:
+        pipeline.PAD_CLASSES_IN_BUCKETS = True
     seg_a = pipeline.segment_tensors(b["tokens"].input_ids.tolist(), b["tok"].decode, b["class_lists"], torch.device("cpu"))
     seg_b = pipeline.segment_tensors(b["tokens"].input_ids.tolist(), b["tok"].decode, b["class_lists"], torch.device("cpu"))
     assert seg_a is seg_b and isinstance(seg_a[3], int)                     # same captions: nothing is rebuilt or uploaded
