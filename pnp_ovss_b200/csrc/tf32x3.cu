@@ -49,42 +49,53 @@ struct Split3<false> {
     }
 };
 
-__device__ __forceinline__ void split_half(float x, float hi_scale, __half &hs, __half &l, __half &h, bool &bad) {
-    h = __float2half_rn(x);
-    const float hf = __half2float(h);
-    l = __float2half_rn((x - hf) * 2048.0f);          // x - hf is exact in fp32; |(x - hf) * 2^11| <= |x| / 2
-    hs = __float2half_rn(hf * hi_scale);              // a power of two: exact unless it overflows
-    bad = bad || !(fabsf(hf * hi_scale) <= 65504.0f); // also catches NaN / inf inputs
+// (x0, x1) -> packed (h, l) pairs: h = fp16(x), l = fp16((x - h) 2^11); x - h is exact in fp32 and |(x - h) 2^11| <= |x| / 2.
+// Packed cvt.rn.f16x2.f32 conversions: one instruction per pair.
+__device__ __forceinline__ void split_half2(float x0, float x1, __half2 &h, __half2 &l) {
+    h = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(h);
+    l = __floats2half2_rn((x0 - hf.x) * 2048.0f, (x1 - hf.y) * 2048.0f);
+}
+// either half of a packed pair is inf or NaN (exponent field all ones): 0x7C00 + 0x0400 carries into the half's sign bit
+__device__ __forceinline__ bool half2_nonfinite(__half2 v) {
+    const unsigned u = *reinterpret_cast<const unsigned *>(&v);
+    return (((u & 0x7C007C00u) + 0x04000400u) & 0x80008000u) != 0u;
 }
 
 template <>
 struct Split3<true> {
     typedef __half out_t;
     static __device__ __forceinline__ void store(__half *__restrict__ row_out, int K, int k, float4 v, float hi_scale, int *flag) {
-        __half hs[4], l[4], h[4];
-        bool bad = false;
-        split_half(v.x, hi_scale, hs[0], l[0], h[0], bad);
-        split_half(v.y, hi_scale, hs[1], l[1], h[1], bad);
-        split_half(v.z, hi_scale, hs[2], l[2], h[2], bad);
-        split_half(v.w, hi_scale, hs[3], l[3], h[3], bad);
-        *reinterpret_cast<uint2 *>(row_out + k) = *reinterpret_cast<const uint2 *>(hs);
-        *reinterpret_cast<uint2 *>(row_out + K + k) = *reinterpret_cast<const uint2 *>(l);
-        *reinterpret_cast<uint2 *>(row_out + 2 * K + k) = *reinterpret_cast<const uint2 *>(h);
+        __half2 h01, h23, l01, l23;
+        split_half2(v.x, v.y, h01, l01);
+        split_half2(v.z, v.w, h23, l23);
+        // h * 2^a in half arithmetic: exact (a power of two) unless it overflows, which -- like an inf / NaN input -- raises the flag
+        __half2 s01 = h01, s23 = h23;
+        if (hi_scale != 1.0f) {
+            const __half2 sc = __float2half2_rn(hi_scale);
+            s01 = __hmul2(h01, sc);
+            s23 = __hmul2(h23, sc);
+        }
+        const bool bad = half2_nonfinite(s01) || half2_nonfinite(s23);
+        *reinterpret_cast<uint2 *>(row_out + k) = make_uint2(*reinterpret_cast<unsigned *>(&s01), *reinterpret_cast<unsigned *>(&s23));
+        *reinterpret_cast<uint2 *>(row_out + K + k) = make_uint2(*reinterpret_cast<unsigned *>(&l01), *reinterpret_cast<unsigned *>(&l23));
+        *reinterpret_cast<uint2 *>(row_out + 2 * K + k) = make_uint2(*reinterpret_cast<unsigned *>(&h01), *reinterpret_cast<unsigned *>(&h23));
         if (bad && flag) *flag = 1;
     }
 };
 
+// Rows are walked by CTAs (grid-stride), the float4 pieces of a row by the CTA's threads: no division per item.
 template <bool kHalf>
 __global__ void __launch_bounds__(256) split3_kernel(const float *__restrict__ x, typename Split3<kHalf>::out_t *__restrict__ out,
                                                      long long M, int K, float in_scale, float hi_scale, int *__restrict__ flag) {
-    const int kq = K >> 2;
-    const long long total = M * kq;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long m = i / kq;
-        const int k = (int)(i - m * kq) * 4;
-        float4 v = ldg_stream4(x + m * K + k);
-        v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
-        Split3<kHalf>::store(out + m * 3 * K, K, k, v, hi_scale, flag);
+    for (long long m = blockIdx.x; m < M; m += gridDim.x) {
+        const float *xr = x + m * K;
+        typename Split3<kHalf>::out_t *orow = out + m * 3 * K;
+        for (int k = threadIdx.x * 4; k < K; k += blockDim.x * 4) {
+            float4 v = ldg_stream4(xr + k);
+            v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
+            Split3<kHalf>::store(orow, K, k, v, hi_scale, flag);
+        }
     }
 }
 
@@ -94,18 +105,18 @@ template <bool kHalf>
 __global__ void __launch_bounds__(256) gelu_split3_kernel(const float *__restrict__ x, const float *__restrict__ bias,
                                                           typename Split3<kHalf>::out_t *__restrict__ out, long long M, int K,
                                                           float in_scale, float hi_scale, int *__restrict__ flag) {
-    const int kq = K >> 2;
-    const long long total = M * kq;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long m = i / kq;
-        const int k = (int)(i - m * kq) * 4;
-        float4 v = ldg_stream4(x + m * K + k);
-        v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
-        if (bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + k));
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    for (long long m = blockIdx.x; m < M; m += gridDim.x) {
+        const float *xr = x + m * K;
+        typename Split3<kHalf>::out_t *orow = out + m * 3 * K;
+        for (int k = threadIdx.x * 4; k < K; k += blockDim.x * 4) {
+            float4 v = ldg_stream4(xr + k);
+            v.x *= in_scale; v.y *= in_scale; v.z *= in_scale; v.w *= in_scale;
+            if (bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + k));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            Split3<kHalf>::store(orow, K, k, make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w)), hi_scale, flag);
         }
-        Split3<kHalf>::store(out + m * 3 * K, K, k, make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w)), hi_scale, flag);
     }
 }
 
@@ -187,8 +198,7 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 namespace {
 template <bool kHalf>
 int run_split3(const float *x, void *out3, long long M, int K, float in_scale, float hi_scale, int *flag, cudaStream_t st) {
-    const long long total = M * (K / 4);
-    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(M, (long long)kNumSMs * 16));   // CTAs walk rows
     typedef typename Split3<kHalf>::out_t out_t;
     PNP_LAUNCH(kTf32Split, st, (split3_kernel<kHalf><<<grid, 256, 0, st>>>(x, reinterpret_cast<out_t *>(out3), M, K, in_scale, hi_scale, flag)));
     return launch_status();
@@ -196,8 +206,7 @@ int run_split3(const float *x, void *out3, long long M, int K, float in_scale, f
 template <bool kHalf>
 int run_gelu_split3(const float *x, const float *bias, void *out3, long long M, int K, float in_scale, float hi_scale, int *flag,
                     cudaStream_t st) {
-    const long long total = M * (K / 4);
-    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(M, (long long)kNumSMs * 16));   // CTAs walk rows
     typedef typename Split3<kHalf>::out_t out_t;
     PNP_LAUNCH(kGeluSplit, st, (gelu_split3_kernel<kHalf><<<grid, 256, 0, st>>>(x, bias, reinterpret_cast<out_t *>(out3), M, K, in_scale, hi_scale, flag)));
     return launch_status();
