@@ -218,14 +218,20 @@ def algorithmic_bytes(kernel, w, stats, T, gemm="3xfp16"):
     N, K = G * G, P * P + 1
     Ms, Mb = stats.get("M_s", 0), stats.get("M_b", 0)
     L = P * P + 1                      # ViT tokens per image
+    # blurred modes run the fused low-rank (d) group: the direct separable blur then sees ONE map per image (the background
+    # indicator), and only when the configuration has a background channel
+    from pnp_ovss_b200 import pipeline as _pl
+    lowrank = _pl.USE_LOWRANK_BLUR and P <= 32 and "blur" in (w.get("mode") or "")
+    blur_maps = (1 if Cc > C else 0) if lowrank else Cc
+    fused_pairs = (Cc + 3) // 4 * 4 <= 112   # crf.cu: two lattice-blur axes per launch up to 448-byte rows
     return {
         "softmax_fwd": 8 * B * 12 * T * K,
         "softmax_bwd_gradcam": 8 * B * (T - 1) * K + 4 * B * (T - 1) * (K - 1),
         "token_merge": 4 * B * (T - 1) * P * P + 4 * B * C * P * P,
         "salience_dropout_round": 4 * B * (T - 1) * P * P * 3 + B * 10 * 3 * 256 * 4,
         "upsample_write": 4 * B * C * P * P + 4 * B * Cc * N,
-        "blur_vertical": 8 * B * Cc * N,
-        "blur_horizontal": 8 * B * Cc * N,
+        "blur_vertical": 8 * B * blur_maps * N or None,
+        "blur_horizontal": 8 * B * blur_maps * N or None,
         "crf_unary": 8 * B * Cc * N,
         # SURVEY 8(d) prices the whole (d) group at ONE write of the blurred maps: the fused low-rank kernel reads the PxP grids
         # and writes the unary (pixel-major; the padding channels count in neither figure)
@@ -235,9 +241,9 @@ def algorithmic_bytes(kernel, w, stats, T, gemm="3xfp16"):
         "crf_splat_bilateral": 4 * Cc * (B * N + Mb) + 8 * 6 * B * N,
         # "2 per blur pass" = one read + one write of the lattice values per axis pass, (d+1) passes.  A fused launch
         # covers two axis passes; the figure is per launch and bench.py also reports the kernel against its REAL traffic.
-        "crf_blur_axis_bilateral": (2 if (Cc + 3) // 4 * 4 <= 112 else 1) * (8 * Cc + 8) * Mb,   # pairs are fused up to 448-byte rows
+        "crf_blur_axis_bilateral": (2 if fused_pairs else 1) * (8 * Cc + 8) * Mb,
         "crf_splat_spatial": 4 * Cc * B * (N + Ms) + 8 * 3 * N,
-        "crf_blur_axis_spatial": 1.5 * (8 * Cc + 8) * Ms * B,  # 3 axes in 2 launches (one fused pair + one single)
+        "crf_blur_axis_spatial": (1.5 if fused_pairs else 1.0) * (8 * Cc + 8) * Ms * B,  # fused: 3 axes in 2 launches (a pair + a single)
         "crf_meanfield_update": 4 * Cc * B * (2 * N) + 4 * Cc * (B * Ms + Mb) + 8 * 9 * B * N,
         "confusion": 12 * B * N,
         "argmax_channels": 4 * Cc * B * N + 4 * B * N,

@@ -276,8 +276,9 @@ int pnp_layernorm_fp16_split3(const float *x, const float *residual, float resid
                               int *overflow_flag, long long M, int K, pnp_stream_t stream);
 
 /* Encoder self-attention softmax(Q K^T * softmax_scale) V (VIT:93-119) at fp32-grade accuracy on the fp16 tensor cores: every
- * operand split as above, each product as three fp16 mma with fp32 accumulation (main term and corrections apart), online
- * softmax in fp32; nothing of size L x L touches HBM.  qkv [B,L,3,H,D] fp32 exactly as the fused qkv GEMM leaves it (each value
+ * operand split as above, each product as three fp16 products with fp32 accumulation (main term and corrections apart), online
+ * softmax in fp32; nothing of size L x L touches HBM.  The main kernel issues tcgen05.mma with its accumulators in tensor memory
+ * (csrc/attention_tc5.cu); the environment variable PNP_ATT_TCGEN05=0 (read per call) selects the mma.sync kernel instead.  qkv [B,L,3,H,D] fp32 exactly as the fused qkv GEMM leaves it (each value
  * times 1/in_scale, in_scale a power of two; 1 for a plain projection); out [B,L,H*D] fp32, unscaled.  D must be 64. */
 size_t pnp_attention_fp16x3_workspace_bytes(int B, int L, int H, int D);
 /* out and / or out3 (at least one): out3 [B*L, 3*H*D] fp16 is the [h * out3_hi_scale | l | h] operand split of the output
