@@ -77,6 +77,10 @@ def get_args_parser():
     parser.add_argument("--checkpoint", default=None, type=str, help="LAVIS BlipITM checkpoint (model_large_retrieval_flickr.pth)")
     parser.add_argument("--coco_annotation_file", default=None, type=str, help="instances_val2017.json (COCO category table)")
     parser.add_argument("--max_images", default=0, type=int, help="real data: evaluate only the first N images (0 = all)")
+    parser.add_argument("--gemm_precision", default="3xfp16", choices=["fp32", "3xtf32", "3xfp16"],
+                        help="how the model's dense contractions run: torch's native fp32 GEMMs, or fp32-grade error-compensated "
+                             "products on the TF32 / fp16 tensor cores (the shipped default; DESIGN.md 3b).  A 3xfp16 run whose "
+                             "activations leave fp16's range is repeated in 3xtf32.")
     parser.add_argument("--synthetic_gt_size", default=0, type=int,
                         help="side of the ground-truth / guide images (0 = img_size); the maps are upsampled to it (DRV:435-437)")
     return parser
@@ -104,6 +108,17 @@ def synthetic_shard(args, names, n_class, start, end):
                           classes=[names[c] for c in ids], gt=synthetic.gt_labels(args.synthetic_seed + i, G, G, n_class),
                           guide=synthetic.guide_image(args.synthetic_seed + i, G, G)))
     return items
+
+
+def _fp16_range_exceeded(model, dev, world_size):
+    """True on every rank when any rank's 3xFP16 operand kernels saw an activation outside fp16's range (the device flag is read
+    here, once per run)."""
+    if model.gemm_precision != "3xfp16":
+        return False
+    flag = model.fp16_overflow_flag(dev).clone()
+    if world_size > 1:
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MAX)
+    return bool(int(flag.item()))
 
 
 def main_real(rank, world_size, args, model=None):
@@ -134,6 +149,7 @@ def main_real(rank, world_size, args, model=None):
             model.load_lavis_checkpoint(args.checkpoint)
     model.tokenizer = tok
     model = model.to(dev).requires_grad_(False)
+    model.gemm_precision = getattr(args, "gemm_precision", "3xfp16")
     ids = data.image_ids(args)
     if args.max_images:
         ids = ids[:int(args.max_images)]
@@ -154,6 +170,14 @@ def main_real(rank, world_size, args, model=None):
             hist0 += h0
         if hall is not None:
             hist_all += hall
+    if _fp16_range_exceeded(model, dev, world_size):
+        if rank == 0:
+            print("warning: an activation left fp16's range in a 3xFP16 GEMM operand; repeating the run with --gemm_precision 3xtf32")
+        model.fp16_overflow_flag(dev).zero_()
+        args.gemm_precision = "3xtf32"
+        if world_size > 1:
+            torch.distributed.destroy_process_group()
+        return main_real(rank, world_size, args, model=model)
     pipeline.allreduce_hist(hist0)
     pipeline.allreduce_hist(hist_all)
     result = None
@@ -187,6 +211,7 @@ def main(rank, world_size, args):
     tok = synthetic.SyntheticWordPieceTokenizer()
     torch.manual_seed(4321)
     model = BlipITM(img_size=int(args.img_size), tokenizer=tok).to(dev).eval().requires_grad_(False)
+    model.gemm_precision = getattr(args, "gemm_precision", "3xfp16")
     layer, head = int(args.max_att_block_num) - 1, int(args.prune_att_head)
     start, end = host.shard_range(args.synthetic_images, rank, world_size)
     items = synthetic_shard(args, names, n_class, start, end)
@@ -215,6 +240,13 @@ def main(rank, world_size, args):
         if rank == 0:   # batch_confusion ends with a host read of its error flag, so the batch is complete here
             dt = time.perf_counter() - tic_batch
             print("Time: batch of %d images %.4f seconds (%.2f images/s on this rank)" % (len(batch), dt, len(batch) / dt))
+    if _fp16_range_exceeded(model, dev, world_size):
+        if rank == 0:
+            print("warning: an activation left fp16's range in a 3xFP16 GEMM operand; repeating the run with --gemm_precision 3xtf32")
+        args.gemm_precision = "3xtf32"
+        if world_size > 1:
+            torch.distributed.destroy_process_group()
+        return main(rank, world_size, args)
     pipeline.allreduce_hist(hist0)
     pipeline.allreduce_hist(hist_all)
     result = None
