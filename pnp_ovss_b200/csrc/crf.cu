@@ -677,8 +677,25 @@ static inline int env_mult(const char *name, int dflt) {
     return v > 0 ? v : dflt;
 }
 static inline int mult_blur() { static int m = env_mult("PNP_GRID_MULT_BLUR", 8); return m; }
-static inline int mult_splat() { static int m = env_mult("PNP_GRID_MULT_SPLAT", 64); return m; }
-static inline int mult_update() { static int m = env_mult("PNP_GRID_MULT_UPDATE", 8); return m; }
+// Splat: the wider the rows, the more CTAs.  Measured per CRF pass (10 launches, profiles/time_other_configs.py; grid = 148 SMs x mult
+// CTAs of 256 threads, grid-stride): 21 channels  64: 4.69 ms, 512: 5.26;  59 channels  128: 9.2, 256: 9.3, 512: 9.9;
+// 81 channels @448  64: 24.5, 128: 21.3, 256: 19.6, 512: 20.0;  150 channels  64: 24.0, 128: 21.0, 256: 19.6, 512: 19.3, 1024: 20.4,
+// one chunk per CTA (4096): 23.2.  (ncu at 150 channels, mult 64: 8.6 GB of DRAM reads per launch for 2.4 GB of Q, L2 hit rate 30 %:
+// every CTA of a long grid-stride loop hops through the whole batch.  Handing chunks of consecutive vertices out in order from a
+// global counter to one resident wave was also measured: 21.7 ms at 150 channels -- better than mult 64, worse than mult 256.)
+static inline int mult_splat(int nch) {
+    static int forced = env_mult("PNP_GRID_MULT_SPLAT", 1 << 30);
+    if (forced != (1 << 30)) return forced;
+    return nch <= 8 ? 64 : (nch <= 16 ? 128 : 256);
+}
+// Update: one resident wave for narrow rows; with wide rows more, shorter-lived CTAs hide the gather latency a little better
+// (per CRF pass, mult 8 / 16 / 32 / 64: 21 channels 5.36 / 5.36 / 5.42 / 5.48 ms, 81 channels @448 29.2 / 28.1 / 27.0 / 27.3, 150
+// channels 31.2 / 30.3 / 29.2 / 28.8).
+static inline int mult_update(int nch) {
+    static int forced = env_mult("PNP_GRID_MULT_UPDATE", 1 << 30);
+    if (forced != (1 << 30)) return forced;
+    return nch <= 8 ? 8 : 32;
+}
 static inline int grid_for(long long work_items, int threads, int mult = 16) {
     return (int)std::max<long long>(1, std::min<long long>((work_items + threads - 1) / threads, (long long)kNumSMs * mult));
 }
@@ -715,7 +732,7 @@ static const float *run_splat_blur(const LatticeView &L, const float *x, float *
     const int nch = Cp / 4;
     const int gy = L.shared ? B : 1;
     const int div = L.shared ? std::min(B, 8) : 1;
-    const int gx_splat = std::max(1, grid_for((long long)(L.M + 1) * nch, 256, mult_splat()) / div);
+    const int gx_splat = std::max(1, grid_for((long long)(L.M + 1) * nch, 256, mult_splat(nch)) / div);
     const int gx = std::max(1, grid_for((long long)(L.M + 1) * nch, 256, mult_blur()) / div);
     const int id_splat = L.shared ? kSplatSpatial : kSplatBilateral;
     const int id_blur = L.shared ? kBlurAxisSpatial : kBlurAxisBilateral;
@@ -840,7 +857,7 @@ extern "C" int pnp_crf_inference(const pnp_lattice *const *lattices, const float
     const bool occ3 = (CPL == 4 || CPL == 6) && nch_all >= occ3_min_nch;
     const bool warp_path = CPL > 0 && Wimg > 0 && (long long)Himg * Wimg == N && (long long)B * N < (1ll << 31) / Cp;
     const int grid_w = (int)std::max<long long>(
-        1, std::min<long long>((long long)B * ((Himg + kTile - 1) / kTile) * ((Wimg + kTile - 1) / kTile), (long long)kNumSMs * mult_update()));
+        1, std::min<long long>((long long)B * ((Himg + kTile - 1) / kTile) * ((Wimg + kTile - 1) / kTile), (long long)kNumSMs * mult_update(nch_all)));
     auto launch_warp = [&](auto labels_tag, auto fast_tag) {
         constexpr bool kL = decltype(labels_tag)::value, kF = decltype(fast_tag)::value;
         if (occ3) {
