@@ -89,3 +89,15 @@ def test_two_gpu_run_gives_the_same_matrix_as_one_gpu(tmp_path):
     one = _run_driver(1, str(tmp_path / "w1"), 29611)
     two = _run_driver(2, str(tmp_path / "w2"), 29612)
     assert one.sum() > 0 and np.array_equal(one, two)
+
+
+def test_driver_gemm_precision_flag_defaults_to_the_shipped_mode():
+    """--gemm_precision is the one flag added on top of the reference's parser for the model pass: default 3xfp16 (what bench.py
+    times), fp32 / 3xtf32 selectable."""
+    import argparse
+    from pnp_ovss_b200 import driver
+    p = argparse.ArgumentParser(parents=[driver.get_args_parser()])
+    assert p.parse_args([]).gemm_precision == "3xfp16"
+    assert p.parse_args(["--gemm_precision", "fp32"]).gemm_precision == "fp32"
+    with pytest.raises(SystemExit):
+        p.parse_args(["--gemm_precision", "fp8"])

@@ -93,3 +93,30 @@ def test_ragged_batch_is_bucketed_and_segment_tables_are_cached(pipe):
     seg_b = pipeline.segment_tensors(b["tokens"].input_ids.tolist(), b["tok"].decode, b["class_lists"], torch.device("cpu"))
     assert seg_a is seg_b and isinstance(seg_a[3], int)                     # same captions: nothing is rebuilt or uploaded
     assert seg_a[3] == int((seg_a[0] + seg_a[1]).max())
+
+
+def test_run_on_streams_keeps_order_and_propagates_errors():
+    """pipeline._run_on_streams without streams (CPU): results come back in job order, the first exception is re-raised."""
+    from pnp_ovss_b200 import pipeline
+    assert pipeline._run_on_streams(torch.device("cpu"), [], [lambda i=i: i * i for i in range(7)]) == [i * i for i in range(7)]
+
+    def boom():
+        raise ValueError("job failed")
+
+    with pytest.raises(ValueError):
+        pipeline._run_on_streams(torch.device("cpu"), [], [lambda: 1, boom, lambda: 3])
+
+
+def test_ragged_bucket_keys_pad_class_counts_only_in_blurred_modes(pipe):
+    """Class counts share a bucket only where the fused low-rank (d) group can take them per image (a blurred mode); without blur the
+    exact count stays in the key, and either way every image lands in exactly one bucket (the matrices count every valid pixel once)."""
+    pipeline, stub = pipe
+    b = _batch(6, 3, ragged=True)
+    args = (b["fn"], b["imgs"], b["tokens"].input_ids.tolist(), b["tok"].decode, b["class_lists"], b["ids"], b["gts"], b["guides"])
+    counts = {}
+    for mode in ("blur", "crf", ""):
+        stub.calls.clear()
+        h0, _, _ = pipeline.batch_confusion(*args, drop_iter=1, patch_num=b["P"], threshold=0.15, data_type="voc", mode=mode, n_class=21)
+        assert int(h0.sum()) == b["valid"]
+        counts[mode] = stub.calls.count("confusion_accumulate")
+    assert counts["blur"] == 1 and counts["crf"] == counts[""] == 3
