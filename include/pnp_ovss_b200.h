@@ -12,10 +12,12 @@
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and the call returns immediately;
  *   - return value: PNP_OK (0) or a negative code; no exception crosses the boundary;
  *   - tensors are dense, row-major, fp32 unless stated; shapes are written [outer, ..., inner];
- *   - one host thread per process, one process per GPU (DRV:1439 mp.spawn).  Process-global state is limited to: the
- *     in-situ profiler (pnp_profile_*, off by default), the per-kernel "allow > 48 KB of dynamic shared memory" function
- *     attribute (idempotent), and tuning environment variables read once (PNP_GRID_MULT_*, PNP_BLUR_FUSE*, PNP_UPDATE_*,
- *     PNP_VALUE_PITCH, PNP_SPLAT_ATOMIC, PNP_ATT_VARIANT: experiment switches, unset in production).  No data is cached between calls.
+ *   - one process per GPU (DRV:1439 mp.spawn).  Every entry point except pnp_profile_* may be called from several host threads
+ *     at once, each on its own stream (pipeline.py issues the buckets of a ragged batch that way).  Process-global state is limited
+ *     to: the in-situ profiler (pnp_profile_*, off by default, single-threaded use only), the per-kernel "allow > 48 KB of dynamic
+ *     shared memory" function attribute (granted once per kernel at the device maximum, under a mutex), and tuning environment
+ *     variables (PNP_GRID_MULT_*, PNP_BLUR_FUSE*, PNP_UPDATE_*, PNP_VALUE_PITCH, PNP_SPLAT_ATOMIC, PNP_ATT_VARIANT read once,
+ *     PNP_ATT_TCGEN05 read per call: experiment switches, unset in production).  No data is cached between calls.
  *   - exception to "returns immediately": pnp_lattice_finish synchronises the stream (it reads the vertex count back).
  */
 #ifndef PNP_OVSS_B200_H
