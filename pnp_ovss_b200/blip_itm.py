@@ -154,16 +154,20 @@ class _Linear3(torch.autograd.Function):
     backward: dL/dx = dL/dy W is the same kind of product against the split of W^T.  TF32 keeps fp32's exponent range, so the
     tiny gradients of the trimmed backward (1e-6 and below) lose nothing -- which is why the text side does not use fp16."""
 
+    SINGLE_GEMM = False   # True: all three products in one depth-3K GEMM (one launch per linear instead of two)
+
     @staticmethod
     def forward(ctx, x, w3, wt3, bias):
         ctx.wt3 = wt3
         ctx.x_shape = x.shape
-        y = _mm3(ops.tf32_split3(x.reshape(-1, x.shape[-1]).contiguous()), w3, bias)
+        mm = _mm3_single if _Linear3.SINGLE_GEMM else _mm3
+        y = mm(ops.tf32_split3(x.reshape(-1, x.shape[-1]).contiguous()), w3, bias)
         return y.view(*x.shape[:-1], w3.shape[0])
 
     @staticmethod
     def backward(ctx, gy):
-        gx = _mm3(ops.tf32_split3(gy.reshape(-1, gy.shape[-1]).contiguous()), ctx.wt3)
+        mm = _mm3_single if _Linear3.SINGLE_GEMM else _mm3
+        gx = mm(ops.tf32_split3(gy.reshape(-1, gy.shape[-1]).contiguous()), ctx.wt3)
         return gx.view(ctx.x_shape), None, None, None
 
 
